@@ -1,0 +1,564 @@
+// Memory-bound glue kernels of the per-frame path (K1, K4, K6-K11): coalesced, 16-byte
+// vectorised, warp-shuffle reductions, shared-memory staging where rows are revisited.
+// Every activation tensor is NHWC 16-bit (fp16 default / bf16 option) with a pixel stride so
+// that a kernel can read or write a channel slice of a wider (concat) buffer.
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+#include "host.h"
+#include "common.cuh"
+
+namespace frb {
+
+template <bool kBF16>
+struct H16;
+template <>
+struct H16<false> {
+  static __device__ __forceinline__ float2 up(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+  static __device__ __forceinline__ uint32_t down(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <>
+struct H16<true> {
+  static __device__ __forceinline__ float2 up(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+  }
+  static __device__ __forceinline__ uint32_t down(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+template <bool kBF16>
+__device__ __forceinline__ void unpack8(const uint4& r, float* y) {
+  float2 f;
+  f = H16<kBF16>::up(r.x); y[0] = f.x; y[1] = f.y;
+  f = H16<kBF16>::up(r.y); y[2] = f.x; y[3] = f.y;
+  f = H16<kBF16>::up(r.z); y[4] = f.x; y[5] = f.y;
+  f = H16<kBF16>::up(r.w); y[6] = f.x; y[7] = f.y;
+}
+template <bool kBF16>
+__device__ __forceinline__ uint4 pack8(const float* y) {
+  uint4 o;
+  o.x = H16<kBF16>::down(y[0], y[1]);
+  o.y = H16<kBF16>::down(y[2], y[3]);
+  o.z = H16<kBF16>::down(y[4], y[5]);
+  o.w = H16<kBF16>::down(y[6], y[7]);
+  return o;
+}
+
+static inline int grid_for(long long work, int block, int num_sms, int per_sm = 16) {
+  long long g = (work + block - 1) / block;
+  long long cap = static_cast<long long>(num_sms) * per_sm;
+  return static_cast<int>(std::max(1LL, std::min(g, cap)));
+}
+
+// ------------------------------------------------------------------------------------------ K1
+// u8 HWC -> 16-bit NHWC(8): RetinaFace input is BGR minus (104,117,123), channels 3..7 zero.
+// One thread = 4 pixels: three 32-bit loads (12 B), four 16 B stores.
+template <bool kBF16>
+__global__ void preprocess_kernel(const uint8_t* __restrict__ in, long long npix, int src_is_rgb,
+                                  uint4* __restrict__ out) {
+  const long long nquad = (npix + 3) >> 2;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < nquad;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p0 = q << 2;
+    uint8_t px[12];
+    if (p0 + 4 <= npix) {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(in + p0 * 3);   // p0*3 is a multiple of 12
+      const uint32_t a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+      memcpy(px, &a, 4); memcpy(px + 4, &b, 4); memcpy(px + 8, &c, 4);
+    } else {
+      for (int i = 0; i < 12; ++i) px[i] = (p0 * 3 + i < npix * 3) ? in[p0 * 3 + i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (p0 + i >= npix) break;
+      const float c0 = px[i * 3 + 0], c1 = px[i * 3 + 1], c2 = px[i * 3 + 2];
+      const float bl = (src_is_rgb ? c2 : c0) - 104.f;
+      const float gr = c1 - 117.f;
+      const float rd = (src_is_rgb ? c0 : c2) - 123.f;
+      uint4 o;
+      o.x = H16<kBF16>::down(bl, gr);
+      o.y = H16<kBF16>::down(rd, 0.f);
+      o.z = 0u; o.w = 0u;
+      out[p0 + i] = o;
+    }
+  }
+}
+
+int launch_preprocess(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int out_c, void* d_out,
+                      cudaStream_t st) {
+  if (out_c != 8) return set_err(ctx, FRB_ERR_INVALID, "preprocess: out_c must be 8");
+  if (reinterpret_cast<uintptr_t>(d_frames) & 3) return set_err(ctx, FRB_ERR_INVALID, "preprocess: frames must be 4-byte aligned");
+  const long long npix = static_cast<long long>(B) * H * W;
+  const int grid = grid_for((npix + 3) / 4, 256, ctx->num_sms);
+  if (ctx->use_bf16) preprocess_kernel<true><<<grid, 256, 0, st>>>(d_frames, npix, src_is_rgb, static_cast<uint4*>(d_out));
+  else preprocess_kernel<false><<<grid, 256, 0, st>>>(d_frames, npix, src_is_rgb, static_cast<uint4*>(d_out));
+  ctx->launches++;
+  return check_last(ctx, "preprocess_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// Depthwise 3x3 (pad 1, stride 1|2) + bias + activation, NHWC, 8 channels per thread.
+// w: [9][C] fp32 (tap-major), bias [C] fp32.
+template <bool kBF16>
+__global__ void dwconv3x3_kernel(const uint4* __restrict__ in, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                                 const float* __restrict__ w, const float* __restrict__ bias, int act, float slope,
+                                 uint4* __restrict__ out) {
+  const int cg = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long t = i / cg;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + g * 8 + j);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * stride - 1 + r;
+      if (static_cast<unsigned>(ih) >= static_cast<unsigned>(H)) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * stride - 1 + s;
+        if (static_cast<unsigned>(iw) >= static_cast<unsigned>(W)) continue;
+        const uint4 v = __ldg(in + (static_cast<long long>(b) * H * W + static_cast<long long>(ih) * W + iw) * cg + g);
+        float x[8];
+        unpack8<kBF16>(v, x);
+        const float* wt = w + (r * 3 + s) * C + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], __ldg(wt + j), acc[j]);
+      }
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    } else if (act == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * slope;
+    }
+    out[i] = pack8<kBF16>(acc);
+  }
+}
+
+int launch_dwconv3x3(frb_ctx* ctx, const void* in, int B, int H, int W, int C, int stride, const void* d_w9c,
+                     const float* d_bias, int act, float slope, void* out, cudaStream_t st) {
+  if (C % 8) return set_err(ctx, FRB_ERR_INVALID, "dwconv: C=%d must be a multiple of 8", C);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  const int grid = grid_for(total, 256, ctx->num_sms);
+  if (ctx->use_bf16)
+    dwconv3x3_kernel<true><<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), B, H, W, C, stride, Ho, Wo,
+                                                 static_cast<const float*>(d_w9c), d_bias, act, slope, static_cast<uint4*>(out));
+  else
+    dwconv3x3_kernel<false><<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), B, H, W, C, stride, Ho, Wo,
+                                                  static_cast<const float*>(d_w9c), d_bias, act, slope, static_cast<uint4*>(out));
+  ctx->launches++;
+  return check_last(ctx, "dwconv3x3_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K9
+// 3x3 stride-2 max pool, `pad` in {0,1} (padding never wins: -inf), pixel strides in elements.
+template <bool kBF16>
+__global__ void maxpool3x3s2_kernel(const uint16_t* __restrict__ in, int in_ld, int B, int H, int W, int C, int pad,
+                                    int Ho, int Wo, uint16_t* __restrict__ out, int out_ld) {
+  const int cg = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long t = i / cg;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - pad + r;
+      if (static_cast<unsigned>(ih) >= static_cast<unsigned>(H)) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - pad + s;
+        if (static_cast<unsigned>(iw) >= static_cast<unsigned>(W)) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            in + (static_cast<long long>(b) * H * W + static_cast<long long>(ih) * W + iw) * in_ld + g * 8));
+        float x[8];
+        unpack8<kBF16>(v, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], x[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * Ho * Wo + static_cast<long long>(oh) * Wo + ow) * out_ld +
+                              g * 8) = pack8<kBF16>(m);
+  }
+}
+
+int launch_maxpool3x3s2(frb_ctx* ctx, const void* in, int in_ld, int B, int H, int W, int C, int pad, void* out,
+                        int out_ld, cudaStream_t st) {
+  if (C % 8 || in_ld % 8 || out_ld % 8) return set_err(ctx, FRB_ERR_INVALID, "maxpool: C/in_ld/out_ld must be multiples of 8");
+  const int Ho = (H + 2 * pad - 3) / 2 + 1, Wo = (W + 2 * pad - 3) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  const int grid = grid_for(total, 256, ctx->num_sms);
+  if (ctx->use_bf16)
+    maxpool3x3s2_kernel<true><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(in), in_ld, B, H, W, C, pad, Ho, Wo,
+                                                    static_cast<uint16_t*>(out), out_ld);
+  else
+    maxpool3x3s2_kernel<false><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(in), in_ld, B, H, W, C, pad, Ho, Wo,
+                                                     static_cast<uint16_t*>(out), out_ld);
+  ctx->launches++;
+  return check_last(ctx, "maxpool3x3s2_kernel");
+}
+
+// ----------------------------------------------------------------------------------------- K10
+// Global average pool over HW positions: [B,HW,C] -> [B,C] 16-bit (feeds last_linear as a 1x1 conv).
+template <bool kBF16>
+__global__ void avgpool_kernel(const uint4* __restrict__ in, int B, int HW, int C, uint4* __restrict__ out) {
+  const int cg = C >> 3;
+  const long long total = static_cast<long long>(B) * cg;
+  const float inv = 1.f / static_cast<float>(HW);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    const long long b = i / cg;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < HW; ++p) {
+      float x[8];
+      unpack8<kBF16>(__ldg(in + (b * HW + p) * cg + g), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += x[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    out[i] = pack8<kBF16>(acc);
+  }
+}
+
+int launch_avgpool(frb_ctx* ctx, const void* in, int B, int HW, int C, void* out, cudaStream_t st) {
+  if (C % 8) return set_err(ctx, FRB_ERR_INVALID, "avgpool: C must be a multiple of 8");
+  const int grid = grid_for(static_cast<long long>(B) * (C / 8), 128, ctx->num_sms);
+  if (ctx->use_bf16) avgpool_kernel<true><<<grid, 128, 0, st>>>(static_cast<const uint4*>(in), B, HW, C, static_cast<uint4*>(out));
+  else avgpool_kernel<false><<<grid, 128, 0, st>>>(static_cast<const uint4*>(in), B, HW, C, static_cast<uint4*>(out));
+  ctx->launches++;
+  return check_last(ctx, "avgpool_kernel");
+}
+
+// ----------------------------------------------------------------------------------------- K11
+// Row-wise L2 normalisation, fp32 in place: one warp per row, float4 loads, shuffle reduction.
+__global__ void l2norm_kernel(float* __restrict__ x, int rows, int cols) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    float* row = x + static_cast<size_t>(r) * cols;
+    float ss = 0.f;
+    for (int c = lane * 4; c < cols; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(fmaxf(ss, 1e-30f));
+    for (int c = lane * 4; c < cols; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(row + c);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      *reinterpret_cast<float4*>(row + c) = v;
+    }
+  }
+}
+
+int launch_l2norm(frb_ctx* ctx, float* x, int rows, int cols, cudaStream_t st) {
+  if (cols % 4) return set_err(ctx, FRB_ERR_INVALID, "l2norm: cols must be a multiple of 4");
+  if (rows <= 0) return FRB_OK;
+  const int grid = grid_for(static_cast<long long>(rows) * 32, 256, ctx->num_sms);
+  l2norm_kernel<<<grid, 256, 0, st>>>(x, rows, cols);
+  ctx->launches++;
+  return check_last(ctx, "l2norm_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K6
+// PriorBox decode + 2-class softmax + score filter + per-frame compaction.
+// Priors are analytic: level k has step 8<<k, min sizes {16,32}<<(2k); prior p of a level maps
+// to cell (p/2) and anchor (p&1).  Arithmetic is fp32 with explicit rounding (no FMA
+// contraction) in the order of the numpy oracle so boxes agree to the last ulp of expf.
+struct PriorGeom {
+  int fh[3], fw[3], off[4];
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__global__ void prior_decode_filter_kernel(const float* __restrict__ loc, const float* __restrict__ conf,
+                                           const float* __restrict__ landm, int P, int H, int W, PriorGeom g, float thr,
+                                           int max_cand, float* __restrict__ cand, int32_t* __restrict__ count,
+                                           int32_t* __restrict__ prior_idx) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+  const int p_base = blockIdx.x * blockDim.x;
+  // grid.x covers P in chunks; each warp handles 32 consecutive priors per step (coalesced float2 conf reads)
+  for (int p0 = p_base + (threadIdx.x & ~31); p0 < P; p0 += gridDim.x * blockDim.x) {
+    const int p = p0 + lane;
+    bool keep = false;
+    float score = 0.f;
+    if (p < P) {
+      const float2 c = __ldg(reinterpret_cast<const float2*>(conf) + static_cast<size_t>(b) * P + p);
+      const float m = fmaxf(c.x, c.y);
+      const float e0 = expf(fsub(c.x, m)), e1 = expf(fsub(c.y, m));
+      score = __fdiv_rn(e1, fadd(e0, e1));
+      keep = score > thr;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count + b, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!keep) continue;
+    const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+    if (slot >= max_cand) continue;
+    const int k = p >= g.off[2] ? 2 : (p >= g.off[1] ? 1 : 0);
+    const int q = p - g.off[k];
+    const int cell = q >> 1, a = q & 1;
+    const int i = cell / g.fw[k], j = cell - i * g.fw[k];
+    const float step = static_cast<float>(8 << k);
+    const float ms = static_cast<float>((16 << (2 * k)) << a);
+    const float pcx = __fdiv_rn(fmul(fadd(static_cast<float>(j), 0.5f), step), fW);
+    const float pcy = __fdiv_rn(fmul(fadd(static_cast<float>(i), 0.5f), step), fH);
+    const float pw = __fdiv_rn(ms, fW), ph = __fdiv_rn(ms, fH);
+    const float4 l = __ldg(reinterpret_cast<const float4*>(loc) + static_cast<size_t>(b) * P + p);
+    const float cx = fadd(pcx, fmul(fmul(l.x, 0.1f), pw));
+    const float cy = fadd(pcy, fmul(fmul(l.y, 0.1f), ph));
+    const float bw = fmul(pw, expf(fmul(l.z, 0.2f)));
+    const float bh = fmul(ph, expf(fmul(l.w, 0.2f)));
+    const float x1 = fsub(cx, fmul(bw, 0.5f)), y1 = fsub(cy, fmul(bh, 0.5f));
+    const float x2 = fadd(x1, bw), y2 = fadd(y1, bh);
+    float* o = cand + (static_cast<size_t>(b) * max_cand + slot) * 15;
+    o[0] = fmul(x1, fW); o[1] = fmul(y1, fH); o[2] = fmul(x2, fW); o[3] = fmul(y2, fH);
+    o[4] = score;
+    const float* lm = landm + (static_cast<size_t>(b) * P + p) * 10;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      o[5 + 2 * t] = fmul(fadd(pcx, fmul(fmul(__ldg(lm + 2 * t), 0.1f), pw)), fW);
+      o[6 + 2 * t] = fmul(fadd(pcy, fmul(fmul(__ldg(lm + 2 * t + 1), 0.1f), ph)), fH);
+    }
+    prior_idx[static_cast<size_t>(b) * max_cand + slot] = p;
+  }
+}
+
+int launch_prior_decode_filter(frb_ctx* ctx, const float* d_loc, const float* d_conf, const float* d_landm, int B, int H,
+                               int W, float thr, int max_cand, float* d_cand, int32_t* d_count, int32_t* d_prior_idx,
+                               cudaStream_t st) {
+  if (B <= 0 || B > 65535 || max_cand <= 0) return set_err(ctx, FRB_ERR_INVALID, "prior_decode_filter: bad B/max_cand");
+  PriorGeom g;
+  int off = 0;
+  for (int k = 0; k < 3; ++k) {
+    const int s = 8 << k;
+    g.fh[k] = (H + s - 1) / s;
+    g.fw[k] = (W + s - 1) / s;
+    g.off[k] = off;
+    off += 2 * g.fh[k] * g.fw[k];
+  }
+  g.off[3] = off;
+  const int P = off;
+  FRB_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int32_t) * B, st));
+  const int gx = std::max(1, std::min((P + 255) / 256, std::max(1, ctx->num_sms * 8 / B)));
+  prior_decode_filter_kernel<<<dim3(gx, B), 256, 0, st>>>(d_loc, d_conf, d_landm, P, H, W, g, thr, max_cand, d_cand,
+                                                          d_count, d_prior_idx);
+  ctx->launches++;
+  return check_last(ctx, "prior_decode_filter_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K7
+// One CTA per frame: bitonic sort of (score desc, prior index asc) in shared memory, IoU
+// suppression bitmask (n x n/32 words), then a single-warp sequential scan.  n <= 1024.
+constexpr int kNmsMax = 1024;
+
+__device__ __forceinline__ bool nms_before(float sa, int pa, float sb, int pb) {
+  return sa > sb || (sa == sb && pa < pb);
+}
+
+__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand, const int32_t* __restrict__ count,
+                                                  const int32_t* __restrict__ prior_idx, int max_cand, float iou_thr,
+                                                  int plus_one, int32_t* __restrict__ keep, int32_t* __restrict__ nkeep) {
+  extern __shared__ uint8_t nms_smem[];
+  const int b = blockIdx.x;
+  const int n = min(count[b], max_cand);
+  int np2 = 32;
+  while (np2 < n) np2 <<= 1;
+  float* s_score = reinterpret_cast<float*>(nms_smem);                 // [np2]
+  int* s_prior = reinterpret_cast<int*>(s_score + np2);                // [np2]
+  int* s_idx = s_prior + np2;                                          // [np2]
+  float4* s_box = reinterpret_cast<float4*>(s_idx + np2);              // [np2]
+  float* s_area = reinterpret_cast<float*>(s_box + np2);               // [np2]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_area + np2);        // [np2 * np2/32]
+  const float* cb = cand + static_cast<size_t>(b) * max_cand * 15;
+  const int32_t* pb = prior_idx + static_cast<size_t>(b) * max_cand;
+
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    if (i < n) { s_score[i] = cb[i * 15 + 4]; s_prior[i] = pb[i]; s_idx[i] = i; }
+    else { s_score[i] = -INFINITY; s_prior[i] = 0x7fffffff; s_idx[i] = -1; }
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;   // ascending position = earlier in (score desc) order
+          const bool i_first = nms_before(s_score[i], s_prior[i], s_score[ixj], s_prior[ixj]);
+          if (up != i_first) {
+            const float ts = s_score[i]; s_score[i] = s_score[ixj]; s_score[ixj] = ts;
+            const int tp = s_prior[i]; s_prior[i] = s_prior[ixj]; s_prior[ixj] = tp;
+            const int ti = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const float po = plus_one ? 1.f : 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* c = cb + s_idx[i] * 15;
+    const float4 bx = make_float4(c[0], c[1], c[2], c[3]);
+    s_box[i] = bx;
+    s_area[i] = fmul(fadd(fsub(bx.z, bx.x), po), fadd(fsub(bx.w, bx.y), po));
+  }
+  __syncthreads();
+  const int words = (n + 31) >> 5;
+  for (int t = threadIdx.x; t < n * words; t += blockDim.x) {
+    const int i = t / words, w = t - i * words;
+    const float4 a = s_box[i];
+    const float aa = s_area[i];
+    uint32_t bits = 0;
+    const int j0 = w << 5;
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = j0 + jj;
+      if (j <= i || j >= n) continue;
+      const float4 q = s_box[j];
+      const float iw = fmaxf(0.f, fadd(fsub(fminf(a.z, q.z), fmaxf(a.x, q.x)), po));
+      const float ih = fmaxf(0.f, fadd(fsub(fminf(a.w, q.w), fmaxf(a.y, q.y)), po));
+      const float inter = fmul(iw, ih);
+      const float ovr = __fdiv_rn(inter, fsub(fadd(aa, s_area[j]), inter));
+      if (ovr > iou_thr) bits |= 1u << jj;
+    }
+    s_mask[i * words + w] = bits;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // removed[] lives in registers: lane l owns word l (n <= 1024 -> 32 words)
+    uint32_t removed = 0;
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t rw = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if ((rw >> (i & 31)) & 1u) continue;
+      if (threadIdx.x == 0) keep[static_cast<size_t>(b) * max_cand + nk] = s_idx[i];
+      ++nk;
+      if (static_cast<int>(threadIdx.x) < words) removed |= s_mask[i * words + threadIdx.x];
+    }
+    if (threadIdx.x == 0) nkeep[b] = nk;
+  }
+}
+
+int launch_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
+               float iou_thr, int legacy_plus_one, int32_t* d_keep, int32_t* d_nkeep, cudaStream_t st) {
+  if (max_cand <= 0 || max_cand > kNmsMax)
+    return set_err(ctx, FRB_ERR_INVALID, "nms: max_cand must be in 1..%d", kNmsMax);
+  if (B <= 0) return FRB_OK;
+  int np2 = 32;
+  while (np2 < max_cand) np2 <<= 1;
+  const size_t smem = static_cast<size_t>(np2) * (4 + 4 + 4 + 16 + 4) + static_cast<size_t>(np2) * (np2 / 32) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  nms_kernel<<<B, 256, smem, st>>>(d_cand, d_count, d_prior_idx, max_cand, iou_thr, legacy_plus_one, d_keep, d_nkeep);
+  ctx->launches++;
+  return check_last(ctx, "nms_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K8
+// crop + bilinear resize to 160x160 with cv2.resize(INTER_LINEAR) uint8 fixed-point semantics
+// (11-bit coefficients, (S>>4 * b)>>16 vertical pass, +2 >>2 rounding) + (x-127.5)/128.
+// One thread per output pixel; the four taps come straight from the resident u8 frame.
+constexpr int kFace = 160;
+
+__device__ __forceinline__ void resize_coef(int d, int ssize, int& s0, short& a0, short& a1, bool horizontal) {
+  const double inv_scale = static_cast<double>(kFace) / static_cast<double>(ssize);
+  const double scale = 1.0 / inv_scale;
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s);
+  if (horizontal) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  }
+  s0 = s;
+  // saturate_cast<short>(float) == round-half-even then clamp
+  const int i0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  const int i1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  a0 = static_cast<short>(max(-32768, min(32767, i0)));
+  a1 = static_cast<short>(max(-32768, min(32767, i1)));
+}
+
+template <bool kBF16>
+__global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, int W, const int32_t* __restrict__ boxes,
+                                   uint4* __restrict__ out) {
+  const int f = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= kFace * kFace) return;
+  const int dy = t / kFace, dx = t - dy * kFace;
+  const int32_t* bx = boxes + f * 5;
+  const int fr = bx[0], x0 = bx[1], y0 = bx[2], cw = bx[3], ch = bx[4];
+  int sx, sy;
+  short ax0, ax1, by0, by1;
+  resize_coef(dx, cw, sx, ax0, ax1, true);
+  resize_coef(dy, ch, sy, by0, by1, false);
+  const int sx1 = min(sx + 1, cw - 1);
+  const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
+  const uint8_t* base = frames + static_cast<size_t>(fr) * H * W * 3;
+  const uint8_t* p00 = base + (static_cast<size_t>(y0 + r0) * W + (x0 + sx)) * 3;
+  const uint8_t* p01 = base + (static_cast<size_t>(y0 + r0) * W + (x0 + sx1)) * 3;
+  const uint8_t* p10 = base + (static_cast<size_t>(y0 + r1) * W + (x0 + sx)) * 3;
+  const uint8_t* p11 = base + (static_cast<size_t>(y0 + r1) * W + (x0 + sx1)) * 3;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int S0 = static_cast<int>(__ldg(p00 + c)) * ax0 + static_cast<int>(__ldg(p01 + c)) * ax1;
+    const int S1 = static_cast<int>(__ldg(p10 + c)) * ax0 + static_cast<int>(__ldg(p11 + c)) * ax1;
+    int r = (((by0 * (S0 >> 4)) >> 16) + ((by1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    r = max(0, min(255, r));
+    v[c] = (static_cast<float>(r) - 127.5f) * (1.f / 128.f);
+  }
+  uint4 o;
+  o.x = H16<kBF16>::down(v[0], v[1]);
+  o.y = H16<kBF16>::down(v[2], 0.f);
+  o.z = 0u; o.w = 0u;
+  out[static_cast<size_t>(f) * kFace * kFace + t] = o;
+}
+
+int launch_crop_resize(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, const int32_t* d_boxes, int F,
+                       int out_c, void* d_out, cudaStream_t st) {
+  if (out_c != 8) return set_err(ctx, FRB_ERR_INVALID, "crop_resize: out_c must be 8");
+  if (F <= 0) return FRB_OK;
+  (void)B;
+  for (int f0 = 0; f0 < F; f0 += 65535) {
+    const int nf = std::min(65535, F - f0);
+    dim3 grid((kFace * kFace + 255) / 256, nf);
+    uint4* o = static_cast<uint4*>(d_out) + static_cast<size_t>(f0) * kFace * kFace;
+    if (ctx->use_bf16) crop_resize_kernel<true><<<grid, 256, 0, st>>>(d_frames, H, W, d_boxes + f0 * 5, o);
+    else crop_resize_kernel<false><<<grid, 256, 0, st>>>(d_frames, H, W, d_boxes + f0 * 5, o);
+    ctx->launches++;
+  }
+  return check_last(ctx, "crop_resize_kernel");
+}
+
+}  // namespace frb

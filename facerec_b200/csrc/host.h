@@ -1,0 +1,128 @@
+// Internal host-side declarations shared by the translation units of libfacerec_b200.so.
+// Nothing here crosses the C ABI; see include/facerec_b200.h for the exported surface.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/facerec_b200.h"
+
+namespace frb {
+
+struct Net;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace frb
+
+struct frb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int use_bf16 = 0;            // 0: fp16 activations/weights (default), 1: bf16
+  int bn_cap = 128;            // largest conv tile N the planner may pick
+  int force_gather = 0;        // debugging: never use the TMA A path
+  std::string err;
+  int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
+  int* wd_dev = nullptr;
+  frb::EncodeTiledFn encode_tiled = nullptr;
+  std::map<int, frb::Net*> nets;
+  long long launches = 0;      // kernels launched through this context (bench bookkeeping)
+  void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace frb {
+
+int set_err(frb_ctx* ctx, int code, const char* fmt, ...);
+int check_cuda(frb_ctx* ctx, cudaError_t e, const char* what);
+// Maps a failed launch / sync to an error string, appending the pipeline watchdog record if set.
+int check_last(frb_ctx* ctx, const char* what);
+
+#define FRB_CUDA(ctx, expr)                                   \
+  do {                                                        \
+    int _rc = frb::check_cuda((ctx), (expr), #expr);          \
+    if (_rc != 0) return _rc;                                 \
+  } while (0)
+
+// ------------------------------------------------------------------ conv
+struct ConvLayer {
+  int Cin = 0, Cout = 0, kh = 1, kw = 1, sh = 1, sw = 1, ph = 0, pw = 0;
+  int K = 0, K_pad = 0, BN = 0, Cout_pad = 0, n_tiles = 0;
+  void* d_w = nullptr;       // [Cout_pad, K_pad] 16-bit, K-major, K ordered (r, s, c)
+  float* d_bias = nullptr;   // [Cout_pad]
+  float* d_slope = nullptr;  // [Cout_pad] negative slope per output channel (1 linear, 0 relu)
+  CUtensorMap tmB;
+};
+
+struct ConvIO {
+  const void* in = nullptr;  // pre-offset to first input channel
+  int in_ld = 0;
+  int B = 0, H = 0, W = 0;
+  void* out = nullptr;       // pre-offset to first output channel
+  int out_ld = 0;
+  int out_mode = 0;          // ConvOut
+  const void* res = nullptr;
+  int res_ld = 0;
+  int res_mode = 0;          // ConvRes
+  int rH = 0, rW = 0;
+  float* loc = nullptr;
+  float* conf = nullptr;
+  float* landm = nullptr;
+  int P_total = 0, P_off = 0;
+};
+
+inline int conv_out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+// 2D tiled tensor map over a row-major 16-bit matrix [outer, inner], 128-byte swizzle.
+int encode_2d(frb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+              uint32_t box_inner, uint32_t box_outer);
+// Grow-only device scratch owned by the context (slot = independent buffer).
+int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out);
+
+// h_w: [Cout][kh][kw][Cin] fp32 (BN already folded); h_bias: [Cout] or null.
+// h_slope: [Cout] per-channel negative slope or null (= linear everywhere).
+int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bias, const float* h_slope);
+void conv_release(ConvLayer& L);
+int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
+
+// ------------------------------------------------------------------ glue kernels (glue.cu)
+int launch_preprocess(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int out_c, void* d_out,
+                      cudaStream_t);
+int launch_dwconv3x3(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_w9c,
+                     const float* d_bias, int act, float slope, void* out, cudaStream_t);
+int launch_maxpool3x3s2(frb_ctx*, const void* in, int in_ld, int B, int H, int W, int C, int pad, void* out, int out_ld,
+                        cudaStream_t);
+int launch_avgpool(frb_ctx*, const void* in, int B, int HW, int C, void* out, cudaStream_t);
+int launch_l2norm(frb_ctx*, float* x, int rows, int cols, cudaStream_t);
+int launch_prior_decode_filter(frb_ctx*, const float* d_loc, const float* d_conf, const float* d_landm, int B, int H,
+                               int W, float thr, int max_cand, float* d_cand, int32_t* d_count, int32_t* d_prior_idx,
+                               cudaStream_t);
+int launch_nms(frb_ctx*, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
+               float iou_thr, int legacy_plus_one, int32_t* d_keep, int32_t* d_nkeep, cudaStream_t);
+int launch_crop_resize(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, const int32_t* d_boxes, int F,
+                       int out_c, void* d_out, cudaStream_t);
+
+// ------------------------------------------------------------------ distance stage (dist.cu)
+int run_pdist(frb_ctx*, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, cudaStream_t);
+int run_knn_topk(frb_ctx*, const float* d_Q, int Q, const float* d_DB, int M, int D, int k, int32_t* d_idx, float* d_dist,
+                 cudaStream_t);
+int run_knn_vote(frb_ctx*, const int32_t* d_idx, const int32_t* d_label_idx, int Q, int k, int n_classes, float* d_proba,
+                 cudaStream_t);
+int run_segment_mean(frb_ctx*, const float* d_X, const int32_t* d_offsets, int S, int D, float* d_out, cudaStream_t);
+
+// ------------------------------------------------------------------ nets (nets.cu)
+struct WeightBlob;
+Net* build_net(frb_ctx* ctx, int model_id, const void* blob, size_t bytes);
+int net_forward_retina(frb_ctx* ctx, Net* net, const void* d_in, int B, int H, int W, float* d_loc, float* d_conf,
+                       float* d_landm, cudaStream_t stream);
+int net_forward_irv1(frb_ctx* ctx, Net* net, const void* d_in, int F, float* d_emb, cudaStream_t stream);
+void destroy_net(Net* net);
+
+}  // namespace frb

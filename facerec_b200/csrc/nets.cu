@@ -1,0 +1,709 @@
+// Network graphs of the per-frame path, expressed over the K2 conv kernel and the glue kernels:
+//   RetinaFace (MobileNetV1-0.25 or ResNet-50 backbone, FPN, SSH, fused heads)  -> loc / conf / landm
+//   FaceNet InceptionResnetV1                                                   -> 512-d unit embeddings
+//
+// Weights arrive as one fp32 blob (BatchNorm folded on the host, see facerec_b200/weights.py).  At
+// load time sibling convolutions that read the same tensor are assembled into ONE wider layer
+// (SSH c3+c5_1 and c5+c7_2, the three head convs, the parallel 1x1 branch convs of the
+// Inception blocks, a block-diagonal pair of 3x3 convs in Block35) and concat buffers are laid out
+// so that every producer writes, and every consumer reads, one contiguous channel range: concat,
+// channel reorder, residual scale and the final ReLU of SSH cost nothing at run time.
+//
+// A forward for a given (batch, H, W) is planned once: tensors get arena offsets by liveness
+// (greedy interval placement), ops are replayed on the caller's stream.
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <stdexcept>
+#include <tuple>
+
+#include "host.h"
+#include "conv_igemm.cuh"
+
+namespace frb {
+
+// ------------------------------------------------------------------------------------ blob
+struct BlobEntry {
+  std::vector<int> dims;
+  const float* data = nullptr;
+  size_t count = 0;
+};
+struct WeightBlob {
+  std::map<std::string, BlobEntry> entries;
+  const BlobEntry& get(const std::string& name) const {
+    auto it = entries.find(name);
+    if (it == entries.end()) throw std::runtime_error("weight blob has no entry '" + name + "'");
+    return it->second;
+  }
+};
+
+static void parse_blob(const void* blob, size_t bytes, WeightBlob& out) {
+  const uint8_t* p = static_cast<const uint8_t*>(blob);
+  if (bytes < 20 || memcmp(p, "FRBW", 4) != 0) throw std::runtime_error("weight blob: bad magic (expected FRBW)");
+  uint32_t version, n;
+  uint64_t data_off;
+  memcpy(&version, p + 4, 4);
+  memcpy(&n, p + 8, 4);
+  memcpy(&data_off, p + 12, 8);
+  if (version != 1) throw std::runtime_error("weight blob: unsupported version");
+  if (data_off > bytes || (data_off & 3)) throw std::runtime_error("weight blob: bad data offset");
+  size_t pos = 20;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (pos + 2 > data_off) throw std::runtime_error("weight blob: truncated entry table");
+    uint16_t nl;
+    memcpy(&nl, p + pos, 2);
+    pos += 2;
+    if (pos + nl + 4 > data_off) throw std::runtime_error("weight blob: truncated entry table");
+    std::string name(reinterpret_cast<const char*>(p + pos), nl);
+    pos += nl;
+    uint32_t nd;
+    memcpy(&nd, p + pos, 4);
+    pos += 4;
+    if (nd > 8 || pos + 4 * nd + 8 > data_off) throw std::runtime_error("weight blob: truncated entry table");
+    BlobEntry e;
+    e.count = 1;
+    for (uint32_t d = 0; d < nd; ++d) {
+      uint32_t v;
+      memcpy(&v, p + pos, 4);
+      pos += 4;
+      e.dims.push_back(static_cast<int>(v));
+      e.count *= v;
+    }
+    uint64_t eo;
+    memcpy(&eo, p + pos, 8);
+    pos += 8;
+    if (data_off + (eo + e.count) * 4 > bytes) throw std::runtime_error("weight blob: entry '" + name + "' out of range");
+    e.data = reinterpret_cast<const float*>(p + data_off) + eo;
+    out.entries[name] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------ layer assembly
+struct HostConv {
+  int Cout = 0, kh = 1, kw = 1, Cin = 0;
+  std::vector<float> w, b, slope;
+  HostConv(int co, int kh_, int kw_, int ci) : Cout(co), kh(kh_), kw(kw_), Cin(ci) {
+    w.assign(static_cast<size_t>(co) * kh_ * kw_ * ci, 0.f);
+    b.assign(co, 0.f);
+    slope.assign(co, 1.f);
+  }
+};
+
+// Copies source conv `name` (all of it, or the input-channel range [src_ci0, src_ci0+src_cin)) into
+// dst at output-channel offset dst_co / input-channel offset dst_ci, scaling weights and bias.
+static void place(HostConv& dst, const WeightBlob& blob, const std::string& name, int dst_co, int dst_ci, float slope,
+                  float scale = 1.f, int src_ci0 = 0, int src_cin = -1, bool with_bias = true) {
+  const BlobEntry& w = blob.get(name + ".w");
+  const BlobEntry& b = blob.get(name + ".b");
+  if (w.dims.size() != 4) throw std::runtime_error("'" + name + ".w' must be 4-d [Cout,kh,kw,Cin]");
+  const int co = w.dims[0], kh = w.dims[1], kw = w.dims[2], ci = w.dims[3];
+  if (src_cin < 0) src_cin = ci - src_ci0;
+  if (kh != dst.kh || kw != dst.kw || dst_co + co > dst.Cout || dst_ci + src_cin > dst.Cin || src_ci0 + src_cin > ci ||
+      static_cast<int>(b.count) != co)
+    throw std::runtime_error("layer assembly: '" + name + "' does not fit its slot");
+  for (int o = 0; o < co; ++o) {
+    for (int t = 0; t < kh * kw; ++t)
+      for (int c = 0; c < src_cin; ++c)
+        dst.w[(static_cast<size_t>(dst_co + o) * kh * kw + t) * dst.Cin + dst_ci + c] =
+            w.data[(static_cast<size_t>(o) * kh * kw + t) * ci + src_ci0 + c] * scale;
+    if (with_bias) dst.b[dst_co + o] = b.data[o] * scale;
+    dst.slope[dst_co + o] = slope;
+  }
+}
+
+struct DwLayer {
+  int C = 0, stride = 1;
+  float slope = 0.f;
+  float* d_w = nullptr;   // [9][C]
+  float* d_bias = nullptr;
+};
+
+// ------------------------------------------------------------------------------------ plan
+struct TensorInfo {
+  int H = 0, W = 0, C = 0, elem = 2, ext = 0;   // ext: 0 arena, 1 network input, 2 embedding output
+  size_t bytes = 0, off = 0;
+  int first = -1, last = -1;
+};
+struct View {
+  int t = -1, coff = 0;
+};
+enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4 };
+struct Op {
+  int kind = 0, layer = -1;
+  View in, out, res;
+  int res_mode = 0, out_mode = 0, pad = 0, C = 0, P_off = 0;
+};
+struct Plan {
+  int B = 0, H = 0, W = 0, P_total = 0;
+  std::vector<TensorInfo> tensors;
+  std::vector<Op> ops;
+  size_t arena_bytes = 0;
+};
+
+struct Net {
+  int model = 0;
+  frb_ctx* ctx = nullptr;
+  std::vector<ConvLayer> convs;
+  std::map<std::string, int> conv_idx;
+  std::vector<DwLayer> dws;
+  std::map<std::tuple<int, int, int>, Plan> plans;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+};
+
+static void add_conv(Net* net, const std::string& name, const HostConv& h, int sh, int sw, int ph, int pw) {
+  ConvLayer L;
+  L.Cin = h.Cin; L.Cout = h.Cout; L.kh = h.kh; L.kw = h.kw; L.sh = sh; L.sw = sw; L.ph = ph; L.pw = pw;
+  if (conv_prepare(net->ctx, L, h.w.data(), h.b.data(), h.slope.data()) != FRB_OK) {
+    conv_release(L);
+    throw std::runtime_error("conv_prepare('" + name + "'): " + net->ctx->err);
+  }
+  net->conv_idx[name] = static_cast<int>(net->convs.size());
+  net->convs.push_back(L);
+}
+
+// Single source conv, optional zero-padding of input channels up to cin_pad.
+static void add_plain(Net* net, const WeightBlob& blob, const std::string& name, float slope, int sh, int sw, int ph, int pw,
+                      int cin_pad = 0, float scale = 1.f) {
+  const BlobEntry& w = blob.get(name + ".w");
+  if (w.dims.size() != 4) throw std::runtime_error("'" + name + ".w' must be 4-d");
+  HostConv h(w.dims[0], w.dims[1], w.dims[2], std::max(cin_pad, w.dims[3]));
+  place(h, blob, name, 0, 0, slope, scale);
+  add_conv(net, name, h, sh, sw, ph, pw);
+}
+
+static void add_dw(Net* net, const WeightBlob& blob, const std::string& name, int stride, float slope) {
+  const BlobEntry& w = blob.get(name + ".w");
+  const BlobEntry& b = blob.get(name + ".b");
+  if (w.dims.size() != 4 || w.dims[1] != 3 || w.dims[2] != 3 || w.dims[3] != 1) throw std::runtime_error("'" + name + "' is not a depthwise 3x3");
+  DwLayer L;
+  L.C = w.dims[0]; L.stride = stride; L.slope = slope;
+  std::vector<float> w9c(static_cast<size_t>(9) * L.C);
+  for (int c = 0; c < L.C; ++c)
+    for (int t = 0; t < 9; ++t) w9c[static_cast<size_t>(t) * L.C + c] = w.data[static_cast<size_t>(c) * 9 + t];
+  if (cudaMalloc(&L.d_w, w9c.size() * 4) != cudaSuccess || cudaMalloc(&L.d_bias, L.C * 4) != cudaSuccess)
+    throw std::runtime_error("cudaMalloc failed for depthwise layer");
+  cudaMemcpy(L.d_w, w9c.data(), w9c.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(L.d_bias, b.data, L.C * 4, cudaMemcpyHostToDevice);
+  net->dws.push_back(L);
+}
+
+// ------------------------------------------------------------------------------------ architecture tables
+static const int kMnetStride[13] = {1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1};
+static const int kMnetCout[13] = {16, 32, 32, 64, 64, 128, 128, 128, 128, 128, 128, 256, 256};
+static const int kR50Blocks[4] = {3, 4, 6, 3};
+static const int kR50Planes[4] = {64, 128, 256, 512};
+
+static std::string sfmt(const char* fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
+  const float neck_slope = r50 ? 0.f : 0.1f;   // out_channels <= 64 -> LeakyReLU(0.1), else ReLU
+  const int C = r50 ? 256 : 64;
+  if (r50) {
+    add_plain(net, blob, "conv1", 0.f, 2, 2, 3, 3, 8);
+    for (int l = 0; l < 4; ++l)
+      for (int i = 0; i < kR50Blocks[l]; ++i) {
+        const int s = (i == 0 && l > 0) ? 2 : 1;
+        const std::string p = sfmt("layer%d.%d", l + 1, i);
+        add_plain(net, blob, p + ".conv1", 0.f, 1, 1, 0, 0);
+        add_plain(net, blob, p + ".conv2", 0.f, s, s, 1, 1);
+        add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0);   // ReLU after the residual add
+        if (i == 0) add_plain(net, blob, p + ".down", 1.f, s, s, 0, 0);
+      }
+  } else {
+    add_plain(net, blob, "body.0", 0.1f, 2, 2, 1, 1, 8);
+    for (int i = 1; i <= 13; ++i) {
+      add_dw(net, blob, sfmt("body.%d.dw", i), kMnetStride[i - 1], 0.1f);
+      add_plain(net, blob, sfmt("body.%d.pw", i), 0.1f, 1, 1, 0, 0);
+    }
+  }
+  for (int k = 1; k <= 3; ++k) add_plain(net, blob, sfmt("fpn.out%d", k), neck_slope, 1, 1, 0, 0);
+  for (int k = 1; k <= 2; ++k) add_plain(net, blob, sfmt("fpn.merge%d", k), neck_slope, 1, 1, 1, 1);
+  const int q = C / 4;
+  for (int k = 1; k <= 3; ++k) {
+    // SSH buffer layout (channels): [c5_1 (q) | c3 (2q) | c7 (q) | c5 (q) | c7_2 (q)]; the block's
+    // final ReLU over cat[c3,c5,c7] is applied by the producers of those three slices.
+    const std::string s = sfmt("ssh%d", k);
+    HostConv a(3 * q, 3, 3, C);
+    place(a, blob, s + ".c5_1", 0, 0, neck_slope);
+    place(a, blob, s + ".c3", q, 0, 0.f);
+    add_conv(net, s + ".A", a, 1, 1, 1, 1);
+    HostConv b(2 * q, 3, 3, q);
+    place(b, blob, s + ".c5_2", 0, 0, 0.f);
+    place(b, blob, s + ".c7_2", q, 0, neck_slope);
+    add_conv(net, s + ".B", b, 1, 1, 1, 1);
+    HostConv c(q, 3, 3, q);
+    place(c, blob, s + ".c7_3", 0, 0, 0.f);
+    add_conv(net, s + ".C", c, 1, 1, 1, 1);
+    // fused head: columns [cls 4 | box 8 | ldm 20]; input order (c3, c7, c5) vs source (c3, c5, c7)
+    HostConv h(32, 1, 1, C);
+    const char* parts[3] = {"cls", "box", "ldm"};
+    const int co[3] = {0, 4, 12};
+    for (int t = 0; t < 3; ++t) {
+      const std::string hn = sfmt("head%d.%s", k, parts[t]);
+      place(h, blob, hn, co[t], 0, 1.f, 1.f, 0, 2 * q);            // c3
+      place(h, blob, hn, co[t], 2 * q, 1.f, 1.f, 3 * q, q);         // c7
+      place(h, blob, hn, co[t], 3 * q, 1.f, 1.f, 2 * q, q);         // c5
+    }
+    add_conv(net, sfmt("head%d", k), h, 1, 1, 0, 0);
+  }
+}
+
+static void load_irv1(Net* net, const WeightBlob& blob) {
+  add_plain(net, blob, "conv2d_1a", 0.f, 2, 2, 0, 0, 8);
+  add_plain(net, blob, "conv2d_2a", 0.f, 1, 1, 0, 0);
+  add_plain(net, blob, "conv2d_2b", 0.f, 1, 1, 1, 1);
+  add_plain(net, blob, "conv2d_3b", 0.f, 1, 1, 0, 0);
+  add_plain(net, blob, "conv2d_4a", 0.f, 1, 1, 0, 0);
+  add_plain(net, blob, "conv2d_4b", 0.f, 2, 2, 0, 0);
+  for (int i = 0; i < 5; ++i) {
+    // Block35 buffer: [b1.0 | b2.0 | b0 | b2.2 | b1.1 | b2.1], 32 channels each
+    const std::string p = sfmt("repeat_1.%d", i);
+    HostConv a(96, 1, 1, 256);
+    place(a, blob, p + ".branch1.0", 0, 0, 0.f);
+    place(a, blob, p + ".branch2.0", 32, 0, 0.f);
+    place(a, blob, p + ".branch0", 64, 0, 0.f);
+    add_conv(net, p + ".A", a, 1, 1, 0, 0);
+    HostConv g(64, 3, 3, 64);   // block diagonal: (b1.0 -> b1.1), (b2.0 -> b2.1)
+    place(g, blob, p + ".branch1.1", 0, 0, 0.f);
+    place(g, blob, p + ".branch2.1", 32, 32, 0.f);
+    add_conv(net, p + ".G", g, 1, 1, 1, 1);
+    add_plain(net, blob, p + ".branch2.2", 0.f, 1, 1, 1, 1);
+    HostConv u(256, 1, 1, 96);  // input order (b0, b2.2, b1.1) vs source (b0, b1, b2); residual scale folded
+    place(u, blob, p + ".conv2d", 0, 0, 0.f, 0.17f, 0, 32);
+    place(u, blob, p + ".conv2d", 0, 32, 0.f, 0.17f, 64, 32);
+    place(u, blob, p + ".conv2d", 0, 64, 0.f, 0.17f, 32, 32);
+    add_conv(net, p + ".up", u, 1, 1, 0, 0);
+  }
+  add_plain(net, blob, "mixed_6a.branch0", 0.f, 2, 2, 0, 0);
+  add_plain(net, blob, "mixed_6a.branch1.0", 0.f, 1, 1, 0, 0);
+  add_plain(net, blob, "mixed_6a.branch1.1", 0.f, 1, 1, 1, 1);
+  add_plain(net, blob, "mixed_6a.branch1.2", 0.f, 2, 2, 0, 0);
+  auto add_block_17_8 = [&](const std::string& p, int cin, int cb, float scale, float out_slope, bool is17) {
+    // buffer: [b1.0 | b0 | b1.2 | b1.1], cb channels each
+    HostConv a(2 * cb, 1, 1, cin);
+    place(a, blob, p + ".branch1.0", 0, 0, 0.f);
+    place(a, blob, p + ".branch0", cb, 0, 0.f);
+    add_conv(net, p + ".A", a, 1, 1, 0, 0);
+    if (is17) {
+      add_plain(net, blob, p + ".branch1.1", 0.f, 1, 1, 0, 3);   // 1x7
+      add_plain(net, blob, p + ".branch1.2", 0.f, 1, 1, 3, 0);   // 7x1
+    } else {
+      add_plain(net, blob, p + ".branch1.1", 0.f, 1, 1, 0, 1);   // 1x3
+      add_plain(net, blob, p + ".branch1.2", 0.f, 1, 1, 1, 0);   // 3x1
+    }
+    add_plain(net, blob, p + ".conv2d", out_slope, 1, 1, 0, 0, 0, scale);   // input order (b0, b1.2) == source order
+    net->conv_idx[p + ".up"] = net->conv_idx[p + ".conv2d"];
+  };
+  for (int i = 0; i < 10; ++i) add_block_17_8(sfmt("repeat_2.%d", i), 896, 128, 0.10f, 0.f, true);
+  {
+    HostConv a(768, 1, 1, 896);
+    place(a, blob, "mixed_7a.branch0.0", 0, 0, 0.f);
+    place(a, blob, "mixed_7a.branch1.0", 256, 0, 0.f);
+    place(a, blob, "mixed_7a.branch2.0", 512, 0, 0.f);
+    add_conv(net, "mixed_7a.A", a, 1, 1, 0, 0);
+    add_plain(net, blob, "mixed_7a.branch0.1", 0.f, 2, 2, 0, 0);
+    add_plain(net, blob, "mixed_7a.branch1.1", 0.f, 2, 2, 0, 0);
+    add_plain(net, blob, "mixed_7a.branch2.1", 0.f, 1, 1, 1, 1);
+    add_plain(net, blob, "mixed_7a.branch2.2", 0.f, 2, 2, 0, 0);
+  }
+  for (int i = 0; i < 5; ++i) add_block_17_8(sfmt("repeat_3.%d", i), 1792, 192, 0.20f, 0.f, false);
+  add_block_17_8("block8", 1792, 192, 1.0f, 1.f, false);
+  add_plain(net, blob, "last_linear", 1.f, 1, 1, 0, 0);   // Linear(1792->512) with BatchNorm1d folded
+}
+
+// ------------------------------------------------------------------------------------ plan builder
+struct Builder {
+  Net* net;
+  Plan* plan;
+  int tensor(int H, int W, int C, int elem = 2, int ext = 0) {
+    TensorInfo t;
+    t.H = H; t.W = W; t.C = C; t.elem = elem; t.ext = ext;
+    t.bytes = (static_cast<size_t>(plan->B) * H * W * C * elem + 255) & ~static_cast<size_t>(255);
+    plan->tensors.push_back(t);
+    return static_cast<int>(plan->tensors.size()) - 1;
+  }
+  void touch(View v) {
+    if (v.t < 0) return;
+    TensorInfo& t = plan->tensors[v.t];
+    const int i = static_cast<int>(plan->ops.size());
+    if (t.first < 0) t.first = i;
+    t.last = i;
+  }
+  int layer(const std::string& name) {
+    auto it = net->conv_idx.find(name);
+    if (it == net->conv_idx.end()) throw std::runtime_error("plan: unknown layer '" + name + "'");
+    return it->second;
+  }
+  void conv(const std::string& name, View in, View out, int res_mode = RES_NONE, View res = View(), int out_mode = OUT_16BIT,
+            int P_off = 0) {
+    Op op;
+    op.kind = OP_CONV; op.layer = layer(name); op.in = in; op.out = out; op.res = res; op.res_mode = res_mode;
+    op.out_mode = out_mode; op.P_off = P_off;
+    const ConvLayer& L = net->convs[op.layer];
+    const TensorInfo& ti = plan->tensors[in.t];
+    if (in.coff + L.Cin > ti.C) throw std::runtime_error("plan: layer '" + name + "' reads past its input tensor");
+    if (out.t >= 0) {
+      const TensorInfo& to = plan->tensors[out.t];
+      if (to.H != conv_out_dim(ti.H, L.kh, L.sh, L.ph) || to.W != conv_out_dim(ti.W, L.kw, L.sw, L.pw) ||
+          out.coff + L.Cout > to.C)
+        throw std::runtime_error("plan: layer '" + name + "' output shape mismatch");
+    }
+    touch(in); touch(out); touch(res);
+    plan->ops.push_back(op);
+  }
+  void dw(int idx, View in, View out) {
+    Op op;
+    op.kind = OP_DW; op.layer = idx; op.in = in; op.out = out;
+    touch(in); touch(out);
+    plan->ops.push_back(op);
+  }
+  void maxpool(View in, View out, int C, int pad) {
+    Op op;
+    op.kind = OP_MAXPOOL; op.in = in; op.out = out; op.C = C; op.pad = pad;
+    touch(in); touch(out);
+    plan->ops.push_back(op);
+  }
+  void avgpool(View in, View out) {
+    Op op;
+    op.kind = OP_AVGPOOL; op.in = in; op.out = out;
+    touch(in); touch(out);
+    plan->ops.push_back(op);
+  }
+  void l2norm(View io) {
+    Op op;
+    op.kind = OP_L2NORM; op.in = io; op.out = io;
+    touch(io);
+    plan->ops.push_back(op);
+  }
+};
+
+static View V(int t, int coff = 0) {
+  View v;
+  v.t = t; v.coff = coff;
+  return v;
+}
+
+static void plan_retina(Net* net, Plan& plan, bool r50) {
+  Builder b{net, &plan};
+  const int H = plan.H, W = plan.W;
+  const int x0 = b.tensor(H, W, 8, 2, 1);
+  int c[3];
+  if (r50) {
+    const int H1 = conv_out_dim(H, 7, 2, 3), W1 = conv_out_dim(W, 7, 2, 3);
+    const int t1 = b.tensor(H1, W1, 64);
+    b.conv("conv1", V(x0), V(t1));
+    int h = conv_out_dim(H1, 3, 2, 1), w = conv_out_dim(W1, 3, 2, 1);
+    int x = b.tensor(h, w, 64);
+    b.maxpool(V(t1), V(x), 64, 1);
+    for (int l = 0; l < 4; ++l) {
+      const int planes = kR50Planes[l];
+      for (int i = 0; i < kR50Blocks[l]; ++i) {
+        const int s = (i == 0 && l > 0) ? 2 : 1;
+        const std::string p = sfmt("layer%d.%d", l + 1, i);
+        const int ho = conv_out_dim(h, 3, s, 1), wo = conv_out_dim(w, 3, s, 1);
+        const int y1 = b.tensor(h, w, planes);
+        b.conv(p + ".conv1", V(x), V(y1));
+        const int y2 = b.tensor(ho, wo, planes);
+        b.conv(p + ".conv2", V(y1), V(y2));
+        int idn = x;
+        if (i == 0) {
+          idn = b.tensor(ho, wo, planes * 4);
+          b.conv(p + ".down", V(x), V(idn));
+        }
+        const int y = b.tensor(ho, wo, planes * 4);
+        b.conv(p + ".conv3", V(y2), V(y), RES_PRE_ACT, V(idn));
+        x = y; h = ho; w = wo;
+      }
+      if (l >= 1) c[l - 1] = x;
+    }
+  } else {
+    int h = conv_out_dim(H, 3, 2, 1), w = conv_out_dim(W, 3, 2, 1);
+    int x = b.tensor(h, w, 8);
+    b.conv("body.0", V(x0), V(x));
+    int cin = 8;
+    for (int i = 1; i <= 13; ++i) {
+      const int s = kMnetStride[i - 1];
+      const int ho = conv_out_dim(h, 3, s, 1), wo = conv_out_dim(w, 3, s, 1);
+      const int d = b.tensor(ho, wo, cin);
+      b.dw(i - 1, V(x), V(d));
+      const int y = b.tensor(ho, wo, kMnetCout[i - 1]);
+      b.conv(sfmt("body.%d.pw", i), V(d), V(y));
+      x = y; h = ho; w = wo; cin = kMnetCout[i - 1];
+      if (i == 5) c[0] = x;
+      if (i == 11) c[1] = x;
+      if (i == 13) c[2] = x;
+    }
+  }
+  const int C = r50 ? 256 : 64, q = C / 4;
+  auto dims = [&](int t, int& h, int& w) { h = plan.tensors[t].H; w = plan.tensors[t].W; };
+  int h1, w1, h2, w2, h3, w3;
+  dims(c[0], h1, w1); dims(c[1], h2, w2); dims(c[2], h3, w3);
+  const int o3 = b.tensor(h3, w3, C);
+  b.conv("fpn.out3", V(c[2]), V(o3));
+  const int m2 = b.tensor(h2, w2, C);
+  b.conv("fpn.out2", V(c[1]), V(m2), RES_POST_ACT_UPSAMPLE, V(o3));
+  const int p2 = b.tensor(h2, w2, C);
+  b.conv("fpn.merge2", V(m2), V(p2));
+  const int m1 = b.tensor(h1, w1, C);
+  b.conv("fpn.out1", V(c[0]), V(m1), RES_POST_ACT_UPSAMPLE, V(p2));
+  const int p1 = b.tensor(h1, w1, C);
+  b.conv("fpn.merge1", V(m1), V(p1));
+  const int feat[3] = {p1, p2, o3};
+  plan.P_total = 2 * (h1 * w1 + h2 * w2 + h3 * w3);
+  int P_off = 0;
+  for (int k = 0; k < 3; ++k) {
+    int h, w;
+    dims(feat[k], h, w);
+    const int S = b.tensor(h, w, 6 * q);
+    const std::string s = sfmt("ssh%d", k + 1);
+    b.conv(s + ".A", V(feat[k]), V(S, 0));          // -> [c5_1 | c3]
+    b.conv(s + ".B", V(S, 0), V(S, 4 * q));         // c5_1 -> [c5 | c7_2]
+    b.conv(s + ".C", V(S, 5 * q), V(S, 3 * q));     // c7_2 -> c7
+    b.conv(sfmt("head%d", k + 1), V(S, q), View(), RES_NONE, View(), OUT_HEAD_SCATTER, P_off);
+    P_off += 2 * h * w;
+  }
+}
+
+static void plan_irv1(Net* net, Plan& plan) {
+  Builder b{net, &plan};
+  const int x0 = b.tensor(160, 160, 8, 2, 1);
+  const int t1 = b.tensor(79, 79, 32);
+  b.conv("conv2d_1a", V(x0), V(t1));
+  const int t2 = b.tensor(77, 77, 32);
+  b.conv("conv2d_2a", V(t1), V(t2));
+  const int t3 = b.tensor(77, 77, 64);
+  b.conv("conv2d_2b", V(t2), V(t3));
+  const int t4 = b.tensor(38, 38, 64);
+  b.maxpool(V(t3), V(t4), 64, 0);
+  const int t5 = b.tensor(38, 38, 80);
+  b.conv("conv2d_3b", V(t4), V(t5));
+  const int t6 = b.tensor(36, 36, 192);
+  b.conv("conv2d_4a", V(t5), V(t6));
+  int x = b.tensor(17, 17, 256);
+  b.conv("conv2d_4b", V(t6), V(x));
+  for (int i = 0; i < 5; ++i) {
+    const std::string p = sfmt("repeat_1.%d", i);
+    const int S = b.tensor(17, 17, 192);
+    b.conv(p + ".A", V(x), V(S, 0));
+    b.conv(p + ".G", V(S, 0), V(S, 128));
+    b.conv(p + ".branch2.2", V(S, 160), V(S, 96));
+    const int y = b.tensor(17, 17, 256);
+    b.conv(p + ".up", V(S, 64), V(y), RES_PRE_ACT, V(x));
+    x = y;
+  }
+  {
+    const int y = b.tensor(8, 8, 896);
+    b.conv("mixed_6a.branch0", V(x), V(y, 0));
+    const int u1 = b.tensor(17, 17, 192);
+    b.conv("mixed_6a.branch1.0", V(x), V(u1));
+    const int u2 = b.tensor(17, 17, 192);
+    b.conv("mixed_6a.branch1.1", V(u1), V(u2));
+    b.conv("mixed_6a.branch1.2", V(u2), V(y, 384));
+    b.maxpool(V(x), V(y, 640), 256, 0);
+    x = y;
+  }
+  auto block_17_8 = [&](const std::string& p, int hw, int cb, int cout) {
+    const int S = b.tensor(hw, hw, 4 * cb);
+    b.conv(p + ".A", V(x), V(S, 0));
+    b.conv(p + ".branch1.1", V(S, 0), V(S, 3 * cb));
+    b.conv(p + ".branch1.2", V(S, 3 * cb), V(S, 2 * cb));
+    const int y = b.tensor(hw, hw, cout);
+    b.conv(p + ".up", V(S, cb), V(y), RES_PRE_ACT, V(x));
+    x = y;
+  };
+  for (int i = 0; i < 10; ++i) block_17_8(sfmt("repeat_2.%d", i), 8, 128, 896);
+  {
+    const int y = b.tensor(3, 3, 1792);
+    const int U = b.tensor(8, 8, 768);
+    b.conv("mixed_7a.A", V(x), V(U));
+    b.conv("mixed_7a.branch0.1", V(U, 0), V(y, 0));
+    b.conv("mixed_7a.branch1.1", V(U, 256), V(y, 384));
+    const int Vt = b.tensor(8, 8, 256);
+    b.conv("mixed_7a.branch2.1", V(U, 512), V(Vt));
+    b.conv("mixed_7a.branch2.2", V(Vt), V(y, 640));
+    b.maxpool(V(x), V(y, 896), 896, 0);
+    x = y;
+  }
+  for (int i = 0; i < 5; ++i) block_17_8(sfmt("repeat_3.%d", i), 3, 192, 1792);
+  block_17_8("block8", 3, 192, 1792);
+  const int a = b.tensor(1, 1, 1792);
+  b.avgpool(V(x), V(a));
+  const int e = b.tensor(1, 1, 512, 4, 2);
+  b.conv("last_linear", V(a), V(e), RES_NONE, View(), OUT_FP32);
+  b.l2norm(V(e));
+}
+
+// Greedy interval placement: largest tensors first, each at the lowest offset that does not
+// collide with an already placed tensor whose live range overlaps.
+static void assign_arena(Plan& plan) {
+  std::vector<int> order;
+  for (size_t i = 0; i < plan.tensors.size(); ++i)
+    if (plan.tensors[i].ext == 0 && plan.tensors[i].first >= 0) order.push_back(static_cast<int>(i));
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return plan.tensors[a].bytes > plan.tensors[b].bytes; });
+  std::vector<int> placed;
+  size_t total = 0;
+  for (int id : order) {
+    TensorInfo& t = plan.tensors[id];
+    std::vector<std::pair<size_t, size_t>> busy;
+    for (int pid : placed) {
+      const TensorInfo& o = plan.tensors[pid];
+      if (o.first <= t.last && t.first <= o.last) busy.push_back({o.off, o.off + o.bytes});
+    }
+    std::sort(busy.begin(), busy.end());
+    size_t off = 0;
+    for (auto& iv : busy) {
+      if (off + t.bytes <= iv.first) break;
+      off = std::max(off, iv.second);
+    }
+    t.off = off;
+    total = std::max(total, off + t.bytes);
+    placed.push_back(id);
+  }
+  plan.arena_bytes = total;
+}
+
+static Plan* get_plan(Net* net, int B, int H, int W) {
+  const auto key = std::make_tuple(B, H, W);
+  auto it = net->plans.find(key);
+  if (it != net->plans.end()) return &it->second;
+  Plan plan;
+  plan.B = B; plan.H = H; plan.W = W;
+  if (net->model == FRB_IRV1) plan_irv1(net, plan);
+  else plan_retina(net, plan, net->model == FRB_RETINA_R50);
+  assign_arena(plan);
+  if (plan.arena_bytes > net->arena_bytes) {
+    if (net->arena) {
+      if (cudaDeviceSynchronize() != cudaSuccess) throw std::runtime_error("device sync failed before arena growth");
+      cudaFree(net->arena);
+      net->arena = nullptr;
+      net->arena_bytes = 0;
+    }
+    if (cudaMalloc(&net->arena, plan.arena_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      throw std::runtime_error(sfmt("cudaMalloc of %.2f GB activation arena failed", plan.arena_bytes / 1e9));
+    }
+    net->arena_bytes = plan.arena_bytes;
+  }
+  auto res = net->plans.emplace(key, std::move(plan));
+  return &res.first->second;
+}
+
+// ------------------------------------------------------------------------------------ execution
+struct ExecPtrs {
+  const void* in = nullptr;
+  float* emb = nullptr;
+  float* loc = nullptr;
+  float* conf = nullptr;
+  float* landm = nullptr;
+};
+
+static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep, cudaStream_t st) {
+  auto base = [&](View v) -> uint8_t* {
+    const TensorInfo& t = plan.tensors[v.t];
+    uint8_t* p = t.ext == 1 ? static_cast<uint8_t*>(const_cast<void*>(ep.in))
+                            : (t.ext == 2 ? reinterpret_cast<uint8_t*>(ep.emb) : static_cast<uint8_t*>(net->arena) + t.off);
+    return p + static_cast<size_t>(v.coff) * t.elem;
+  };
+  for (const Op& op : plan.ops) {
+    int rc = FRB_OK;
+    const TensorInfo& ti = plan.tensors[op.in.t];
+    switch (op.kind) {
+      case OP_CONV: {
+        ConvIO io;
+        io.in = base(op.in); io.in_ld = ti.C; io.B = plan.B; io.H = ti.H; io.W = ti.W;
+        io.out_mode = op.out_mode;
+        if (op.out.t >= 0) { io.out = base(op.out); io.out_ld = plan.tensors[op.out.t].C; }
+        io.res_mode = op.res_mode;
+        if (op.res.t >= 0) {
+          const TensorInfo& tr = plan.tensors[op.res.t];
+          io.res = base(op.res); io.res_ld = tr.C; io.rH = tr.H; io.rW = tr.W;
+        }
+        io.loc = ep.loc; io.conf = ep.conf; io.landm = ep.landm; io.P_total = plan.P_total; io.P_off = op.P_off;
+        rc = conv_launch(ctx, net->convs[op.layer], io, st);
+        break;
+      }
+      case OP_DW: {
+        const DwLayer& L = net->dws[op.layer];
+        rc = launch_dwconv3x3(ctx, base(op.in), plan.B, ti.H, ti.W, L.C, L.stride, L.d_w, L.d_bias, 2, L.slope, base(op.out), st);
+        break;
+      }
+      case OP_MAXPOOL:
+        rc = launch_maxpool3x3s2(ctx, base(op.in), ti.C, plan.B, ti.H, ti.W, op.C, op.pad, base(op.out),
+                                 plan.tensors[op.out.t].C, st);
+        break;
+      case OP_AVGPOOL:
+        rc = launch_avgpool(ctx, base(op.in), plan.B, ti.H * ti.W, ti.C, base(op.out), st);
+        break;
+      case OP_L2NORM:
+        rc = launch_l2norm(ctx, reinterpret_cast<float*>(base(op.in)), plan.B, ti.C, st);
+        break;
+    }
+    if (rc != FRB_OK) return rc;
+  }
+  return FRB_OK;
+}
+
+Net* build_net(frb_ctx* ctx, int model_id, const void* blob, size_t bytes) {
+  Net* net = new Net();
+  net->model = model_id;
+  net->ctx = ctx;
+  try {
+    WeightBlob wb;
+    parse_blob(blob, bytes, wb);
+    if (model_id == FRB_IRV1) load_irv1(net, wb);
+    else if (model_id == FRB_RETINA_MNET025 || model_id == FRB_RETINA_R50) load_retina(net, wb, model_id == FRB_RETINA_R50);
+    else throw std::runtime_error("unknown model id");
+  } catch (const std::exception& e) {
+    set_err(ctx, FRB_ERR_INVALID, "frb_load_model: %s", e.what());
+    destroy_net(net);
+    return nullptr;
+  }
+  return net;
+}
+
+void destroy_net(Net* net) {
+  if (net == nullptr) return;
+  std::vector<bool> seen(net->convs.size(), false);
+  for (auto& L : net->convs) conv_release(L);
+  for (auto& L : net->dws) {
+    if (L.d_w) cudaFree(L.d_w);
+    if (L.d_bias) cudaFree(L.d_bias);
+  }
+  if (net->arena) cudaFree(net->arena);
+  delete net;
+}
+
+int net_forward_retina(frb_ctx* ctx, Net* net, const void* d_in, int B, int H, int W, float* d_loc, float* d_conf,
+                       float* d_landm, cudaStream_t stream) {
+  if (B <= 0 || H < 32 || W < 32) return set_err(ctx, FRB_ERR_INVALID, "retina_forward: bad shape B=%d H=%d W=%d", B, H, W);
+  try {
+    Plan* plan = get_plan(net, B, H, W);
+    ExecPtrs ep;
+    ep.in = d_in; ep.loc = d_loc; ep.conf = d_conf; ep.landm = d_landm;
+    return run_plan(ctx, net, *plan, ep, stream);
+  } catch (const std::exception& e) {
+    return set_err(ctx, FRB_ERR_INVALID, "retina_forward: %s", e.what());
+  }
+}
+
+int net_forward_irv1(frb_ctx* ctx, Net* net, const void* d_in, int F, float* d_emb, cudaStream_t stream) {
+  if (F <= 0) return set_err(ctx, FRB_ERR_INVALID, "irv1_forward: F must be positive");
+  try {
+    Plan* plan = get_plan(net, F, 160, 160);
+    ExecPtrs ep;
+    ep.in = d_in; ep.emb = d_emb;
+    return run_plan(ctx, net, *plan, ep, stream);
+  } catch (const std::exception& e) {
+    return set_err(ctx, FRB_ERR_INVALID, "irv1_forward: %s", e.what());
+  }
+}
+
+}  // namespace frb

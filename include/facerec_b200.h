@@ -1,0 +1,150 @@
+/* facerec_b200 — C ABI of libfacerec_b200.so (CUDA, sm_100a only).
+ *
+ * Drop-in boundary for the per-frame face path of MoMaF/facerec.  The reference has no FFI of
+ * its own: its operator API for this path is three duck-typed Python call sites plus two
+ * library calls.  Each entry point below names the reference site whose arithmetic it replaces
+ * (paths relative to the reference checkout).  The Python adapters in facerec_b200/ present the
+ * reference-side objects (detect(), embeddings(), linkage input, kNN classifier) on top of this
+ * ABI; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 (FRB_OK) or a negative frb_status; frb_last_error(ctx) gives text;
+ *  - `d_` pointers are device pointers owned by the caller; `h_` pointers are host pointers;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *    asynchronous on that stream unless stated otherwise;
+ *  - one frb_ctx per (process, device); a ctx is not thread-safe;
+ *  - no torch / pybind types cross this boundary;
+ *  - there is no CPU fallback: without an sm_100 device frb_init fails.
+ */
+#ifndef FACEREC_B200_H_
+#define FACEREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frb_ctx frb_ctx;
+
+enum frb_status {
+  FRB_OK = 0,
+  FRB_ERR_INVALID = -1,   /* bad argument / unmet precondition */
+  FRB_ERR_CUDA = -2,      /* CUDA runtime or driver error (text in frb_last_error) */
+  FRB_ERR_STATE = -3,     /* e.g. model not loaded */
+  FRB_ERR_NO_DEVICE = -4  /* no sm_100 GPU */
+};
+
+enum frb_model {
+  FRB_RETINA_MNET025 = 0, /* RetinaFace, MobileNetV1-0.25 backbone, FPN/SSH 64 ch  */
+  FRB_RETINA_R50 = 1,     /* RetinaFace, ResNet-50 backbone, FPN/SSH 256 ch        */
+  FRB_IRV1 = 2            /* FaceNet InceptionResnetV1, 512-d                      */
+};
+
+enum frb_pdist_layout {
+  FRB_CONDENSED_F32 = 0,  /* scipy pdist order, float  */
+  FRB_CONDENSED_F64 = 1,  /* scipy pdist order, double */
+  FRB_SQUARE_F32 = 2      /* rows x N row-major, float */
+};
+
+enum frb_option {
+  FRB_OPT_BF16 = 0,        /* 1: bf16 activations/weights instead of fp16 (set before frb_load_model) */
+  FRB_OPT_BN_CAP = 1,      /* largest conv tile N (multiple of 16, <= 256)                           */
+  FRB_OPT_FORCE_GATHER = 2 /* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int frb_version(void);
+int frb_init(int device, frb_ctx** out);
+int frb_destroy(frb_ctx* ctx);
+const char* frb_last_error(frb_ctx* ctx); /* valid until the next call on ctx */
+int frb_set_option(frb_ctx* ctx, int option, int value);
+long long frb_launch_count(frb_ctx* ctx); /* kernels launched through ctx so far */
+
+/* Weights.  `h_blob` is the self-describing fp32 blob written by facerec_b200/weights.py
+ * (magic "FRBW", entry table of name/shape/offset, then data): one "<layer>.w" [Cout,kh,kw,Cin]
+ * and "<layer>.b" [Cout] per convolution with BatchNorm already folded on the host.
+ * Replaces: model construction at facerec/extract.py:392 and facerec/detector.py:64. */
+int frb_load_model(frb_ctx* ctx, int model_id, const void* h_blob, size_t bytes);
+
+/* ---- per-frame path ----------------------------------------------------------------------- */
+
+/* K1  u8 HWC frames -> 16-bit NHWC with 8 channels (3 real + 5 zero) for the tensor-core stem:
+ * RetinaFace input = BGR minus (104,117,123), no scaling.
+ * Replaces the input transform inside RetinaFace.predict (facerec/detector.py:68); frames arrive RGB
+ * from facerec/extract.py:300, so src_is_rgb=1 swaps channels back. */
+int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb,
+                      void* d_out16 /*[B,H,W,8]*/, void* stream);
+
+/* K2-K5  RetinaFace forward -> loc [B,P,4], conf [B,P,2] (logits), landm [B,P,10], fp32.
+ * Replaces the network inside RetinaFace.predict (facerec/detector.py:64,68). */
+int frb_retina_forward(frb_ctx* ctx, int model_id, const void* d_in16 /*[B,H,W,8]*/, int B, int H, int W,
+                       float* d_loc, float* d_conf, float* d_landm, void* stream);
+/* number of priors for an H x W input: 2 * sum over steps {8,16,32} of ceil(H/s)*ceil(W/s) */
+int frb_num_priors(int H, int W);
+
+/* K6  PriorBox decode + softmax + score>thr + compaction; priors are computed in-kernel.
+ * cand row = x1,y1,x2,y2,score, 10 landmark coords (pixels).  Candidates beyond max_cand are
+ * dropped but still counted in d_count (caller checks for overflow).
+ * Replaces anchor decode / confidence filter inside RetinaFace.predict(img, threshold=0.95)
+ * (facerec/detector.py:68). */
+int frb_prior_decode_filter(frb_ctx* ctx, const float* d_loc, const float* d_conf, const float* d_landm, int B, int H,
+                            int W, float score_thr, int max_cand, float* d_cand /*[B,max_cand,15]*/,
+                            int32_t* d_count /*[B]*/, int32_t* d_prior_idx /*[B,max_cand]*/, void* stream);
+
+/* K7  per-frame sort by score (descending, ties by lower prior index) + greedy IoU NMS.
+ * d_keep holds indices into the frame's cand rows, in score order. */
+int frb_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
+            float iou_thr, int legacy_plus_one, int32_t* d_keep /*[B,max_cand]*/, int32_t* d_nkeep /*[B]*/,
+            void* stream);
+
+/* K8  crop + bilinear resize (cv2.INTER_LINEAR u8 fixed-point semantics) to 160x160 +
+ * fixed_image_standardization (x-127.5)/128 -> 16-bit NHWC with 8 channels (3 real + 5 zero).
+ * d_boxes rows = (frame, x, y, w, h): ints AFTER the host-side cropBox clamping.
+ * Replaces keras_facenet cropBox + the resize/standardise part of FaceNet.embeddings
+ * (facerec/extract.py:161-166). */
+int frb_crop_resize_std(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, const int32_t* d_boxes /*[F,5]*/,
+                        int F, void* d_out16 /*[F,160,160,8]*/, void* stream);
+
+/* K2,K9-K11  InceptionResnetV1 forward incl. last_linear + BatchNorm1d + L2 normalisation.
+ * Replaces FaceNet.embeddings model.predict (facerec/extract.py:166) and the explicit
+ * normalisation of facerec/utils/utils.py:20-22. */
+int frb_irv1_forward(frb_ctx* ctx, const void* d_in16 /*[F,160,160,8]*/, int F, float* d_emb /*[F,512]*/, void* stream);
+
+/* Generic K2 entry (unit tests, micro-benchmarks): one convolution with the fused epilogue.
+ * h_w [Cout,kh,kw,Cin] fp32 and h_bias [Cout] are host pointers; the call prepares the layer,
+ * launches, synchronises the stream and releases the layer.  act: 0 none, 1 relu, 2 leaky(slope).
+ * res_mode: 0 none, 1 add d_res before activation ([B,Ho,Wo,Cout]), 2 add nearest-upsampled
+ * d_res [B,rH,rW,Cout] after activation.  out_fp32: 0 -> 16-bit out, 1 -> fp32 out. */
+int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, const float* h_w, const float* h_bias,
+               int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int act, float slope, const void* d_res16,
+               int res_mode, int rH, int rW, void* d_out, int out_fp32, int iters, float* h_ms /*nullable*/,
+               void* stream);
+
+/* ---- embedding-distance stage ------------------------------------------------------------- */
+
+/* K12  per-trajectory mean of per-frame embeddings (facerec/cluster.py:26-29). */
+int frb_segment_mean(frb_ctx* ctx, const float* d_X /*[n,D]*/, const int32_t* d_offsets /*[S+1]*/, int S, int D,
+                     float* d_out /*[S,D]*/, void* stream);
+
+/* K13  Euclidean distances of rows [row0,row0+rows) of X against all of X (split-bf16 tensor-core
+ * GEMM, fp32 accumulate, d = sqrt(max(|a|^2+|b|^2-2ab,0))).  Condensed layouts receive only the
+ * j>i entries of those rows, at their scipy pdist offsets in a full-size condensed vector.
+ * Replaces the implicit pdist inside scipy linkage (facerec/cluster.py:41,199). */
+int frb_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, void* stream);
+
+/* K14  k smallest Euclidean distances, never materialising Q x M.  Ties -> lower DB index.
+ * Replaces KNeighborsClassifier.fit/kneighbors (facerec/classify_knn.py:212,227). */
+int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k,
+                 int32_t* d_idx /*[Q,k] ascending distance*/, float* d_dist /*[Q,k]*/, void* stream);
+
+/* K15  neighbour labels -> class histogram / k (predict_proba with uniform weights,
+ * facerec/classify_knn.py:227). */
+int frb_knn_vote(frb_ctx* ctx, const int32_t* d_idx, const int32_t* d_label_idx /*[M] in [0,n_classes)*/, int Q, int k,
+                 int n_classes, float* d_proba /*[Q,n_classes]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACEREC_B200_H_ */

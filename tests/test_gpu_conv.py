@@ -1,0 +1,92 @@
+"""K2 parity: the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32 conv of the same
+16-bit-rounded operands (tolerance: one fp16 output rounding + fp32 accumulation-order noise)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x16, w, b, stride, pad, act, slope, res16=None, res_mode=0):
+    x = x16.float().cpu().permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w).half().float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, wt, None if b is None else torch.from_numpy(b), stride=stride, padding=pad)
+    if res_mode == 1:
+        y = y + res16.float().cpu().permute(0, 3, 1, 2)
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
+        y = F.leaky_relu(y, slope)
+    if res_mode == 2:
+        r = res16.float().cpu().permute(0, 3, 1, 2)
+        y = y + F.interpolate(r, size=y.shape[2:], mode="nearest")
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CASES = [
+    # B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32
+    (2, 20, 24, 64, 128, 1, 1, (1, 1), (0, 0), 1, 0, False),     # plain GEMM, TMA A path
+    (1, 17, 17, 96, 32, 1, 1, (1, 1), (0, 0), 0, 0, False),      # K tail (96 -> 128), small N
+    (2, 19, 23, 32, 64, 3, 3, (1, 1), (1, 1), 2, 0, False),      # 3x3 pad 1, leaky
+    (2, 36, 40, 8, 8, 3, 3, (2, 2), (1, 1), 2, 0, False),        # MobileNet first conv (Cin padded to 8)
+    (1, 64, 80, 8, 64, 7, 7, (2, 2), (3, 3), 1, 0, False),       # ResNet stem
+    (2, 8, 8, 128, 128, 1, 7, (1, 1), (0, 3), 1, 0, False),      # Block17 1x7
+    (2, 8, 8, 128, 128, 7, 1, (1, 1), (3, 0), 1, 0, False),      # Block17 7x1
+    (1, 36, 36, 192, 256, 3, 3, (2, 2), (0, 0), 1, 0, False),    # stride 2, no pad, two N tiles
+    (2, 17, 17, 96, 256, 1, 1, (1, 1), (0, 0), 1, 1, False),     # residual before activation
+    (1, 23, 40, 128, 64, 1, 1, (1, 1), (0, 0), 2, 2, False),     # FPN lateral + nearest-upsampled top-down
+    (3, 1, 1, 1792, 512, 1, 1, (1, 1), (0, 0), 0, 0, True),      # last_linear, fp32 out
+    (4, 68, 120, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),     # > 148 tiles: persistent loop, TMEM double buffer
+    (1, 30, 30, 256, 512, 1, 1, (2, 2), (0, 0), 0, 0, False),    # strided 1x1 (ResNet downsample) via gather
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv2d_matches_torch(ctx, case):
+    from facerec_b200 import ops
+    B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32 = case
+    g = torch.Generator().manual_seed(1234 + Cin * 7 + Cout)
+    x16 = (torch.randn(B, H, W, Cin, generator=g)).half().cuda()
+    w = (torch.randn(Cout, kh, kw, Cin, generator=g) / np.sqrt(kh * kw * Cin)).numpy().astype(np.float32)
+    b = (torch.randn(Cout, generator=g) * 0.1).numpy().astype(np.float32)
+    Ho = (H + 2 * pad[0] - kh) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - kw) // stride[1] + 1
+    res16 = None
+    if res_mode == 1:
+        res16 = torch.randn(B, Ho, Wo, Cout, generator=g).half().cuda()
+    elif res_mode == 2:
+        res16 = torch.randn(B, (Ho + 1) // 2, (Wo + 1) // 2, Cout, generator=g).half().cuda()
+    out, _ = ops.conv2d(ctx, x16, w, b, stride, pad, act, 0.1, res16, res_mode, out_fp32)
+    torch.cuda.synchronize()
+    ref = _ref(x16, w, b, stride, pad, act, 0.1, res16, res_mode)
+    got = out.float().cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 2e-3 * ref.abs() + 2e-3
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4g} at ref {ref.flatten()[err.argmax()].item():.4g}"
+
+
+def test_conv2d_bf16_option():
+    from facerec_b200 import ops, _lib
+    c = _lib.Context(0)
+    try:
+        c.set_option(_lib.FRB_OPT_BF16, 1)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(2, 12, 12, 64, generator=g).bfloat16().cuda()
+        w = (torch.randn(96, 3, 3, 64, generator=g) / 24).numpy().astype(np.float32)
+        out, _ = ops.conv2d(c, x, w, None, (1, 1), (1, 1), 1, 0.0)
+        torch.cuda.synchronize()
+        ref = F.relu(F.conv2d(x.float().cpu().permute(0, 3, 1, 2), torch.from_numpy(w).bfloat16().float().permute(0, 3, 1, 2),
+                              padding=1)).permute(0, 2, 3, 1)
+        err = (out.float().cpu() - ref).abs()
+        assert bool((err <= 1e-2 * ref.abs() + 1e-2).all()), err.max().item()
+    finally:
+        c.close()
+
+
+def test_conv2d_rejects_bad_shapes(ctx):
+    from facerec_b200 import ops, _lib
+    x = torch.zeros(1, 8, 8, 12, dtype=torch.float16, device="cuda")   # Cin not a multiple of 8
+    with pytest.raises(_lib.FrbError):
+        ops.conv2d(ctx, x, np.zeros((16, 1, 1, 12), np.float32), None)

@@ -1,0 +1,98 @@
+"""Parity of the memory-bound glue kernels (K1, K6, K7, K8) against the numpy oracle: bit-exact for the
+integer / index work, last-ulp (expf) tolerance for decoded boxes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_preprocess_matches_numpy(ctx):
+    from facerec_b200 import ops
+    rng = np.random.RandomState(0)
+    for shape in [(2, 36, 50, 3), (1, 7, 9, 3), (3, 360, 640, 3)]:
+        fr = rng.randint(0, 256, shape).astype(np.uint8)
+        out = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True).float().cpu().numpy()
+        ref = np.zeros(shape[:3] + (8,), np.float32)
+        ref[..., 0] = fr[..., 2].astype(np.float32) - 104
+        ref[..., 1] = fr[..., 1].astype(np.float32) - 117
+        ref[..., 2] = fr[..., 0].astype(np.float32) - 123
+        assert np.array_equal(out, ref)
+        out_bgr = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), False).float().cpu().numpy()
+        assert np.array_equal(out_bgr[..., 0], fr[..., 0].astype(np.float32) - 104)
+
+
+def _raw(rng, B, H, W, frac=0.01):
+    from oracle import postproc
+    P = postproc.num_priors(H, W)
+    loc = rng.standard_normal((B, P, 4)).astype(np.float32)
+    landm = rng.standard_normal((B, P, 10)).astype(np.float32) * 2
+    conf = rng.standard_normal((B, P, 2)).astype(np.float32)
+    hot = rng.rand(B, P) < frac
+    conf[..., 1] += hot * rng.uniform(3, 12, (B, P)).astype(np.float32)
+    return loc, conf, landm
+
+
+@pytest.mark.parametrize("H,W,frac", [(360, 640, 0.01), (135, 97, 0.05), (1080, 1920, 0.001)])
+def test_decode_filter_nms_matches_oracle(ctx, H, W, frac):
+    from facerec_b200 import ops
+    from oracle import postproc
+    rng = np.random.RandomState(H + W)
+    B = 3
+    loc, conf, landm = _raw(rng, B, H, W, frac)
+    assert ops.num_priors(H, W) == postproc.num_priors(H, W)
+    tl, tc, tm = (torch.from_numpy(a).cuda() for a in (loc, conf, landm))
+    cand, count, pidx = ops.prior_decode_filter(ctx, tl, tc, tm, H, W, 0.95, 1024)
+    keep, nkeep = ops.nms(ctx, cand, count, pidx, 0.4, True)
+    cand, count, pidx, keep, nkeep = (t.cpu().numpy() for t in (cand, count, pidx, keep, nkeep))
+    for b in range(B):
+        scores = postproc.face_scores(conf[b])
+        sel = np.nonzero(scores > np.float32(0.95))[0]
+        assert count[b] == len(sel) <= 1024
+        got_sel = pidx[b, :count[b]]
+        assert np.array_equal(np.sort(got_sel), sel)            # identical candidate set (order is arbitrary)
+        dets, kept_priors = postproc.postprocess(loc[b], conf[b], landm[b], H, W)
+        k = keep[b, :nkeep[b]]
+        assert np.array_equal(pidx[b, k], kept_priors)           # identical kept set, identical order
+        got = cand[b, k]
+        assert np.array_equal(got[:, 4], dets[:, 4])             # scores bit-exact
+        np.testing.assert_allclose(got[:, :4], dets[:, :4], rtol=0, atol=2e-3)    # expf ulp * 1920 px
+        np.testing.assert_allclose(got[:, 5:], dets[:, 5:], rtol=0, atol=1e-3)
+
+
+def test_nms_empty_and_overflow(ctx):
+    from facerec_b200 import ops
+    rng = np.random.RandomState(3)
+    H, W = 64, 64
+    loc, conf, landm = _raw(rng, 2, H, W, 0.0)
+    conf[0, :, 1] = -20          # frame 0: nothing passes
+    conf[1, :, 1] = 20           # frame 1: everything passes -> overflow is reported through count
+    tl, tc, tm = (torch.from_numpy(a).cuda() for a in (loc, conf, landm))
+    cand, count, pidx = ops.prior_decode_filter(ctx, tl, tc, tm, H, W, 0.95, 32)
+    keep, nkeep = ops.nms(ctx, cand, count, pidx)
+    count, nkeep = count.cpu().numpy(), nkeep.cpu().numpy()
+    assert count[0] == 0 and nkeep[0] == 0
+    assert count[1] == loc.shape[1] and 1 <= nkeep[1] <= 32
+
+
+def test_crop_resize_standardize_matches_cv2_semantics(ctx):
+    from facerec_b200 import ops
+    from oracle import crop
+    rng = np.random.RandomState(7)
+    B, H, W = 2, 90, 120
+    frames = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    boxes = []
+    for f in range(B):
+        for _ in range(6):
+            x, y = rng.randint(0, W - 4), rng.randint(0, H - 4)
+            w, h = rng.randint(2, W - x + 1), rng.randint(2, H - y + 1)
+            boxes.append((f, x, y, w, h))
+    boxes.append((0, 0, 0, W, H))          # whole frame
+    boxes.append((1, 5, 5, 1, 1))          # single pixel
+    boxes.append((1, 10, 10, 160, 80)[:1] + (0, 0, 120, 80))
+    bx = np.asarray(boxes, np.int32)
+    out = ops.crop_resize_std(ctx, torch.from_numpy(frames).cuda(), torch.from_numpy(bx).cuda()).float().cpu().numpy()
+    for i, (f, x, y, w, h) in enumerate(bx):
+        ref = crop.standardize(crop.resize_linear_u8(frames[f, y:y + h, x:x + w]))
+        assert np.array_equal(out[i, :, :, :3], ref), i       # (u8 - 127.5)/128 is exact in fp16
+        assert not out[i, :, :, 3:].any()

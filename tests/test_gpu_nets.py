@@ -1,0 +1,66 @@
+"""Whole-network parity: the CUDA graphs (fused layers, concat-by-offset buffers, fp16 activations,
+fp32 accumulation) against the fp32 PyTorch oracle on the same seeded weights and inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(rng, B, H, W):
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    out = np.empty((B, H, W, 3), np.uint8)
+    for b in range(B):
+        img = np.zeros((H, W, 3), np.float32)
+        for c in range(3):
+            img[..., c] = 127 + 60 * np.sin(xx / rng.uniform(7, 40) + rng.uniform(0, 6)) * np.cos(yy / rng.uniform(7, 40))
+        img += rng.standard_normal((H, W, 3)) * 12
+        out[b] = np.clip(img, 0, 255).astype(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("model,backbone,B,H,W", [("retina_mnet025", "mnet025", 2, 360, 640),
+                                                  ("retina_r50", "r50", 2, 135, 240),
+                                                  ("retina_r50", "r50", 1, 270, 481)])
+def test_retina_forward_matches_oracle(ctx, model, backbone, B, H, W):
+    from facerec_b200 import ops, weights
+    from oracle import nets, postproc
+    w = weights.synth_weights(model, 0)
+    ops.load_model(ctx, weights.MODEL_IDS[model], weights.write_blob(w))
+    rng = np.random.RandomState(H)
+    fr = _frames(rng, B, H, W)
+    x16 = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True)
+    loc, conf, landm = (t.cpu() for t in ops.retina_forward(ctx, weights.MODEL_IDS[model], x16))
+    P = nets.params_from_weights(w)
+    x = torch.from_numpy(fr[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32)).permute(0, 3, 1, 2)
+    with torch.no_grad():
+        rloc, rconf, rlandm = nets.retina_forward(P, x.contiguous(), backbone)
+    assert loc.shape == rloc.shape == (B, postproc.num_priors(H, W), 4)
+    for got, ref, name in ((loc, rloc, "loc"), (conf, rconf, "conf"), (landm, rlandm, "landm")):
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 0.02 * scale + 0.02, f"{name}: max err {err:.4g} vs scale {scale:.4g}"
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel < 5e-3, f"{name}: relative L2 error {rel:.3g}"
+
+
+def test_irv1_forward_matches_oracle(ctx):
+    from facerec_b200 import ops, weights
+    from oracle import nets, crop
+    w = weights.synth_weights("irv1", 0)
+    ops.load_model(ctx, weights.MODEL_IDS["irv1"], weights.write_blob(w))
+    rng = np.random.RandomState(1)
+    fr = _frames(rng, 2, 200, 260)
+    boxes = np.array([[0, 10, 20, 120, 150], [0, 100, 30, 160, 160], [1, 0, 0, 260, 200], [1, 50, 60, 33, 47],
+                      [1, 200, 150, 60, 50]], np.int32)
+    faces = ops.crop_resize_std(ctx, torch.from_numpy(fr).cuda(), torch.from_numpy(boxes).cuda())
+    emb = ops.irv1_forward(ctx, faces).cpu()
+    P = nets.params_from_weights(w)
+    x = np.stack([crop.standardize(crop.resize_linear_u8(fr[f, y:y + h, x0:x0 + ww])) for f, x0, y, ww, h in boxes])
+    with torch.no_grad():
+        ref = nets.irv1_forward(P, torch.from_numpy(x).permute(0, 3, 1, 2).contiguous())
+    cos = (emb * ref).sum(1)
+    assert torch.allclose(emb.norm(dim=1), torch.ones(len(boxes)), atol=1e-5)
+    assert cos.min().item() >= 0.999, cos
+    # distinct faces stay distinct (the test is not vacuous)
+    assert (ref @ ref.T - torch.eye(len(boxes))).max().item() < 0.9999
