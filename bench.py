@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""Headline benchmark: video frames/s of detect+embed (BASELINE.json metric) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): 1920x1080 synthetic clip, RetinaFace-ResNet50 + InceptionResnetV1,
+64-frame batches, seeded random-init weights.  A step = one pass of the hot path over one 64-frame
+batch: K1 preprocess -> RetinaFace forward (tcgen05 implicit-GEMM convs) -> K6 decode/filter -> K7 NMS ->
+host box arithmetic -> K8 crop/resize -> InceptionResnetV1 + L2 norm, faces embedded on every
+`save_every`-th frame (the reference's gate, facerec/extract.py:336).  Frames shard over ranks exactly
+like the reference's --shard-i/--n-shards split (no data-path collective): weak scaling.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the CPU oracle on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
+
+`value`  : frames/s with the batch already resident in HBM when the timed region starts.
+`e2e`    : the same through the host-facing call (FacePipeline.detect_embed) with pinned HOST frames:
+           H2D of the batch and D2H of detections + embeddings inside the timed region.
+`roofline`: the RetinaFace-R50 forward (82 conv launches of conv_igemm_kernel + 1 max-pool), timed with
+           CUDA events on the launching stream inside the timed region; algorithmic work
+           449.71 GFLOP/frame x 64 frames per launch of the forward.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R50_GFLOP_PER_FRAME_1080P = 449.71    # SURVEY App. C (82 convs, 1920x1080)
+IRV1_GFLOP_PER_FACE = 2.835
+METRIC = "video_frames_per_sec_detect_embed"
+
+
+def conv_gflop_retina(backbone: str, H: int, W: int) -> float:
+    """Analytic conv FLOPs per frame of the RetinaFace graph (2 FLOP per MAC), any input size."""
+    from facerec_b200 import weights as Wt
+    o = lambda n, k, s, p: (n + 2 * p - k) // s + 1
+    macs = 0
+    if backbone == "r50":
+        h, w = o(H, 7, 2, 3), o(W, 7, 2, 3)
+        macs += h * w * 64 * 49 * 3
+        h, w = o(h, 3, 2, 1), o(w, 3, 2, 1)
+        cin = 64
+        feats = []
+        for l, (nb, planes) in enumerate(zip(Wt.R50_BLOCKS, Wt.R50_PLANES)):
+            for i in range(nb):
+                s = 2 if (i == 0 and l > 0) else 1
+                macs += h * w * planes * cin
+                ho, wo = o(h, 3, s, 1), o(w, 3, s, 1)
+                macs += ho * wo * planes * planes * 9 + ho * wo * planes * 4 * planes
+                if i == 0:
+                    macs += ho * wo * planes * 4 * cin
+                cin, h, w = planes * 4, ho, wo
+            if l >= 1:
+                feats.append((h, w, cin))
+        C = 256
+    else:
+        h, w = o(H, 3, 2, 1), o(W, 3, 2, 1)
+        macs += h * w * 8 * 27
+        cin = 8
+        feats = []
+        for i, (s, cout) in enumerate(zip(Wt.MNET_STRIDES, Wt.MNET_COUT), start=1):
+            h, w = o(h, 3, s, 1), o(w, 3, s, 1)
+            macs += h * w * cin * 9 + h * w * cin * cout
+            cin = cout
+            if i in (5, 11, 13):
+                feats.append((h, w, cin))
+        C = 64
+    for (h, w, c) in feats:
+        macs += h * w * c * C
+    for (h, w, _) in feats[:2]:
+        macs += h * w * C * C * 9
+    q = C // 4
+    for (h, w, _) in feats:
+        macs += h * w * 9 * (C * 2 * q + C * q + 3 * q * q) + h * w * C * 32
+    return 2.0 * macs / 1e9
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+
+
+def make_batch(seed, first, B, H, W):
+    from facerec_b200 import synth
+    return synth.clip(seed, first, B, H, W)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_fps(frames: np.ndarray, first_index: int, backbone: str, save_every: int, threads: int):
+    """The fp32 oracle driven like the reference loop (one frame per detect call, one face per embed call):
+    returns (frames/s, faces embedded)."""
+    import torch
+    from facerec_b200 import weights as Wt
+    from facerec_b200.pipeline import boxes_to_rects
+    from oracle import nets, postproc, crop
+    torch.set_num_threads(threads)
+    H, W = frames.shape[1:3]
+    Pd = nets.params_from_weights(Wt.synth_weights("retina_" + backbone, 0))
+    Pe = nets.params_from_weights(Wt.synth_weights("irv1", 0))
+    t0 = time.time()
+    faces = 0
+    with torch.no_grad():
+        for b in range(len(frames)):
+            f = frames[b]
+            x = torch.from_numpy(f[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32))
+            loc, conf, landm = nets.retina_forward(Pd, x.permute(2, 0, 1)[None].contiguous(), backbone)
+            dets, _ = postproc.postprocess(loc[0].numpy(), conf[0].numpy(), landm[0].numpy(), H, W)
+            if (first_index + b) % save_every != 0:
+                continue
+            dets = dets[np.minimum(dets[:, 2] - dets[:, 0], dets[:, 3] - dets[:, 1]) >= 20] if len(dets) else dets
+            rects = boxes_to_rects(dets[:, :4], np.zeros(len(dets), np.int64), W, H)
+            for (_, x0, y0, w, h) in rects:
+                if w <= 0 or h <= 0:
+                    continue
+                face = crop.standardize(crop.resize_linear_u8(f[y0:y0 + h, x0:x0 + w]))
+                nets.irv1_forward(Pe, torch.from_numpy(face).permute(2, 0, 1)[None].contiguous())
+                faces += 1
+    dt = time.time() - t0
+    return len(frames) / dt, faces, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(1, a.ref_frames)
+    # sample index 0 lands on the save_every gate so every step also embeds that frame's faces
+    frames = make_batch(a.clip_seed, 0, sample, a.height, a.width)
+    for _ in range(a.warmup):
+        cpu_reference_fps(frames[:1], 0, a.backbone, a.save_every, threads)
+    t0 = time.time()
+    faces = 0
+    for _ in range(a.steps):
+        _, f, _ = cpu_reference_fps(frames, 0, a.backbone, a.save_every, threads)
+        faces += f
+    dt = time.time() - t0
+    fps = a.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(a, sample_frames=sample),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frame(s) of the {a.width}x{a.height} clip per step, fp32 PyTorch oracle, "
+                                   f"batch 1 per frame/face like facerec/extract.py:303,166; {faces} faces embedded"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, sample_frames=None):
+    c = {"workload": f"configs[1]: {a.width}x{a.height} synthetic clip, RetinaFace-{a.backbone} + InceptionResnetV1, "
+                     f"{a.batch}-frame batches, save_every={a.save_every}, random-init seeded weights",
+         "global_batch_frames": a.batch * a.gpus, "frames_per_gpu_per_step": a.batch, "parallelism": f"frame-shard x{a.gpus}",
+         "l2_policy": "inputs larger than L2 (one 64-frame 1080p batch = 398 MB u8, 1.06 GB after K1)"}
+    if sample_frames is not None:
+        c["sample_frames_per_step"] = sample_frames
+    return c
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from facerec_b200._lib import Context
+    from facerec_b200.pipeline import FacePipeline
+    ctx = Context(local)   # raises without an sm_100 GPU / the built library: no fallback
+    pipe = FacePipeline(a.backbone, min_face_size=20, save_every=a.save_every, ctx=ctx)
+    H, W, B = a.height, a.width, a.batch
+    # this rank's shard of the clip: the reference's split, shard_len frames per rank (extract.py:230-232)
+    first = rank * 100000
+    frames_h = make_batch(a.clip_seed, first, B, H, W)
+    pinned = torch.from_numpy(frames_h).pin_memory()
+    frames_d = pinned.to(pipe.device)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also plans the activation arena)
+    res = None
+    for _ in range(max(a.warmup, 3)):
+        res = pipe.step_device(frames_d, first)
+    faces_per_step = len(res.rects)
+    dets_per_step = int(sum(len(d) for d in res.dets))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    fwd_ev = []
+    barrier()
+    l0 = ctx.launch_count()
+    t0 = time.time()
+    ev[0].record(stream)
+    for _ in range(a.steps):
+        pipe.step_device(frames_d, first)
+    ev[1].record(stream)
+    barrier()
+    t1 = time.time()
+    launches = ctx.launch_count() - l0
+    ms_total = ev[0].elapsed_time(ev[1])
+
+    # ---- RetinaFace forward alone, CUDA events on the launching stream (roofline) ---------
+    from facerec_b200 import ops
+    x16 = ops.preprocess_u8(ctx, frames_d, True)
+    ops.retina_forward(ctx, pipe.detector.model_id, x16)
+    torch.cuda.synchronize()
+    l1 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        ops.retina_forward(ctx, pipe.detector.model_id, x16)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    fwd_ms = e0.elapsed_time(e1) / a.steps
+    fwd_launches = (ctx.launch_count() - l1) // a.steps
+    del x16
+
+    # ---- timed region 2: end to end from pinned host frames --------------------------------
+    for _ in range(2):
+        pipe.step_device(pinned.to(pipe.device, non_blocking=True), first)
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev2[0].record(stream)
+    for _ in range(a.steps):
+        d = pinned.to(pipe.device, non_blocking=True)
+        r = pipe.step_device(d, first)
+    ev2[1].record(stream)
+    barrier()
+    t2 = time.time()
+    ms_e2e = ev2[0].elapsed_time(ev2[1])
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=pipe.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        clocks = sampler.window(t0, t1) if sampler else {}
+        if sampler:
+            sampler.stop()
+        peak, peak_src = load_peaks()
+        gflop = conv_gflop_retina(a.backbone, H, W)
+        fwd_tflops = gflop * B / fwd_ms          # GFLOP / ms = TFLOP/s
+        frames_total = world * B * a.steps
+        h2d = int(frames_h.nbytes + faces_per_step * 20)
+        d2h = int(B * pipe.max_out * 15 * 4 + 2 * B * 4 + faces_per_step * 512 * 4)
+        line = {
+            "metric": METRIC, "value": frames_total / (ms_total / 1e3), "unit": "frames/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate; heads/decode/NMS fp32)",
+            "data": "synthetic", "config": workload_config(a),
+            "faces_per_sec": world * faces_per_step * a.steps / (ms_total / 1e3),
+            "faces_per_step_per_gpu": faces_per_step, "detections_per_step_per_gpu": dets_per_step,
+            "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
+                    "api": "FacePipeline.detect_embed-equivalent: pinned host frames -> H2D -> step -> D2H dets + embeddings"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": fwd_tflops / peak, "traffic": None,
+                         "kernel": f"conv_igemm_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
+                         "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            fps, faces, dt = cpu_reference_fps(frames_h[:a.ref_frames], first, a.backbone, a.save_every, threads)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"first {a.ref_frames} frame(s) of the same batch ({dt:.1f} s of CPU work), fp32 "
+                                              f"PyTorch oracle, batch 1 per frame/face; {faces} faces embedded"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--backbone", default="r50", choices=["r50", "mnet025"])
+    ap.add_argument("--save-every", type=int, default=5)
+    ap.add_argument("--clip-seed", type=int, default=1234)
+    ap.add_argument("--ref-frames", type=int, default=1, help="frames per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "frb_num_priors": (_i, [_i, _i]),
     "frb_prior_decode_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "frb_nms": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "frb_gather_kept": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "frb_crop_resize_std": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "frb_irv1_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "frb_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _i, _i,

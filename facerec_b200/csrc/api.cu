@@ -75,6 +75,14 @@ int frb_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int
                     static_cast<cudaStream_t>(stream));
 }
 
+int frb_gather_kept(frb_ctx* ctx, const float* d_cand, const int32_t* d_keep, const int32_t* d_nkeep, int B, int max_cand,
+                    int max_out, float* d_out, int32_t* d_nout, void* stream) {
+  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_NEED(ctx, d_cand && d_keep && d_nkeep && d_out && d_nout, "frb_gather_kept: null pointer");
+  return launch_gather_kept(ctx, d_cand, d_keep, d_nkeep, B, max_cand, max_out, d_out, d_nout,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int frb_crop_resize_std(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, const int32_t* d_boxes, int F,
                         void* d_out16, void* stream) {
   if (ctx == nullptr) return FRB_ERR_INVALID;

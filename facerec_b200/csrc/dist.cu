@@ -210,7 +210,7 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
               const int rgi = p.row0 + rli;
               const bool ok = rli < p.rows && j < p.N && (p.mode == DIST_SQUARE_F32 || j > rgi);
               if (ok) {
-                const float val = mytr[r * 33 + lane];
+                const float val = j == rgi ? 0.f : mytr[r * 33 + lane];   // exact zero diagonal (square layout)
                 if (p.mode == DIST_CONDENSED_F64) static_cast<double*>(p.out)[ro + j] = static_cast<double>(val);
                 else static_cast<float*>(p.out)[ro + j] = val;
               }
@@ -318,9 +318,12 @@ __global__ void knn_merge_kernel(const float* __restrict__ part_d, const int32_t
     if (v < d[0] || (v == d[0] && j < id[0])) { d[0] = v; id[0] = j; }
   }
   const float n2 = nq[q];
-  for (int t = 0; t < k; ++t) {
-    idx[static_cast<size_t>(q) * k + t] = id[t] == 0x7fffffff ? -1 : id[t];
-    dist[static_cast<size_t>(q) * k + t] = sqrtf(fmaxf(n2 + d[t], 0.f));
+#pragma unroll
+  for (int t = 0; t < kTopK; ++t) {
+    if (t < k) {
+      idx[static_cast<size_t>(q) * k + t] = id[t] == 0x7fffffff ? -1 : id[t];
+      dist[static_cast<size_t>(q) * k + t] = sqrtf(fmaxf(n2 + d[t], 0.f));
+    }
   }
 }
 

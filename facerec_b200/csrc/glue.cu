@@ -485,6 +485,31 @@ int launch_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const 
   return check_last(ctx, "nms_kernel");
 }
 
+// Kept detections -> dense [B, max_out, 15] rows in NMS order (one small D2H instead of the whole
+// candidate buffer).  One warp per frame.
+__global__ void gather_kept_kernel(const float* __restrict__ cand, const int32_t* __restrict__ keep,
+                                   const int32_t* __restrict__ nkeep, int B, int max_cand, int max_out,
+                                   float* __restrict__ out, int32_t* __restrict__ nout) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int n = min(nkeep[b], max_out);
+  if (lane == 0) nout[b] = nkeep[b];
+  for (int t = lane; t < n * 15; t += 32) {
+    const int i = t / 15, c = t - i * 15;
+    out[(static_cast<size_t>(b) * max_out + i) * 15 + c] =
+        cand[(static_cast<size_t>(b) * max_cand + keep[static_cast<size_t>(b) * max_cand + i]) * 15 + c];
+  }
+}
+
+int launch_gather_kept(frb_ctx* ctx, const float* d_cand, const int32_t* d_keep, const int32_t* d_nkeep, int B,
+                       int max_cand, int max_out, float* d_out, int32_t* d_nout, cudaStream_t st) {
+  if (B <= 0 || max_out <= 0) return set_err(ctx, FRB_ERR_INVALID, "gather_kept: bad shape");
+  gather_kept_kernel<<<(B * 32 + 127) / 128, 128, 0, st>>>(d_cand, d_keep, d_nkeep, B, max_cand, max_out, d_out, d_nout);
+  ctx->launches++;
+  return check_last(ctx, "gather_kept_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ K8
 // crop + bilinear resize to 160x160 with cv2.resize(INTER_LINEAR) uint8 fixed-point semantics
 // (11-bit coefficients, (S>>4 * b)>>16 vertical pass, +2 >>2 rounding) + (x-127.5)/128.

@@ -106,6 +106,8 @@ int launch_prior_decode_filter(frb_ctx*, const float* d_loc, const float* d_conf
                                cudaStream_t);
 int launch_nms(frb_ctx*, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
                float iou_thr, int legacy_plus_one, int32_t* d_keep, int32_t* d_nkeep, cudaStream_t);
+int launch_gather_kept(frb_ctx*, const float* d_cand, const int32_t* d_keep, const int32_t* d_nkeep, int B, int max_cand,
+                       int max_out, float* d_out, int32_t* d_nout, cudaStream_t);
 int launch_crop_resize(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, const int32_t* d_boxes, int F,
                        int out_c, void* d_out, cudaStream_t);
 

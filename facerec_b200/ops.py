@@ -93,6 +93,15 @@ def nms(ctx: Context, cand, count, pidx, iou_thr: float = 0.4, legacy_plus_one: 
     return keep, nkeep
 
 
+def gather_kept(ctx: Context, cand, keep, nkeep, max_out: int = 128):
+    B, max_cand, _ = cand.shape
+    out = torch.empty((B, max_out, 15), dtype=torch.float32, device=cand.device)
+    nout = torch.empty((B,), dtype=torch.int32, device=cand.device)
+    ctx.check(ctx.lib.frb_gather_kept(ctx.handle, ptr(cand), ptr(keep), ptr(nkeep), B, max_cand, max_out, ptr(out), ptr(nout),
+                                      current_stream()), "frb_gather_kept")
+    return out, nout
+
+
 def crop_resize_std(ctx: Context, frames_rgb: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
     """frames [B,H,W,3] uint8 RGB, boxes [F,5] int32 (frame,x,y,w,h inside the frame) -> [F,160,160,8] 16-bit."""
     _need_cuda(frames_rgb, "frames_rgb", torch.uint8)

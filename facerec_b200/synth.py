@@ -1,0 +1,56 @@
+"""Deterministic synthetic video for benchmarks and parity tests (there is no dataset offline).
+
+`frame(seed, idx, H, W)` is counter-based: any frame of any shard is reproducible without generating
+its predecessors, which is what frame sharding (facerec/extract.py:230-234) needs.  A clip is a
+sequence of scenes separated by hard cuts; a scene is a smooth low-contrast background plus a few
+high-contrast textured blobs ("faces") that stay put, with a faint global flicker so consecutive frames
+are not byte-identical.  Random-init detectors respond to local contrast, so the blobs are what the
+calibrated RetinaFace heads fire on, and static blobs let SORT form tracks (min_hits = 3).
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+SCENE_LEN = 192          # frames between hard cuts (8 s at 24 fps)
+
+
+def _rng(*key) -> np.random.RandomState:
+    h = 1469598103
+    for k in key:
+        h = (h * 1099511 + int(k) + 12345) % (2 ** 31 - 1)
+    return np.random.RandomState(h)
+
+
+@functools.lru_cache(maxsize=4)
+def _scene(seed: int, scene: int, H: int, W: int) -> np.ndarray:
+    r = _rng(seed, scene, H, W)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    s = H / 1080.0
+    img = np.empty((H, W, 3), np.float32)
+    for c in range(3):
+        img[..., c] = (118 + 10 * np.sin(xx / (r.uniform(150, 400) * s) + r.uniform(0, 6))
+                       * np.cos(yy / (r.uniform(150, 400) * s) + r.uniform(0, 6)))
+    n_obj = r.randint(3, 9)
+    for _ in range(n_obj):
+        rad = r.uniform(25, 110) * s
+        cx, cy = r.uniform(rad, W - rad), r.uniform(rad, H - rad)
+        d2 = ((xx - cx) / rad) ** 2 + ((yy - cy) / (rad * r.uniform(1.0, 1.3))) ** 2
+        mask = np.clip(1.5 - 1.5 * d2, 0, 1)
+        fx, fy = r.uniform(0.15, 0.5) / max(s, 0.25), r.uniform(0.15, 0.5) / max(s, 0.25)
+        for c in range(3):
+            tex = 95 * np.sin(xx * fx + r.uniform(0, 6)) * np.sin(yy * fy + r.uniform(0, 6)) + r.uniform(-25, 25)
+            img[..., c] += mask * tex
+    return img
+
+
+def frame(seed: int, idx: int, H: int, W: int) -> np.ndarray:
+    """RGB uint8 [H,W,3]."""
+    base = _scene(seed, idx // SCENE_LEN, H, W)
+    flicker = 2.0 * np.sin(idx * 0.7)
+    return np.clip(base + flicker, 0, 255).astype(np.uint8)
+
+
+def clip(seed: int, start: int, n: int, H: int, W: int) -> np.ndarray:
+    return np.stack([frame(seed, start + i, H, W) for i in range(n)])

@@ -99,6 +99,12 @@ int frb_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int
             float iou_thr, int legacy_plus_one, int32_t* d_keep /*[B,max_cand]*/, int32_t* d_nkeep /*[B]*/,
             void* stream);
 
+/* K7b  kept detections of every frame -> dense rows out[b, i, :] = cand[b, keep[b, i], :] for
+ * i < min(nkeep[b], max_out); d_nout[b] = nkeep[b] (caller checks nout <= max_out).  Replaces the
+ * list comprehension input of facerec/detector.py:70 (one small D2H per batch). */
+int frb_gather_kept(frb_ctx* ctx, const float* d_cand, const int32_t* d_keep, const int32_t* d_nkeep, int B, int max_cand,
+                    int max_out, float* d_out /*[B,max_out,15]*/, int32_t* d_nout /*[B]*/, void* stream);
+
 /* K8  crop + bilinear resize (cv2.INTER_LINEAR u8 fixed-point semantics) to 160x160 +
  * fixed_image_standardization (x-127.5)/128 -> 16-bit NHWC with 8 channels (3 real + 5 zero).
  * d_boxes rows = (frame, x, y, w, h): ints AFTER the host-side cropBox clamping.
