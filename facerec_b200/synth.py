@@ -24,13 +24,16 @@ def _rng(*key) -> np.random.RandomState:
 
 
 @functools.lru_cache(maxsize=4)
-def _scene(seed: int, scene: int, H: int, W: int) -> np.ndarray:
+def _scene(seed: int, scene: int, H: int, W: int, vary_level: bool = False) -> np.ndarray:
     r = _rng(seed, scene, H, W)
+    level = 118.0
+    if vary_level:   # hard cuts that also change the frame mean: food for the scene-cut detector tests
+        level = float(_rng(seed, scene, 99).uniform(60, 190))
     yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
     s = H / 1080.0
     img = np.empty((H, W, 3), np.float32)
     for c in range(3):
-        img[..., c] = (118 + 10 * np.sin(xx / (r.uniform(150, 400) * s) + r.uniform(0, 6))
+        img[..., c] = (level + 10 * np.sin(xx / (r.uniform(150, 400) * s) + r.uniform(0, 6))
                        * np.cos(yy / (r.uniform(150, 400) * s) + r.uniform(0, 6)))
     n_obj = r.randint(3, 9)
     for _ in range(n_obj):
@@ -45,9 +48,9 @@ def _scene(seed: int, scene: int, H: int, W: int) -> np.ndarray:
     return img
 
 
-def frame(seed: int, idx: int, H: int, W: int) -> np.ndarray:
+def frame(seed: int, idx: int, H: int, W: int, vary_level: bool = False, scene_len: int = SCENE_LEN) -> np.ndarray:
     """RGB uint8 [H,W,3]."""
-    base = _scene(seed, idx // SCENE_LEN, H, W)
+    base = _scene(seed, idx // scene_len, H, W, vary_level)
     flicker = 2.0 * np.sin(idx * 0.7)
     return np.clip(base + flicker, 0, 255).astype(np.uint8)
 

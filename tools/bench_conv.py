@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--bn-cap", type=int, default=128)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring filter on the layer name")
     a = ap.parse_args()
     ctx = _lib.Context(0)
     ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
@@ -50,6 +51,8 @@ def main():
     print(f"# batch {a.batch} bn_cap {a.bn_cap} peak {peak} TFLOP/s")
     tot_f = tot_t = 0.0
     for name, H, W, Cin, Cout, k, s, p in SHAPES:
+        if a.only and a.only not in name:
+            continue
         x = torch.randn(a.batch, H, W, Cin, device="cuda").half()
         w = (np.random.RandomState(0).standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
         out, ms = ops.conv2d(ctx, x, w, None, (s, s), (p, p), 1, 0.0, iters=a.iters)

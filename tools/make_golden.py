@@ -255,13 +255,13 @@ def main():
     import scene as ref_scene
     sys.path.insert(0, ROOT)
     from facerec_b200 import synth
-    det = ref_scene.SceneChangeDetector(grayscale=False, crop=True)
+    det = ref_scene.SceneChangeDetector(grayscale=False, crop=True, movie_id=100001)
     rows = []
-    idxs = list(range(186, 200)) + list(range(380, 390))
     with contextlib.redirect_stdout(io.StringIO()):
-        for i in idxs:
-            rows.append({"index": i, "cut": bool(det.update(synth.frame(1234, i, 180, 320)))})
-    json.dump({"H": 180, "W": 320, "clip_seed": 1234, "rows": rows}, open(os.path.join(GOLD, "scene_cuts.json"), "w"))
+        for i in range(60):
+            cut = bool(det.update(synth.frame(77, i, 180, 320, vary_level=True, scene_len=7)))
+            rows.append({"index": i, "cut": cut, "prev_mafd_eq": float(det.prev_mafd_eq or 0), "prev_fv_eq": float(det.prev_fv_eq or 0)})
+    json.dump({"H": 180, "W": 320, "clip_seed": 77, "scene_len": 7, "rows": rows}, open(os.path.join(GOLD, "scene_cuts.json"), "w"))
     print("wrote", sorted(os.listdir(GOLD)))
 
 
