@@ -65,22 +65,35 @@ def all_gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], 0)
 
 
-def pdist_sharded(local_rows: torch.Tensor, ctx: Optional[Context] = None, group=None) -> Tuple[torch.Tensor, int, int]:
-    """Row-sharded pdist: all_gather the embeddings, then this rank fills its (area-balanced) row block.
+def _gpu_row_block(ctx, X: torch.Tensor, r0: int, rows: int) -> torch.Tensor:
+    """Condensed entries of rows [r0, r0+rows) (all j > i), fp32, computed by frb_pdist."""
+    n = X.shape[0]
+    beg, end = condensed_offset(n, r0), condensed_offset(n, r0 + rows)
+    # the kernel addresses a full-size condensed vector: hand it a base shifted so this block lands at 0
+    out = torch.empty((max(end - beg, 1),), dtype=torch.float32, device=X.device)
+    ctx.check(ctx.lib.frb_pdist(ctx.handle, X.data_ptr(), n, X.shape[1], r0, rows, _lib.FRB_CONDENSED_F32,
+                                out.data_ptr() - beg * 4, _lib.current_stream()), "frb_pdist")
+    return out[:end - beg]
 
-    Returns (slice of the condensed vector owned by this rank, its start offset, N)."""
+
+def pdist_sharded(local_rows: torch.Tensor, ctx: Optional[Context] = None, group=None, block_fn=None):
+    """Row-sharded pdist: all_gather the embeddings (the path's one exchange step), then this rank
+    fills its area-balanced row block.  Returns (this rank's slice of the condensed vector, its offset, N).
+    `block_fn(X, r0, rows)` computes the slice; default = the CUDA kernel (tests inject a CPU stand-in)."""
     import torch.distributed as dist
-    ctx = _ctx(ctx)
     X = all_gather_rows(local_rows, group).contiguous()
     n = X.shape[0]
     r0, rows = balanced_row_blocks(n, dist.get_world_size(group))[dist.get_rank(group)]
-    beg, end = condensed_offset(n, r0), condensed_offset(n, r0 + rows)
-    # the kernel addresses a full-size condensed vector: hand it a view shifted so that this rank's block lands at 0
-    out = torch.empty((max(end - beg, 1),), dtype=torch.float32, device=X.device)
-    base = out.data_ptr() - beg * 4
-    ctx.check(ctx.lib.frb_pdist(ctx.handle, X.data_ptr(), n, X.shape[1], r0, rows, _lib.FRB_CONDENSED_F32, base,
-                                _lib.current_stream()), "frb_pdist")
-    return out[:end - beg], beg, n
+    if block_fn is None:
+        c = _ctx(ctx)
+        block_fn = lambda X_, a, b: _gpu_row_block(c, X_, a, b)
+    return block_fn(X, r0, rows), condensed_offset(n, r0), n
+
+
+def knn_sharded(local_queries: torch.Tensor, db: torch.Tensor, k: int, ctx: Optional[Context] = None):
+    """Query-sharded kNN: every rank holds the whole database and answers its own queries; no exchange
+    is needed on the data path (the database is replicated once at load time)."""
+    return ops.knn_topk(_ctx(ctx), local_queries, db, k)
 
 
 class B200KNeighborsClassifier:

@@ -1,0 +1,344 @@
+#! /usr/bin/env python3
+"""Per-shard face extractor: the reference's facerec/extract.py on the B200 path.
+
+Same CLI flags and defaults (facerec/extract.py:376-387), same shard arithmetic with the
+`max_trajectory_age` overlap (:230-232,279), same per-frame order of operations (:301-342) and the
+same three per-shard outputs (:248-260,361-363), so `merge_shards.py`, `cluster.py` and
+`classify_knn.py` of the reference consume the result unchanged:
+
+    python -m facerec_b200.extract --n-shards 8 --shard-i $RANK --out-path ./data 100001-film.avi
+
+What differs is *how* the work is scheduled: frames are decoded into batches, RetinaFace runs once
+per batch on the GPU (the reference calls detect() per frame at batch 1), the sequential part
+(scene cut -> SORT -> 3-frame delayed validity gate -> Kalman box -> integer crop rectangle) runs
+on the host exactly in the reference's order, and the face crops of a whole batch are resized and
+embedded in one InceptionResnetV1 pass from the frames still resident in HBM.  One process per GPU;
+shards never talk to each other (the reference's SLURM-array model, scripts/extract.sh:12).
+
+The reference embeds every face with four keras_facenet models and stores one vector per model key
+(facerec/extract.py:24-25,166-167); downstream only reads `'20170512-110547'` (facerec/cluster.py:17,
+facerec/classify_knn.py:13).  Here one 512-d model runs and its vector is written under every key in
+`--emb-keys` (default: the reference's four), so readers keyed on any of them keep working.
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import json
+import os
+import sys
+from time import time
+from typing import List, Optional
+
+import numpy as np
+
+FACENET_KEYS = ["20180402-114759", "20180408-102900", "20170511-185253", "20170512-110547"]
+FACE_IMAGE_SIZE = 160
+SAVE_FACE_PADDING = 0.10
+
+
+def movie_id_from_path(path: str) -> int:
+    """Leading digits of the basename, or all digit groups joined (facerec/extract.py:237-246)."""
+    parts = os.path.splitext(os.path.basename(path))[0].split("-")
+    if parts[0].isdigit():
+        return int(parts[0])
+    return int("".join(p for p in parts if p.isdigit()))
+
+
+def shard_range(n_total: int, n_shards: int, shard_i: int, max_trajectory_age: int):
+    """[beg, end) of the shard and the overlapped end actually processed (facerec/extract.py:230-232,279)."""
+    assert 0 <= shard_i < n_shards, "Bad shard index."
+    shard_len = (n_total + n_shards - 1) // n_shards
+    beg = shard_len * shard_i
+    end = min(beg + shard_len, n_total)
+    return beg, end, min(end + max_trajectory_age, n_total)
+
+
+# --------------------------------------------------------------------------------------- frame sources
+class VideoSource:
+    """cv2.VideoCapture reader with the reference's DAR handling (facerec/extract.py:204-228,284-300)."""
+
+    def __init__(self, path: str, display_width: Optional[int] = None, display_height: Optional[int] = None):
+        import cv2
+        self.cv2 = cv2
+        self.cap = cv2.VideoCapture(path)
+        self.n_frames = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        assert self.n_frames > 0, "Invalid video file <" + path + "> cwd=" + os.getcwd()
+        self.fps = self.cap.get(cv2.CAP_PROP_FPS)
+        self.video_w = int(self.cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        self.video_h = int(self.cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        if display_width is None or display_height is None:
+            par = (self.cap.get(cv2.CAP_PROP_SAR_NUM) or 1.0) / (self.cap.get(cv2.CAP_PROP_SAR_DEN) or 1.0)
+            self.height = self.video_h
+            self.width = round(self.video_h * (self.video_w / self.video_h) * par)
+        else:
+            self.width, self.height = display_width, display_height
+
+    def seek(self, index: int):
+        assert self.cap.set(self.cv2.CAP_PROP_POS_FRAMES, index), f"Couldn't set start frame to: {index}"
+
+    def read(self) -> Optional[np.ndarray]:
+        ok, frame = self.cap.read()
+        if not ok:
+            return None
+        if self.width != self.video_w or self.height != self.video_h:
+            frame = self.cv2.resize(frame, (self.width, self.height))
+        return self.cv2.cvtColor(frame, self.cv2.COLOR_BGR2RGB)
+
+    def close(self):
+        self.cap.release()
+
+
+class SyntheticSource:
+    """facerec_b200.synth clip behind the same interface (path 'synth:<movie_id>:<n_frames>:<W>x<H>[:seed]')."""
+
+    def __init__(self, spec: str):
+        from . import synth
+        f = spec.split(":")
+        self.movie_id = int(f[1])
+        self.n_frames = int(f[2])
+        self.width, self.height = (int(v) for v in f[3].split("x"))
+        self.seed = int(f[4]) if len(f) > 4 else 1234
+        self.fps = 24.0
+        self.video_w, self.video_h = self.width, self.height
+        self._synth = synth
+        self._pos = 0
+
+    def seek(self, index: int):
+        self._pos = index
+
+    def read(self) -> Optional[np.ndarray]:
+        if self._pos >= self.n_frames:
+            return None
+        fr = self._synth.frame(self.seed, self._pos, self.height, self.width)
+        self._pos += 1
+        return fr
+
+    def close(self):
+        pass
+
+
+# --------------------------------------------------------------------------------------- writers
+def trajectory_record(trk, max_w: int, max_h: int) -> dict:
+    """One trajectories.jsonl line (facerec/extract.py:55-80); `index`/`movie_id` are added by merge_shards.py."""
+    from .pipeline import bbox_float_to_int
+    return {"start": trk.first_frame, "len": len(trk.history),
+            "bbs": [bbox_float_to_int(b, max_w, max_h) for b, _ in trk.history],
+            "detected": [bool(d) for _, d in trk.history], "w": max_w, "h": max_h, "object_type": "face"}
+
+
+def dump_line(obj, file):
+    json.dump(obj, file, indent=None, separators=(",", ":"))
+    file.write("\n")
+
+
+def save_thumbnail(img_np, filtered_box, d_width, d_height, path):
+    """Padded face thumbnail (facerec/extract.py:170-185): 10 % padded box, <=160 px, grayscale if R == G, JPEG q65."""
+    from PIL import Image, ImageOps
+    from .pipeline import bbox_float_to_int
+    padded = Image.fromarray(img_np).crop(tuple(bbox_float_to_int(filtered_box, d_width, d_height, SAVE_FACE_PADDING)))
+    padded.thumbnail((FACE_IMAGE_SIZE, FACE_IMAGE_SIZE), resample=Image.BILINEAR)
+    a = np.array(padded).reshape((-1, 3))
+    if np.all(a[:, 0] == a[:, 1]):
+        padded = ImageOps.grayscale(padded)
+    padded.save(path, quality=65)
+
+
+# --------------------------------------------------------------------------------------- the extractor
+class Extractor:
+    def __init__(self, detector, embedder, tracker, out_path: str = "./data", n_shards: int = 256, shard_i: int = 0,
+                 save_every: int = 5, min_trajectory: int = 3, max_trajectory_age: int = 5, save_images: bool = True,
+                 emb_keys: Optional[List[str]] = None, batch: int = 64, display_width=None, display_height=None):
+        self.detector, self.embedder, self.tracker = detector, embedder, tracker
+        self.out_path = out_path.rstrip("/")
+        self.n_shards, self.shard_i = n_shards, shard_i
+        self.save_every, self.min_trajectory, self.max_trajectory_age = save_every, min_trajectory, max_trajectory_age
+        self.save_images = save_images
+        self.emb_keys = list(emb_keys) if emb_keys else list(FACENET_KEYS)
+        self.batch = batch
+        self.display_width, self.display_height = display_width, display_height
+
+    def process_video(self, file: str):
+        import torch
+        from .pipeline import bbox_float_to_int
+        from .embedder import crop_rect
+        from .scene import SceneChangeDetector
+
+        synthetic = file.startswith("synth:")
+        src = SyntheticSource(file) if synthetic else VideoSource(file, self.display_width, self.display_height)
+        movie_id = src.movie_id if synthetic else movie_id_from_path(file)
+        d_width, d_height = src.width, src.height
+        beg, end, end_overlap = shard_range(src.n_frames, self.n_shards, self.shard_i, self.max_trajectory_age)
+        src.seek(beg)
+
+        base = f"{self.out_path}/{movie_id}-data"
+        dirs = {k: f"{base}/{k}" for k in ("features", "trajectories", "scene_changes", "images")}
+        for d in dirs.values():
+            os.makedirs(d, exist_ok=True)
+        suffix = f"{movie_id}_{beg}-{end}"
+        features_file = open(f"{dirs['features']}/features_{suffix}.jsonl", "w")
+        trajectories_file = open(f"{dirs['trajectories']}/trajectories_{suffix}.jsonl", "w")
+        print(f"Shard {self.shard_i + 1} / {self.n_shards}: frames {beg} - {end} (+{end_overlap - end} overlap) of "
+              f"{src.n_frames}, {d_width}x{d_height}, batches of {self.batch}, saving every 1/{self.save_every} frames")
+
+        scene = SceneChangeDetector(grayscale=False, crop=True, movie_id=movie_id)
+        tracker = self.tracker
+        scene_changes: List[int] = []
+        buf = []                      # frames waiting for their tracker verdict (min_trajectory delay)
+        counts = {"boxes": 0, "frames": 0, "traj": 0}
+        device = self.embedder.device
+        recent = {}                   # batch id -> frames on the GPU; delayed frames may live in an earlier batch
+
+        def schedule(fd, pending):
+            """process_frame_new (facerec/extract.py:140-197) up to the embedding call, which is deferred to the batch."""
+            n = 0
+            for face in fd["faces"]:
+                if not tracker.has_valid_tracker(face["detection_id"]):
+                    continue
+                box = tracker.get_detection_bbox(face["detection_id"])
+                tight = bbox_float_to_int(box, d_width, d_height)
+                x, y, w, h = crop_rect([tight[0], tight[1], tight[2] - tight[0], tight[3] - tight[1]], d_width, d_height, 16)
+                tag = fd["tag"] + ":{}_{}_{}_{}".format(*tight)
+                rec = {"frame": fd["index"], "tag": tag, "embeddings": None, "box": tight,
+                       "keypoints": face["keypoints"], "w": d_width, "h": d_height}
+                pending.append((fd["slot"], (x, y, w, h), rec))
+                if self.save_images:
+                    save_thumbnail(fd["img_np"], box, d_width, d_height, f"{dirs['images']}/{tag}.jpeg")
+                n += 1
+            counts["boxes"] += n
+            counts["frames"] += int(n > 0)
+
+        def flush(pending, batches):
+            """Embed every pending face from the GPU-resident batch it came from, then write the lines in order."""
+            for bid, frames_d in batches.items():
+                idx = [i for i, p in enumerate(pending) if p[0][0] == bid]
+                if not idx:
+                    continue
+                rects = np.array([[pending[i][0][1], *pending[i][1]] for i in idx], np.int32)
+                if ((rects[:, 3] <= 0) | (rects[:, 4] <= 0)).any():
+                    raise ValueError("empty face crop (the reference would fail in cv2.resize here)")
+                emb = self.embedder.embed_boxes(frames_d, rects)
+                for i, e in zip(idx, emb):
+                    vec = e.tolist()
+                    pending[i][2]["embeddings"] = {k: vec for k in self.emb_keys}
+            for _, _, rec in pending:
+                dump_line(rec, features_file)
+            pending.clear()
+
+        f = beg
+        batch_id = 0
+        done = False
+        while f < end_overlap and not done:
+            frames = []
+            while len(frames) < self.batch and f + len(frames) < end_overlap:
+                fr = src.read()
+                if fr is None:
+                    done = True
+                    break
+                frames.append(fr)
+            if not frames:
+                break
+            frames_h = np.stack(frames)
+            frames_d = torch.from_numpy(frames_h).to(device)
+            dets = self.detector.detect_batch_raw(frames_d)
+            pending = []
+            for b in range(len(frames)):
+                fi = f + b
+                cut = scene.update(frames_h[b])
+                faces = self.detector.format(dets[b])
+                buf.append({"index": fi, "img_np": frames_h[b], "faces": faces, "tag": f"{movie_id}:{fi}", "slot": (batch_id, b)})
+                if cut:
+                    scene_changes.append(fi)
+                    tracker.kill_trackers()
+                detections = np.array([[*face["box"], 0.95] for face in faces]).reshape((-1, 5))
+                ids = tracker.update(detections, frame=fi)
+                for i, face in enumerate(faces):
+                    face["detection_id"] = ids[i]
+                for trk in tracker.pop_expired(2 * self.min_trajectory, fi):
+                    dump_line(trajectory_record(trk, d_width, d_height), trajectories_file)
+                    counts["traj"] += 1
+                if len(buf) == self.min_trajectory:
+                    fd = buf.pop(0)
+                    if fd["index"] % self.save_every == 0:
+                        schedule(fd, pending)
+            recent[batch_id] = frames_d
+            flush(pending, recent)
+            oldest = min([fd["slot"][0] for fd in buf], default=batch_id)
+            for k in [k for k in recent if k < oldest]:
+                del recent[k]
+            f += len(frames)
+            batch_id += 1
+
+        pending = []
+        for fd in buf:
+            if fd["index"] % self.save_every == 0:
+                schedule(fd, pending)
+        flush(pending, recent)
+        for trk in tracker.pop_expired(expiry_age=0):
+            dump_line(trajectory_record(trk, d_width, d_height), trajectories_file)
+            counts["traj"] += 1
+        with open(f"{dirs['scene_changes']}/scene_changes_{suffix}.json", "w") as fh:
+            json.dump({"frame_indices": [c for c in scene_changes if beg <= c < end]}, fh, indent=None, separators=(",", ":"))
+        features_file.close()
+        trajectories_file.close()
+        src.close()
+        print(f"Saved {counts['boxes']} boxes from {counts['frames']} different frames")
+        print(f"and {counts['traj']} trajectories.")
+        return counts
+
+
+def read_display_size(file_basename: str, aspects_path: str = "aspect_ratios.csv"):
+    """Optional ./aspect_ratios.csv override (facerec/extract.py:398-413)."""
+    if not os.path.exists(aspects_path):
+        return None, None
+    with open(aspects_path, "r") as fh:
+        reader = csv.reader(fh, delimiter=",", quotechar='"')
+        headers = next(reader)
+        name_i, w_i, h_i = (headers.index(c) for c in ("filename", "display_width", "display_height"))
+        for row in reader:
+            if row[name_i] == file_basename:
+                return int(row[w_i]), int(row[h_i])
+    return None, None
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(allow_abbrev=True, formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    p.add_argument("--n-shards", type=int, default=256, help="sets the number of shards")
+    p.add_argument("--shard-i", type=int, required=True, help="indicates specific shard")
+    p.add_argument("--save-every", type=int, default=5, help="interval between saved frame images")
+    p.add_argument("--iou-threshold", type=float, default=0.5, help="required area overlap between matches")
+    p.add_argument("--min-trajectory", type=int, default=3, help="minimum allowed trajectory length")
+    p.add_argument("--max-trajectory-age", type=int, default=5, help="maximum allowed break in trajectory")
+    p.add_argument("--min-face-size", type=int, default=20, help="minimum allowed face size in unknown units")
+    p.add_argument("--face-threshold", type=float, default=0.95, help="minimum allowed face detection score")
+    p.add_argument("--out-path", type=str, default="./data", help="storage directory")
+    p.add_argument("--no-images", action="store_true", help="if set, no images are stored")
+    # additions of the B200 path
+    p.add_argument("--backbone", default="r50", choices=["r50", "mnet025"], help="RetinaFace backbone")
+    p.add_argument("--batch", type=int, default=64, help="frames per GPU batch")
+    p.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")), help="CUDA device of this shard")
+    p.add_argument("--emb-keys", nargs="*", default=FACENET_KEYS, help="keys the embedding is stored under")
+    p.add_argument("--weight-seed", type=int, default=0, help="seed of the random-init weights (no checkpoints offline)")
+    p.add_argument("file")
+    args = p.parse_args(argv)
+
+    start = time()
+    from ._lib import Context
+    from .detector import B200RetinaFaceDetector
+    from .embedder import B200FaceNet
+    from .sort import Sort
+    ctx = Context(args.device)
+    detector = B200RetinaFaceDetector(args.min_face_size, args.backbone, seed=args.weight_seed,
+                                      threshold=args.face_threshold, ctx=ctx)
+    embedder = B200FaceNet(seed=args.weight_seed, ctx=ctx)
+    tracker = Sort(max_age=args.max_trajectory_age, min_hits=args.min_trajectory, iou_threshold=args.iou_threshold)
+    dw, dh = read_display_size(os.path.basename(args.file))
+    ex = Extractor(detector, embedder, tracker, args.out_path, args.n_shards, args.shard_i, args.save_every,
+                   args.min_trajectory, args.max_trajectory_age, not args.no_images, args.emb_keys, args.batch, dw, dh)
+    ex.process_video(args.file)
+    minutes, seconds = divmod(time() - start, 60)
+    print(f"Completed in {int(minutes)} minutes, {int(seconds)} seconds.")
+
+
+if __name__ == "__main__":
+    main()

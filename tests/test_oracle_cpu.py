@@ -1,0 +1,197 @@
+"""CPU suite: pins of the oracle against the libraries the reference calls, the weight blob, the C-ABI export list
+and the multi-rank host logic (gloo, world size 2).  No GPU compute here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_resize_restatement_is_bit_exact_with_cv2():
+    import cv2
+    from oracle import crop
+    rng = np.random.RandomState(0)
+    for _ in range(120):
+        h, w = rng.randint(1, 420), rng.randint(1, 420)
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(cv2.resize(img, (160, 160), interpolation=cv2.INTER_LINEAR), crop.resize_linear_u8(img))
+    assert np.array_equal(crop.standardize(np.array([[0, 255]], np.uint8)), np.array([[-127.5 / 128, 127.5 / 128]], np.float32))
+
+
+def test_crop_box_matches_product_crop_rect():
+    from oracle import crop
+    from facerec_b200.embedder import crop_rect, cropBox
+    rng = np.random.RandomState(1)
+    img = rng.randint(0, 256, (90, 120, 3)).astype(np.uint8)
+    for _ in range(200):
+        box = [int(rng.randint(-5, 110)), int(rng.randint(-5, 85)), int(rng.randint(1, 80)), int(rng.randint(1, 80))]
+        assert crop.crop_rect(box, 120, 90, 16) == crop_rect(box, 120, 90, 16)
+        a, b = crop.crop_box(img, box, 16), cropBox(img, {"box": box}, 16)
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_nms_oracle_matches_torchvision():
+    import torchvision
+    from oracle import postproc
+    rng = np.random.RandomState(2)
+    for n in (1, 7, 60, 300):
+        xy = rng.uniform(0, 300, (n, 2)).astype(np.float32)
+        wh = rng.uniform(10, 90, (n, 2)).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], 1)
+        scores = rng.uniform(0.95, 1, n).astype(np.float32)
+        keep = postproc.nms(boxes, scores, np.arange(n), 0.4, plus_one=False)
+        ref = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.4).numpy()
+        assert np.array_equal(keep, ref)
+
+
+def test_priorbox_layout_and_decode_identity():
+    from oracle import postproc
+    for H, W in ((360, 640), (1080, 1920), (135, 97)):
+        pri = postproc.priorbox(H, W)
+        assert len(pri) == postproc.num_priors(H, W)
+    assert postproc.num_priors(360, 640) == 9520 and postproc.num_priors(1080, 1920) == 85200
+    pri = postproc.priorbox(360, 640)
+    # level 0, cell (0,0): centre (4,4) px, anchors 16 and 32 px
+    assert np.allclose(pri[0] * [640, 360, 640, 360], [4, 4, 16, 16]) and np.allclose(pri[1] * [640, 360, 640, 360], [4, 4, 32, 32])
+    boxes, lm = postproc.decode(np.zeros((len(pri), 4), np.float32), np.zeros((len(pri), 10), np.float32), pri, 360, 640)
+    assert np.allclose(boxes[0], [-4, -4, 12, 12], atol=1e-4) and np.allclose(lm[0], [4, 4] * 5, atol=1e-4)
+    s = postproc.face_scores(np.array([[0.0, np.log(19.0)]], np.float32))
+    assert abs(float(s[0]) - 0.95) < 1e-6
+
+
+def test_detect_post_filter_follows_reference_wrapper():
+    from oracle import postproc
+    d = np.zeros((2, 15), np.float32)
+    d[0, :5] = [10.2, 20.7, 50.9, 39.9, 0.99]           # min side 19.2 -> dropped at min_size 20
+    d[1, :5] = [10.2, 20.7, 50.9, 41.0, 0.99]
+    d[1, 5:] = np.arange(10) + 0.9
+    out = postproc.detect_from_dets(d, 20)
+    assert len(out) == 1 and out[0]["keypoints"]["left_eye"] == (0, 1) and out[0]["keypoints"]["mouth_right"] == (8, 9)
+    assert all(isinstance(v, float) for v in out[0]["box"])
+
+
+def test_weight_factory_and_blob_roundtrip():
+    from facerec_b200 import weights as W
+    w = W.synth_weights("retina_mnet025", 3)
+    w2 = W.synth_weights("retina_mnet025", 3)
+    assert all(np.array_equal(w[k], w2[k]) for k in w)
+    assert sum(v.size for v in w.values()) == 423264
+    r = W.read_blob(W.write_blob(w))
+    assert list(r) == list(w) and all(np.array_equal(r[k], w[k]) for k in w)
+    specs = {s.name: s for s in W.model_specs("irv1")}
+    assert len(specs) == 133 and specs["repeat_2.3.branch1.1"].kw == 7 and specs["last_linear"].cout == 512
+    assert sum(int(np.prod([s.cout, s.kh, s.kw, s.cin])) + s.cout for s in W.model_specs("retina_r50")) == 27264608
+
+
+def test_fold_bn_equals_torch_batchnorm_eval():
+    from facerec_b200 import weights as W
+    rng = np.random.RandomState(0)
+    w = rng.standard_normal((6, 3, 3, 4)).astype(np.float32)
+    g, b, m, v = (rng.uniform(0.5, 1.5, 6).astype(np.float32) for _ in range(4))
+    wf, bf = W.fold_bn(w, g, b, m, v, 1e-3)
+    x = torch.randn(2, 4, 9, 9)
+    bn = torch.nn.BatchNorm2d(6, eps=1e-3).eval()
+    bn.weight.data, bn.bias.data = torch.from_numpy(g), torch.from_numpy(b)
+    bn.running_mean.data, bn.running_var.data = torch.from_numpy(m), torch.from_numpy(v)
+    ref = bn(torch.nn.functional.conv2d(x, torch.from_numpy(w).permute(0, 3, 1, 2)))
+    got = torch.nn.functional.conv2d(x, torch.from_numpy(wf).permute(0, 3, 1, 2), torch.from_numpy(bf))
+    assert torch.allclose(ref, got, atol=1e-5)
+
+
+def test_oracle_networks_shapes():
+    from facerec_b200 import weights as W
+    from oracle import nets, postproc
+    P = nets.params_from_weights(W.synth_weights("retina_mnet025", 0))
+    with torch.no_grad():
+        loc, conf, landm = nets.retina_forward(P, torch.zeros(1, 3, 97, 135), "mnet025")
+    n = postproc.num_priors(97, 135)
+    assert loc.shape == (1, n, 4) and conf.shape == (1, n, 2) and landm.shape == (1, n, 10)
+
+
+def test_library_exports_every_header_symbol():
+    """The C-ABI library loads (no GPU needed) and exports exactly what include/facerec_b200.h declares."""
+    import ctypes
+    from facerec_b200 import _lib, build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "facerec_b200.h")).read()
+    declared = set(re.findall(r"\b(frb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.frb_version() == 100
+    assert lib.frb_num_priors(1080, 1920) == 85200
+
+
+def test_product_fails_loudly_without_gpu():
+    from facerec_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.FrbError):
+        _lib.Context(0)
+
+
+def test_product_never_imports_oracle():
+    for root, _, names in os.walk(os.path.join(ROOT, "facerec_b200")):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, n)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), n
+
+
+def test_balanced_row_blocks_cover_the_triangle():
+    from facerec_b200.distance import balanced_row_blocks, condensed_offset
+    for n, parts in ((50000, 8), (1000, 3), (7, 8), (2, 2)):
+        blocks = balanced_row_blocks(n, parts)
+        assert blocks[0][0] == 0 and sum(r for _, r in blocks) == n
+        assert all(blocks[i][0] + blocks[i][1] == blocks[i + 1][0] for i in range(parts - 1))
+        if n >= 1000:
+            areas = [condensed_offset(n, a + r) - condensed_offset(n, a) for a, r in blocks]
+            assert max(areas) / (sum(areas) / parts) < 1.01
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from scipy.spatial.distance import pdist
+from facerec_b200 import distance
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"], rank=rank, world_size=world)
+rng = np.random.RandomState(0)
+X = rng.standard_normal((301, 32)).astype(np.float32)
+lo, hi = (0, 130) if rank == 0 else (130, 301)          # ragged shards, as produced by frame sharding
+def cpu_block(Xa, r0, rows):
+    n = Xa.shape[0]
+    full = pdist(Xa.numpy().astype(np.float64)).astype(np.float32)
+    return torch.from_numpy(full[distance.condensed_offset(n, r0):distance.condensed_offset(n, r0 + rows)])
+sl, off, n = distance.pdist_sharded(torch.from_numpy(X[lo:hi]), group=None, block_fn=cpu_block)
+assert n == 301
+ref = pdist(X.astype(np.float64)).astype(np.float32)
+assert np.array_equal(sl.numpy(), ref[off:off + len(sl)])
+parts = [None, None]
+dist.all_gather_object(parts, (off, sl.numpy()))
+if rank == 0:
+    whole = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+    assert np.array_equal(whole, ref)
+    print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_row_sharded_pdist_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0][0]

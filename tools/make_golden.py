@@ -265,5 +265,117 @@ def main():
     print("wrote", sorted(os.listdir(GOLD)))
 
 
+# ---------------------------------------------------------------------------------------------------------
+# 7. the reference's own process_video loop (facerec/extract.py:199-369) driven with scripted fakes
+def scripted_faces(index, n_frames=48):
+    """Deterministic per-frame detections (the fake detector's answer), keyed by frame index."""
+    script = detection_script(11, n_frames)
+    out = []
+    for d in script[index % n_frames]["dets"]:
+        x1, y1, x2, y2 = (float(np.float32(v)) for v in d[:4])
+        kp = {n: (int(x1 + (i + 1) * (x2 - x1) / 6), int(y1 + (y2 - y1) / 2)) for i, n in
+              enumerate(["left_eye", "right_eye", "nose", "mouth_left", "mouth_right"])}
+        out.append({"box": [x1, y1, x2, y2], "keypoints": kp})
+    return out
+
+
+def frame_index_of(img):
+    """Frames of the fixture clip carry their index in the blue channel of the top-left 4x4 block."""
+    return int(img[0, 0, 2]) + 256 * int(img[0, 4, 2])
+
+
+def fake_embedding(crop):
+    c = crop.astype(np.float64)
+    return np.array([c.mean(), c[..., 0].mean(), c[..., 2].std(), crop.shape[0], crop.shape[1], float(crop[0, 0, 1]),
+                     float(crop[-1, -1, 0]), 1.0], dtype=np.float32)
+
+
+def fixture_clip_frames(n=48, H=180, W=320):
+    sys.path.insert(0, ROOT)
+    from facerec_b200 import synth
+    out = []
+    for i in range(n):
+        f = synth.frame(77, i, H, W, vary_level=True, scene_len=17).copy()
+        f[0:4, 0:4, 2] = i % 256
+        f[0:4, 4:8, 2] = i // 256
+        out.append(f)
+    return out
+
+
+def write_fixture_clip(path, frames):
+    import cv2
+    H, W = frames[0].shape[:2]
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), 24.0, (W, H))
+    assert vw.isOpened()
+    for f in frames:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    vw.release()
+
+
+def run_reference_extract(reference):
+    ref = os.path.join(reference, "facerec")
+    for name in ("tensorflow", "mtcnn", "retinaface", "keras_facenet", "keras_facenet.utils"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["mtcnn"].MTCNN = object
+    sys.modules["retinaface"].RetinaFace = object
+
+    def cropBox(image, detection, margin):      # keras_facenet.utils.cropBox semantics (SURVEY App. B.3)
+        x, y, w, h = detection["box"]
+        x -= margin; y -= margin; w += 2 * margin; h += 2 * margin
+        if x < 0:
+            w += x; x = 0
+        if y < 0:
+            h += y; y = 0
+        return image[y:y + h, x:x + w]
+
+    class FaceNet:
+        def __init__(self, key=None):
+            self.key = key
+
+        def embeddings(self, crops):
+            return np.stack([fake_embedding(c) for c in crops])
+
+    sys.modules["keras_facenet"].FaceNet = FaceNet
+    sys.modules["keras_facenet.utils"].cropBox = cropBox
+    sys.modules["keras_facenet"].utils = sys.modules["keras_facenet.utils"]
+    import importlib
+    extract = importlib.import_module("extract")
+
+    class FakeDetector:
+        def detect(self, img):
+            return scripted_faces(frame_index_of(img))
+
+    gold = {}
+    tmp = tempfile.mkdtemp()
+    try:
+        frames = fixture_clip_frames()
+        clip = os.path.join(tmp, "100002-fixture.avi")
+        write_fixture_clip(clip, frames)
+        for n_shards, shard_i in ((1, 0), (2, 0), (2, 1)):
+            import sort as ref_sort
+            ref_sort.KalmanBoxTracker.count = 0
+            extract.detector = FakeDetector()
+            extract.embedders = {k: FaceNet(k) for k in extract.facenet_models}
+            extract.multi_tracker = ref_sort.Sort(max_age=5, min_hits=3, iou_threshold=0.5)
+            out = os.path.join(tmp, f"out_{n_shards}_{shard_i}")
+            opt = extract.Options(out_path=out, n_shards=n_shards, shard_i=shard_i, save_every=5, min_trajectory=3,
+                                  display_width=None, display_height=None, max_trajectory_age=5, save_images=False)
+            with contextlib.redirect_stdout(io.StringIO()):
+                extract.process_video(clip, opt)
+            files = {}
+            for root, _, names in os.walk(out):
+                for nme in names:
+                    files[os.path.relpath(os.path.join(root, nme), out)] = open(os.path.join(root, nme)).read()
+            gold[f"{n_shards}_{shard_i}"] = files
+    finally:
+        shutil.rmtree(tmp)
+    json.dump(gold, open(os.path.join(GOLD, "extract_runs.json"), "w"))
+    print("extract golden:", {k: {n: len(v) for n, v in f.items()} for k, f in gold.items()})
+
+
 if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ns = ap.parse_args()
     main()
+    run_reference_extract(ns.reference)
