@@ -1,0 +1,316 @@
+// K2 (main variant) — implicit-GEMM convolution with BOTH operands and the output moved by TMA.
+//
+// The im2col never exists in memory and no thread computes an address for it: the output is tiled
+// into spatial patches of bb x bh x bw = 128 pixels (or 128 consecutive pixels for 1x1 convs), and for
+// every filter tap (r, s) and 64-channel block the A operand of the patch is ONE 4-D tensor-map box
+//   [64 ch, bw (stride sw), bh (stride sh), bb]   at   (c0, w0*sw - pw + s, h0*sh - ph + r, b0)
+// which TMA delivers straight into the 128-byte-swizzled K-major layout tcgen05.mma consumes; padding
+// and ragged image borders are the tensor map's out-of-bounds zero fill.  Weights come the same way
+// (2-D box of the [Cout, K] matrix).  Accumulators live in TMEM (double buffered, 2 x BN columns), and
+// the epilogue (bias, residual, per-channel slope) packs 64-column slabs into a swizzled staging tile
+// that TMA stores back as the same patch box — partial tiles are clipped by the hardware, and every
+// global store is a full 128-byte line.  The residual tile (ResNet / Inception skip) is prefetched by
+// TMA into shared memory while the tile's MMAs are still running.
+//
+// Warp roles (192 threads): 0-3 epilogue (TMEM lane quarter = warp id), 4 MMA issuer + TMEM allocator,
+// 5 TMA producer.  Persistent: one CTA per SM walks tiles round-robin (n fastest, so CTAs running at
+// the same time share the A patch through L2).
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace frb {
+
+constexpr int kTmaThreads = 192;
+constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
+constexpr int kSlabBytes = kBM * kSlab * 2;
+
+struct ConvTmaArgs {
+  int patch;             // 0: linear M tiling (1x1, stride 1, no padding); 1: spatial patch tiling
+  int kw, sh, sw, ph, pw;
+  int cin_blocks;        // 64-channel blocks per filter tap
+  int num_kb;            // kh*kw*cin_blocks
+  int BN, n_tiles, total_tiles;
+  int tiles_w, tiles_h;  // patch grid inside an image group
+  int bw, bh, bb;        // patch = bb images x bh rows x bw cols (<= 128 pixels)
+  int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
+  int stages;
+  const float* bias;     // [n_tiles*BN]
+  const float* slope;    // [n_tiles*BN]
+  int res_mode;          // ConvRes: PRE_ACT comes through tmR; POST_ACT_UPSAMPLE (linear tiling only) from global
+  const void* res;       // POST_ACT_UPSAMPLE source
+  int res_ld, rH, rW, Ho, Wo, M;
+  int* watchdog;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmR) {
+  using E = Elem16<kBF16>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int b_stage_bytes = p.BN * 128;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
+  uint8_t* smem_o = smem_b + p.stages * b_stage_bytes;          // 2 staging slabs
+  uint8_t* smem_r = smem_o + 2 * kSlabBytes;                    // 2 residual slabs (PRE_ACT only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (p.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0));
+  uint64_t* full_bar = bars;                          // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]
+  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * p.BN)) tmem_cols <<= 1;
+
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (p.res_mode == RES_PRE_ACT) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tfull_bar[b], 1);
+        mbar_init(&tempty_bar[b], 4);
+        mbar_init(&res_bar[b], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nslab = (p.BN + kSlab - 1) / kSlab;
+
+  // tile -> coordinates of its first pixel
+  auto decode = [&](int tile, int& n_tile, int& c1, int& c2, int& c3) {
+    const int m_tile = tile / p.n_tiles;
+    n_tile = tile - m_tile * p.n_tiles;
+    if (p.patch) {
+      const int tw = m_tile % p.tiles_w;
+      const int t = m_tile / p.tiles_w;
+      c1 = tw * p.bw;
+      c2 = (t % p.tiles_h) * p.bh;
+      c3 = (t / p.tiles_h) * p.bb;
+    } else {
+      c1 = m_tile * kBM;
+      c2 = 0;
+      c3 = 0;
+    }
+  };
+
+  if (warp < 4) {
+    // ================================================================ epilogue
+    const int row = warp * 32 + lane;
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw7 = static_cast<uint32_t>(row & 7);
+    int tile_iter = 0;
+    uint32_t slab_ctr = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
+      int n_tile, c1, c2, c3;
+      decode(tile, n_tile, c1, c2, c3);
+      const int n_base = n_tile * p.BN;
+      const int buf = tile_iter & 1;
+      const uint32_t tphase = (tile_iter >> 1) & 1;
+
+      if (p.res_mode == RES_PRE_ACT && threadIdx.x == 0) {
+        // both residual slabs were consumed before the last named barrier of the previous tile
+        for (int s = 0; s < nslab; ++s) {
+          mbar_arrive_expect_tx(&res_bar[s], static_cast<uint32_t>(p.a_bytes));
+          if (p.patch) tma_load_4d(smem_r + s * kSlabBytes, &tmR, &res_bar[s], n_base + s * kSlab, c1, c2, c3);
+          else tma_load_2d(smem_r + s * kSlabBytes, &tmR, &res_bar[s], n_base + s * kSlab, c1);
+        }
+      }
+      const typename E::T* up_row = nullptr;
+      if (p.res_mode == RES_POST_ACT_UPSAMPLE) {
+        const int m = c1 + row;
+        if (m < p.M) {
+          const int ow = m % p.Wo;
+          const int t = m / p.Wo;
+          const int oh = t % p.Ho;
+          const int b = t / p.Ho;
+          const int rh = (oh * p.rH) / p.Ho;   // nearest: floor(dst * in / out)
+          const int rw = (ow * p.rW) / p.Wo;
+          up_row = static_cast<const typename E::T*>(p.res) +
+                   (static_cast<size_t>(b) * p.rH * p.rW + static_cast<size_t>(rh) * p.rW + rw) * p.res_ld;
+        }
+      }
+
+      mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
+
+      for (int s = 0; s < nslab; ++s) {
+        const int ncols = min(kSlab, p.BN - s * kSlab);
+        const int n0 = n_base + s * kSlab;
+        float x[kSlab];
+#pragma unroll
+        for (int c0 = 0; c0 < kSlab; c0 += 16) {
+          if (c0 < ncols) {                       // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(taddr + s * kSlab + c0, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+              x[c0 + j + 0] = __uint_as_float(v[j + 0]) + bz.x;
+              x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bz.y;
+              x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bz.z;
+              x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bz.w;
+            }
+          }
+        }
+        if (s == nslab - 1) {                     // accumulator fully read: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        if (p.res_mode == RES_PRE_ACT) {
+          mbar_wait(&res_bar[s], tile_iter & 1, p.watchdog, 500 + s);
+          const uint8_t* rrow = smem_r + s * kSlabBytes + row_off;
+#pragma unroll
+          for (int c = 0; c < kSlab / 8; ++c) {
+            if (c * 8 < ncols) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(c) ^ sw7) << 4));
+              float2 f;
+              f = E::to_f2(r.x); x[c * 8 + 0] += f.x; x[c * 8 + 1] += f.y;
+              f = E::to_f2(r.y); x[c * 8 + 2] += f.x; x[c * 8 + 3] += f.y;
+              f = E::to_f2(r.z); x[c * 8 + 4] += f.x; x[c * 8 + 5] += f.y;
+              f = E::to_f2(r.w); x[c * 8 + 6] += f.x; x[c * 8 + 7] += f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < kSlab; c0 += 4) {
+          if (c0 < ncols) {
+            const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + c0));
+            x[c0 + 0] = x[c0 + 0] > 0.f ? x[c0 + 0] : x[c0 + 0] * sl.x;
+            x[c0 + 1] = x[c0 + 1] > 0.f ? x[c0 + 1] : x[c0 + 1] * sl.y;
+            x[c0 + 2] = x[c0 + 2] > 0.f ? x[c0 + 2] : x[c0 + 2] * sl.z;
+            x[c0 + 3] = x[c0 + 3] > 0.f ? x[c0 + 3] : x[c0 + 3] * sl.w;
+          }
+        }
+        if (p.res_mode == RES_POST_ACT_UPSAMPLE && up_row != nullptr) {
+#pragma unroll
+          for (int c = 0; c < kSlab / 8; ++c) {
+            if (c * 8 < ncols) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(up_row + n0 + c * 8));
+              float2 f;
+              f = E::to_f2(r.x); x[c * 8 + 0] += f.x; x[c * 8 + 1] += f.y;
+              f = E::to_f2(r.y); x[c * 8 + 2] += f.x; x[c * 8 + 3] += f.y;
+              f = E::to_f2(r.z); x[c * 8 + 4] += f.x; x[c * 8 + 5] += f.y;
+              f = E::to_f2(r.w); x[c * 8 + 6] += f.x; x[c * 8 + 7] += f.y;
+            }
+          }
+        }
+        // staging slab `ob` is free once the store issued two slabs ago has finished reading it
+        const uint32_t ob = slab_ctr & 1u;
+        if (threadIdx.x == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* orow = smem_o + ob * kSlabBytes + row_off;
+#pragma unroll
+        for (int c = 0; c < kSlab / 8; ++c) {
+          if (c * 8 < ncols) {
+            uint4 o;
+            o.x = E::from_f2(x[c * 8 + 0], x[c * 8 + 1]);
+            o.y = E::from_f2(x[c * 8 + 2], x[c * 8 + 3]);
+            o.z = E::from_f2(x[c * 8 + 4], x[c * 8 + 5]);
+            o.w = E::from_f2(x[c * 8 + 6], x[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(c) ^ sw7) << 4)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+          if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
+          else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
+          tma_store_commit();
+        }
+        ++slab_ctr;
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait<0>();     // stores must land before the CTA (and its smem) goes away
+  } else if (warp == 4) {
+    // ============================================================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(kBM, p.BN, kBF16 ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int tile_iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int buf = tile_iter & 1;
+      const uint32_t tphase = (tile_iter >> 1) & 1;
+      mbar_wait(&tempty_bar[buf], tphase ^ 1, p.watchdog, 200 + buf);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, p.watchdog, 210 + stage);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kAStageBytes));
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * b_stage_bytes));
+#pragma unroll
+          for (int k4 = 0; k4 < kBK / 16; ++k4)
+            tc_mma_f16(d_tmem, a_desc + static_cast<uint64_t>(k4 * 2), b_desc + static_cast<uint64_t>(k4 * 2), idesc,
+                       (kb | k4) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[stage]);
+          if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================================================ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(b_stage_bytes + p.a_bytes);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n_tile, c1, c2, c3;
+      decode(tile, n_tile, c1, c2, c3);
+      const int aw = c1 * p.sw - p.pw, ah = c2 * p.sh - p.ph;
+      int tap_r = 0, tap_s = 0, cb = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.watchdog, 300 + stage);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, &full_bar[stage], kb * kBK, n_tile * p.BN);
+          if (p.patch) tma_load_4d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBK, aw + tap_s, ah + tap_r, c3);
+          else tma_load_2d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], kb * kBK, c1);
+        }
+        __syncwarp();
+        if (++cb == p.cin_blocks) {
+          cb = 0;
+          if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  // -------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace frb

@@ -5,6 +5,7 @@
 
 #include "host.h"
 #include "conv_igemm.cuh"
+#include "conv_tma.cuh"
 
 namespace frb {
 
@@ -59,6 +60,9 @@ int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out) {
 static int pick_bn(int cout_pad16, int cap) {
   cap = std::max(16, std::min(256, cap)) & ~15;
   if (cout_pad16 <= cap) return cout_pad16;
+  // several N tiles: keep tiles a multiple of the 64-column store slab
+  for (int bn = cap & ~63; bn >= 64; bn -= 64)
+    if (cout_pad16 % bn == 0) return bn;
   for (int bn = cap; bn >= 16; bn -= 16)
     if (cout_pad16 % bn == 0 && bn >= cap / 2) return bn;
   return cap;  // no good divisor: pad Cout up to a multiple of cap
@@ -100,7 +104,7 @@ int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bi
   L.K = L.kh * L.kw * L.Cin;
   L.K_pad = (L.K + kBK - 1) / kBK * kBK;
   const int cout16 = (L.Cout + 15) / 16 * 16;
-  L.BN = pick_bn(cout16, ctx->bn_cap);
+  L.BN = pick_bn(cout16, L.bn_cap > 0 ? std::min(L.bn_cap, ctx->bn_cap) : ctx->bn_cap);
   L.n_tiles = (cout16 + L.BN - 1) / L.BN;
   L.Cout_pad = L.n_tiles * L.BN;
 
@@ -132,6 +136,127 @@ void conv_release(ConvLayer& L) {
   L.d_w = nullptr;
   L.d_bias = nullptr;
   L.d_slope = nullptr;
+}
+
+typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// rank-n tiled map over 16-bit elements, 128-byte swizzle; strides[i] is the byte stride of dim i+1
+static int encode_nd(frb_ctx* ctx, CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, const uint32_t* estr) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+  CUresult r = ctx->encode_tiled(tm, ctx->use_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                 static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, b, e,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(ctx, FRB_ERR_CUDA, "cuTensorMapEncodeTiled(rank %d) failed (%d): dims %llu %llu %llu %llu box %u %u %u %u",
+                   rank, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+                   rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return FRB_OK;
+}
+
+// NHWC activation slice [B,H,W,C] (pixel stride ld) as a 4-D map with a patch box
+static int encode_patch(frb_ctx* ctx, CUtensorMap* tm, const void* base, int C, int W, int H, int B, int ld, int bw, int bh,
+                        int bb, int sw, int sh) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  const uint32_t box[4] = {(uint32_t)kSlab, (uint32_t)((bw - 1) * sw + 1), (uint32_t)((bh - 1) * sh + 1), (uint32_t)bb};
+  const uint32_t est[4] = {1, (uint32_t)sw, (uint32_t)sh, 1};
+  return encode_nd(ctx, tm, base, 4, dims, str, box, est);
+}
+
+// Spatial patch of <= 128 output pixels that wastes the fewest tile slots.
+static void pick_patch(int B, int Ho, int Wo, int sw, int sh, int& bw, int& bh, int& bb) {
+  double best = -1.0;
+  bw = bh = bb = 1;
+  for (int w = 1; w <= std::min(Wo, 128); ++w) {
+    if ((w - 1) * sw + 1 > 256) break;
+    for (int h = 1; h <= std::min(Ho, 128 / w); ++h) {
+      if ((h - 1) * sh + 1 > 256) break;
+      const int b = std::max(1, std::min(B, 128 / (w * h)));
+      const double tiles = static_cast<double>((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((B + b - 1) / b);
+      const double eff = static_cast<double>(B) * Ho * Wo / (tiles * 128.0) + 1e-6 * w;
+      if (eff > best) { best = eff; bw = w; bh = h; bb = b; }
+    }
+  }
+}
+
+static bool tma_path_ok(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io) {
+  if (ctx->force_gather || io.out_mode != OUT_16BIT) return false;
+  const bool linear = L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0;
+  if (!linear && (L.Cin % kBK) != 0) return false;                 // taps are fetched as whole 64-channel blocks
+  if (!linear && io.res_mode == RES_POST_ACT_UPSAMPLE) return false;
+  if (L.n_tiles > 1 && (L.BN % kSlab) != 0) return false;          // store slabs must not spill into the next N tile
+  if (io.res_mode == RES_PRE_ACT && L.BN > 2 * kSlab) return false;  // two residual slabs are staged per tile
+  return true;
+}
+
+static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream) {
+  ConvTmaArgs a;
+  memset(&a, 0, sizeof(a));
+  const int Ho = conv_out_dim(io.H, L.kh, L.sh, L.ph), Wo = conv_out_dim(io.W, L.kw, L.sw, L.pw);
+  const long long M = static_cast<long long>(io.B) * Ho * Wo;
+  if (M <= 0 || M > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv: bad problem size");
+  const bool linear = L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0;
+  a.patch = linear ? 0 : 1;
+  a.kw = L.kw; a.sh = L.sh; a.sw = L.sw; a.ph = L.ph; a.pw = L.pw;
+  a.cin_blocks = (L.Cin + kBK - 1) / kBK;
+  a.num_kb = L.kh * L.kw * a.cin_blocks;
+  a.BN = L.BN; a.n_tiles = L.n_tiles;
+  a.bias = L.d_bias; a.slope = L.d_slope;
+  a.res_mode = io.res_mode; a.res = io.res; a.res_ld = io.res_ld; a.rH = io.rH; a.rW = io.rW;
+  a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M);
+  a.watchdog = ctx->wd_dev;
+
+  CUtensorMap tmA, tmO, tmR;
+  memset(&tmR, 0, sizeof(tmR));
+  int rc;
+  long long m_tiles;
+  if (linear) {
+    m_tiles = (M + kBM - 1) / kBM;
+    a.a_bytes = kAStageBytes;
+    a.bw = kBM; a.bh = 1; a.bb = 1; a.tiles_w = 1; a.tiles_h = 1;
+    if ((rc = encode_2d(ctx, &tmA, io.in, L.Cin, M, static_cast<uint64_t>(io.in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
+    if ((rc = encode_2d(ctx, &tmO, io.out, L.Cout, M, static_cast<uint64_t>(io.out_ld) * 2, kSlab, kBM)) != FRB_OK) return rc;
+    if (io.res_mode == RES_PRE_ACT &&
+        (rc = encode_2d(ctx, &tmR, io.res, L.Cout, M, static_cast<uint64_t>(io.res_ld) * 2, kSlab, kBM)) != FRB_OK)
+      return rc;
+  } else {
+    pick_patch(io.B, Ho, Wo, L.sw, L.sh, a.bw, a.bh, a.bb);
+    a.tiles_w = (Wo + a.bw - 1) / a.bw;
+    a.tiles_h = (Ho + a.bh - 1) / a.bh;
+    m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * ((io.B + a.bb - 1) / a.bb);
+    a.a_bytes = a.bw * a.bh * a.bb * 128;
+    if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
+    if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
+    if (io.res_mode == RES_PRE_ACT &&
+        (rc = encode_patch(ctx, &tmR, io.res, L.Cout, Wo, Ho, io.B, io.res_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK)
+      return rc;
+  }
+  if (m_tiles * L.n_tiles > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv: too many tiles");
+  a.total_tiles = static_cast<int>(m_tiles * L.n_tiles);
+
+  const int stage_bytes = kAStageBytes + L.BN * 128;
+  const int fixed = 2 * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 6) * 8 + 16 + 1024;
+  const int budget = 226 * 1024 - fixed;
+  a.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+  const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
+  const int grid = std::min(a.total_tiles, ctx->num_sms);
+  if (ctx->use_bf16) {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tma_kernel<true><<<grid, kTmaThreads, smem, stream>>>(a, tmA, L.tmB, tmO, tmR);
+  } else {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tma_kernel<false><<<grid, kTmaThreads, smem, stream>>>(a, tmA, L.tmB, tmO, tmR);
+  }
+  ctx->launches++;
+  return check_last(ctx, "conv_tma_kernel launch");
 }
 
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream) {
@@ -169,6 +294,8 @@ int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t
     return set_err(ctx, FRB_ERR_INVALID, "conv: output must be 16-byte aligned with out_ld %% 8 == 0 and Cout %% 8 == 0");
   if (io.res_mode != RES_NONE && ((reinterpret_cast<uintptr_t>(io.res) & 15) || (io.res_ld % 8) != 0))
     return set_err(ctx, FRB_ERR_INVALID, "conv: residual must be 16-byte aligned with res_ld %% 8 == 0");
+
+  if (tma_path_ok(ctx, L, io)) return conv_launch_tma(ctx, L, io, stream);
 
   a.a_tma = (!ctx->force_gather && L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) ? 1 : 0;
   CUtensorMap tmA;
@@ -268,6 +395,7 @@ int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ConvLayer L;
   L.Cin = Cin; L.Cout = Cout; L.kh = kh; L.kw = kw; L.sh = sh; L.sw = sw; L.ph = ph; L.pw = pw;
+  if (res_mode == RES_PRE_ACT) L.bn_cap = 128;
   std::vector<float> sl(Cout, act == 0 ? 1.f : (act == 1 ? 0.f : slope));
   int rc = conv_prepare(ctx, L, h_w, h_bias, sl.data());
   if (rc != FRB_OK) { conv_release(L); return rc; }

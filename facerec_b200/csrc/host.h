@@ -26,7 +26,7 @@ struct frb_ctx {
   int device = 0;
   int num_sms = 148;
   int use_bf16 = 0;            // 0: fp16 activations/weights (default), 1: bf16
-  int bn_cap = 128;            // largest conv tile N the planner may pick
+  int bn_cap = 256;            // largest conv tile N the planner may pick
   int force_gather = 0;        // debugging: never use the TMA A path
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
@@ -55,6 +55,7 @@ int check_last(frb_ctx* ctx, const char* what);
 struct ConvLayer {
   int Cin = 0, Cout = 0, kh = 1, kw = 1, sh = 1, sw = 1, ph = 0, pw = 0;
   int K = 0, K_pad = 0, BN = 0, Cout_pad = 0, n_tiles = 0;
+  int bn_cap = 0;            // per-layer cap on the N tile (0 = context default); residual layers use 128
   void* d_w = nullptr;       // [Cout_pad, K_pad] 16-bit, K-major, K ordered (r, s, c)
   float* d_bias = nullptr;   // [Cout_pad]
   float* d_slope = nullptr;  // [Cout_pad] negative slope per output channel (1 linear, 0 relu)

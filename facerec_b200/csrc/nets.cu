@@ -151,8 +151,9 @@ struct Net {
   size_t arena_bytes = 0;
 };
 
-static void add_conv(Net* net, const std::string& name, const HostConv& h, int sh, int sw, int ph, int pw) {
+static void add_conv(Net* net, const std::string& name, const HostConv& h, int sh, int sw, int ph, int pw, int bn_cap = 0) {
   ConvLayer L;
+  L.bn_cap = bn_cap;
   L.Cin = h.Cin; L.Cout = h.Cout; L.kh = h.kh; L.kw = h.kw; L.sh = sh; L.sw = sw; L.ph = ph; L.pw = pw;
   if (conv_prepare(net->ctx, L, h.w.data(), h.b.data(), h.slope.data()) != FRB_OK) {
     conv_release(L);
@@ -164,12 +165,12 @@ static void add_conv(Net* net, const std::string& name, const HostConv& h, int s
 
 // Single source conv, optional zero-padding of input channels up to cin_pad.
 static void add_plain(Net* net, const WeightBlob& blob, const std::string& name, float slope, int sh, int sw, int ph, int pw,
-                      int cin_pad = 0, float scale = 1.f) {
+                      int cin_pad = 0, float scale = 1.f, int bn_cap = 0) {
   const BlobEntry& w = blob.get(name + ".w");
   if (w.dims.size() != 4) throw std::runtime_error("'" + name + ".w' must be 4-d");
   HostConv h(w.dims[0], w.dims[1], w.dims[2], std::max(cin_pad, w.dims[3]));
   place(h, blob, name, 0, 0, slope, scale);
-  add_conv(net, name, h, sh, sw, ph, pw);
+  add_conv(net, name, h, sh, sw, ph, pw, bn_cap);
 }
 
 static void add_dw(Net* net, const WeightBlob& blob, const std::string& name, int stride, float slope) {
@@ -187,6 +188,9 @@ static void add_dw(Net* net, const WeightBlob& blob, const std::string& name, in
   cudaMemcpy(L.d_bias, b.data, L.C * 4, cudaMemcpyHostToDevice);
   net->dws.push_back(L);
 }
+
+// Layers whose epilogue adds a residual tile stage two 64-column slabs of it in shared memory.
+static const int kResBnCap = 128;
 
 // ------------------------------------------------------------------------------------ architecture tables
 static const int kMnetStride[13] = {1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1};
@@ -214,7 +218,7 @@ static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
         const std::string p = sfmt("layer%d.%d", l + 1, i);
         add_plain(net, blob, p + ".conv1", 0.f, 1, 1, 0, 0);
         add_plain(net, blob, p + ".conv2", 0.f, s, s, 1, 1);
-        add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0);   // ReLU after the residual add
+        add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0, 0, 1.f, kResBnCap);   // ReLU after the residual add
         if (i == 0) add_plain(net, blob, p + ".down", 1.f, s, s, 0, 0);
       }
   } else {
@@ -280,7 +284,7 @@ static void load_irv1(Net* net, const WeightBlob& blob) {
     place(u, blob, p + ".conv2d", 0, 0, 0.f, 0.17f, 0, 32);
     place(u, blob, p + ".conv2d", 0, 32, 0.f, 0.17f, 64, 32);
     place(u, blob, p + ".conv2d", 0, 64, 0.f, 0.17f, 32, 32);
-    add_conv(net, p + ".up", u, 1, 1, 0, 0);
+    add_conv(net, p + ".up", u, 1, 1, 0, 0, kResBnCap);
   }
   add_plain(net, blob, "mixed_6a.branch0", 0.f, 2, 2, 0, 0);
   add_plain(net, blob, "mixed_6a.branch1.0", 0.f, 1, 1, 0, 0);
@@ -299,7 +303,7 @@ static void load_irv1(Net* net, const WeightBlob& blob) {
       add_plain(net, blob, p + ".branch1.1", 0.f, 1, 1, 0, 1);   // 1x3
       add_plain(net, blob, p + ".branch1.2", 0.f, 1, 1, 1, 0);   // 3x1
     }
-    add_plain(net, blob, p + ".conv2d", out_slope, 1, 1, 0, 0, 0, scale);   // input order (b0, b1.2) == source order
+    add_plain(net, blob, p + ".conv2d", out_slope, 1, 1, 0, 0, 0, scale, kResBnCap);   // input order (b0, b1.2) == source order
     net->conv_idx[p + ".up"] = net->conv_idx[p + ".conv2d"];
   };
   for (int i = 0; i < 10; ++i) add_block_17_8(sfmt("repeat_2.%d", i), 896, 128, 0.10f, 0.f, true);

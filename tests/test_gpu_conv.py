@@ -38,7 +38,13 @@ CASES = [
     (1, 23, 40, 128, 64, 1, 1, (1, 1), (0, 0), 2, 2, False),     # FPN lateral + nearest-upsampled top-down
     (3, 1, 1, 1792, 512, 1, 1, (1, 1), (0, 0), 0, 0, True),      # last_linear, fp32 out
     (4, 68, 120, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),     # > 148 tiles: persistent loop, TMEM double buffer
-    (1, 30, 30, 256, 512, 1, 1, (2, 2), (0, 0), 0, 0, False),    # strided 1x1 (ResNet downsample) via gather
+    (1, 30, 30, 256, 512, 1, 1, (2, 2), (0, 0), 0, 0, False),    # strided 1x1 (ResNet downsample): strided patch boxes
+    (2, 21, 37, 64, 128, 3, 3, (1, 1), (1, 1), 1, 1, False),     # patch tiling + TMA-staged residual, ragged borders
+    (5, 8, 8, 128, 384, 3, 3, (1, 1), (1, 1), 1, 0, False),      # patches spanning images (8x8 maps), two 192-wide N tiles
+    (30, 3, 3, 192, 192, 1, 3, (1, 1), (0, 1), 1, 0, False),     # Block8 1x3 on 3x3 maps: 14 images per patch
+    (3, 17, 17, 192, 256, 3, 3, (2, 2), (0, 0), 1, 0, False),    # Mixed_6a stride-2 reduction 17 -> 8
+    (2, 40, 56, 256, 80, 1, 1, (1, 1), (0, 0), 2, 0, False),     # Cout = 80: partial last store slab
+    (1, 135, 240, 64, 256, 1, 1, (1, 1), (0, 0), 1, 1, False),   # ResNet conv3 + skip, 254 M-tiles x 2 N-tiles
 ]
 
 
