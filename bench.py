@@ -269,14 +269,14 @@ def run_b200(a):
 
     # ---- RetinaFace forward alone, CUDA events on the launching stream (roofline) ---------
     from facerec_b200 import ops
-    x16 = ops.preprocess_u8(ctx, frames_d, True)
-    ops.retina_forward(ctx, pipe.detector.model_id, x16)
+    x16 = ops.preprocess_u8(ctx, frames_d, True, ops.input_layout(pipe.detector.model_id))
+    ops.retina_forward(ctx, pipe.detector.model_id, x16, H, W)
     torch.cuda.synchronize()
     l1 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(a.steps):
-        ops.retina_forward(ctx, pipe.detector.model_id, x16)
+        ops.retina_forward(ctx, pipe.detector.model_id, x16, H, W)
     e1.record(stream)
     torch.cuda.synchronize()
     fwd_ms = e0.elapsed_time(e1) / a.steps

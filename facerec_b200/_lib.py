@@ -19,6 +19,9 @@ FRB_CONDENSED_F32 = 0
 FRB_CONDENSED_F64 = 1
 FRB_SQUARE_F32 = 2
 
+FRB_LAYOUT_NHWC8 = 0
+FRB_LAYOUT_S2D16 = 1
+
 FRB_OPT_BF16 = 0
 FRB_OPT_BN_CAP = 1
 FRB_OPT_FORCE_GATHER = 2
@@ -34,7 +37,9 @@ SIGNATURES = {
     "frb_set_option": (_i, [_vp, _i, _i]),
     "frb_launch_count": (C.c_longlong, [_vp]),
     "frb_load_model": (_i, [_vp, _i, _vp, _sz]),
-    "frb_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "frb_input_layout": (_i, [_i]),
+    "frb_input_elems": (_sz, [_i, _i, _i, _i]),
+    "frb_preprocess_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "frb_retina_forward": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "frb_num_priors": (_i, [_i, _i]),
     "frb_prior_decode_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),

@@ -40,10 +40,20 @@ int frb_num_priors(int H, int W) {
   return p;
 }
 
-int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out16,
-                      void* stream) {
+int frb_input_layout(int model_id) { return model_id == FRB_RETINA_R50 ? FRB_LAYOUT_S2D16 : FRB_LAYOUT_NHWC8; }
+
+size_t frb_input_elems(int layout, int B, int H, int W) {
+  if (layout == FRB_LAYOUT_S2D16) return static_cast<size_t>(B) * ((H + 1) / 2) * ((W + 1) / 2 + 3) * 16;
+  return static_cast<size_t>(B) * H * W * 8;
+}
+
+int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int layout,
+                      void* d_out16, void* stream) {
   if (ctx == nullptr) return FRB_ERR_INVALID;
   FRB_NEED(ctx, d_frames && d_out16 && B > 0 && H > 0 && W > 0, "frb_preprocess_u8: bad arguments");
+  if (layout == FRB_LAYOUT_S2D16)
+    return launch_preprocess_s2d(ctx, d_frames, B, H, W, src_is_rgb, d_out16, static_cast<cudaStream_t>(stream));
+  FRB_NEED(ctx, layout == FRB_LAYOUT_NHWC8, "frb_preprocess_u8: unknown layout");
   return launch_preprocess(ctx, d_frames, B, H, W, src_is_rgb, 8, d_out16, static_cast<cudaStream_t>(stream));
 }
 

@@ -12,17 +12,24 @@
 // global store is a full 128-byte line.  The residual tile (ResNet / Inception skip) is prefetched by
 // TMA into shared memory while the tile's MMAs are still running.
 //
-// Warp roles (192 threads): 0-3 epilogue (TMEM lane quarter = warp id), 4 MMA issuer + TMEM allocator,
-// 5 TMA producer.  Persistent: one CTA per SM walks tiles round-robin (n fastest, so CTAs running at
-// the same time share the A patch through L2).
+// Warp roles (576 threads): 0-15 epilogue, 16 MMA issuer + TMEM allocator, 17 TMA producer.
+// The epilogue is instruction-issue bound when one warp per scheduler walks a whole 64-column row
+// (ncu: ~2 400 cycles per slab, issue slots mostly idle), so each TMEM lane quarter (warp % 4) is
+// served by four warps that take 16 columns of the slab each: four warps per scheduler hide each
+// other's dependent-issue latency.
+// Persistent: one CTA per SM walks tiles round-robin (n fastest, so CTAs running at the same time
+// share the A patch through L2).
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace frb {
 
-constexpr int kTmaThreads = 192;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kTmaThreads = kEpiThreads + 64;
 constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
 constexpr int kSlabBytes = kBM * kSlab * 2;
+constexpr int kColsPerWarp = kSlab / (kEpiWarps / 4);   // 16
 
 struct ConvTmaArgs {
   int patch;             // 0: linear M tiling (1x1, stride 1, no padding); 1: spatial patch tiling
@@ -34,6 +41,7 @@ struct ConvTmaArgs {
   int bw, bh, bb;        // patch = bb images x bh rows x bw cols (<= 128 pixels)
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
   int stages;
+  int act_kind;          // 0: per-channel slope (general), 1: ReLU everywhere, 2: linear everywhere
   const float* bias;     // [n_tiles*BN]
   const float* slope;    // [n_tiles*BN]
   int res_mode;          // ConvRes: PRE_ACT comes through tmR; POST_ACT_UPSAMPLE (linear tiling only) from global
@@ -64,19 +72,22 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]
   uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);    // [256]
+  float* s_slope = s_bias + 256;                                          // [256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * p.BN)) tmem_cols <<= 1;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     if (p.res_mode == RES_PRE_ACT) tma_prefetch_desc(&tmR);
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
@@ -84,7 +95,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull_bar[b], 1);
-        mbar_init(&tempty_bar[b], 4);
+        mbar_init(&tempty_bar[b], kEpiWarps);
         mbar_init(&res_bar[b], 1);
       }
       fence_mbar_init();
@@ -116,11 +127,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     }
   };
 
-  if (warp < 4) {
+  if (warp < kEpiWarps) {
     // ================================================================ epilogue
-    const int row = warp * 32 + lane;
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int csub = warp >> 2;                // which 16 columns of every 64-column slab
+    const int row = quarter * 32 + lane;
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
+    const int col0 = csub * kColsPerWarp;
     int tile_iter = 0;
     uint32_t slab_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
@@ -132,10 +146,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
 
       if (p.res_mode == RES_PRE_ACT && threadIdx.x == 0) {
         // both residual slabs were consumed before the last named barrier of the previous tile
-        for (int s = 0; s < nslab; ++s) {
-          mbar_arrive_expect_tx(&res_bar[s], static_cast<uint32_t>(p.a_bytes));
-          if (p.patch) tma_load_4d(smem_r + s * kSlabBytes, &tmR, &res_bar[s], n_base + s * kSlab, c1, c2, c3);
-          else tma_load_2d(smem_r + s * kSlabBytes, &tmR, &res_bar[s], n_base + s * kSlab, c1);
+        for (int rs = 0; rs < nslab; ++rs) {
+          mbar_arrive_expect_tx(&res_bar[rs], static_cast<uint32_t>(p.a_bytes));
+          if (p.patch) tma_load_4d(smem_r + rs * kSlabBytes, &tmR, &res_bar[rs], n_base + rs * kSlab, c1, c2, c3);
+          else tma_load_2d(smem_r + rs * kSlabBytes, &tmR, &res_bar[rs], n_base + rs * kSlab, c1);
         }
       }
       const typename E::T* up_row = nullptr;
@@ -152,92 +166,90 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
                    (static_cast<size_t>(b) * p.rH * p.rW + static_cast<size_t>(rh) * p.rW + rw) * p.res_ld;
         }
       }
+      // bias / slope of this N tile -> shared memory (broadcast reads below); the previous tile's readers
+      // are all past their slab barriers, and the first slab barrier below orders these writes before use
+      for (int t = threadIdx.x; t < p.BN; t += kEpiThreads) {
+        s_bias[t] = __ldg(p.bias + n_base + t);
+        s_slope[t] = __ldg(p.slope + n_base + t);
+      }
 
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
 
       for (int s = 0; s < nslab; ++s) {
         const int ncols = min(kSlab, p.BN - s * kSlab);
         const int n0 = n_base + s * kSlab;
-        float x[kSlab];
+        const bool mine = col0 < ncols;            // warp-uniform (BN is a multiple of 16)
+        float x[kColsPerWarp];
+        if (mine) {
+          uint32_t v[kColsPerWarp];
+          tmem_ld16(taddr + s * kSlab + col0, v);
+          tc_wait_ld();
 #pragma unroll
-        for (int c0 = 0; c0 < kSlab; c0 += 16) {
-          if (c0 < ncols) {                       // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(taddr + s * kSlab + c0, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-              x[c0 + j + 0] = __uint_as_float(v[j + 0]) + bz.x;
-              x[c0 + j + 1] = __uint_as_float(v[j + 1]) + bz.y;
-              x[c0 + j + 2] = __uint_as_float(v[j + 2]) + bz.z;
-              x[c0 + j + 3] = __uint_as_float(v[j + 3]) + bz.w;
-            }
-          }
+          for (int c = 0; c < kColsPerWarp; ++c) x[c] = __uint_as_float(v[c]);
         }
         if (s == nslab - 1) {                     // accumulator fully read: hand the TMEM buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
-        if (p.res_mode == RES_PRE_ACT) {
-          mbar_wait(&res_bar[s], tile_iter & 1, p.watchdog, 500 + s);
-          const uint8_t* rrow = smem_r + s * kSlabBytes + row_off;
-#pragma unroll
-          for (int c = 0; c < kSlab / 8; ++c) {
-            if (c * 8 < ncols) {
-              const uint4 r = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(c) ^ sw7) << 4));
-              float2 f;
-              f = E::to_f2(r.x); x[c * 8 + 0] += f.x; x[c * 8 + 1] += f.y;
-              f = E::to_f2(r.y); x[c * 8 + 2] += f.x; x[c * 8 + 3] += f.y;
-              f = E::to_f2(r.z); x[c * 8 + 4] += f.x; x[c * 8 + 5] += f.y;
-              f = E::to_f2(r.w); x[c * 8 + 6] += f.x; x[c * 8 + 7] += f.y;
-            }
-          }
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < kSlab; c0 += 4) {
-          if (c0 < ncols) {
-            const float4 sl = __ldg(reinterpret_cast<const float4*>(p.slope + n0 + c0));
-            x[c0 + 0] = x[c0 + 0] > 0.f ? x[c0 + 0] : x[c0 + 0] * sl.x;
-            x[c0 + 1] = x[c0 + 1] > 0.f ? x[c0 + 1] : x[c0 + 1] * sl.y;
-            x[c0 + 2] = x[c0 + 2] > 0.f ? x[c0 + 2] : x[c0 + 2] * sl.z;
-            x[c0 + 3] = x[c0 + 3] > 0.f ? x[c0 + 3] : x[c0 + 3] * sl.w;
-          }
-        }
-        if (p.res_mode == RES_POST_ACT_UPSAMPLE && up_row != nullptr) {
-#pragma unroll
-          for (int c = 0; c < kSlab / 8; ++c) {
-            if (c * 8 < ncols) {
-              const uint4 r = __ldg(reinterpret_cast<const uint4*>(up_row + n0 + c * 8));
-              float2 f;
-              f = E::to_f2(r.x); x[c * 8 + 0] += f.x; x[c * 8 + 1] += f.y;
-              f = E::to_f2(r.y); x[c * 8 + 2] += f.x; x[c * 8 + 3] += f.y;
-              f = E::to_f2(r.z); x[c * 8 + 4] += f.x; x[c * 8 + 5] += f.y;
-              f = E::to_f2(r.w); x[c * 8 + 6] += f.x; x[c * 8 + 7] += f.y;
-            }
-          }
-        }
         // staging slab `ob` is free once the store issued two slabs ago has finished reading it
         const uint32_t ob = slab_ctr & 1u;
         if (threadIdx.x == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* orow = smem_o + ob * kSlabBytes + row_off;
+        named_bar_sync(1, kEpiThreads);
+
+        if (mine) {
+          if (p.res_mode == RES_PRE_ACT) mbar_wait(&res_bar[s], tile_iter & 1, p.watchdog, 500 + s);
+          const uint8_t* rrow = smem_r + s * kSlabBytes + row_off;
+          uint8_t* orow = smem_o + ob * kSlabBytes + row_off;
 #pragma unroll
-        for (int c = 0; c < kSlab / 8; ++c) {
-          if (c * 8 < ncols) {
+          for (int c = 0; c < kColsPerWarp / 8; ++c) {
+            float* y = x + c * 8;
+            const int cc = col0 + c * 8;                                   // column inside the slab
+            const uint32_t chunk = (static_cast<uint32_t>(cc >> 3) ^ sw7) << 4;
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + s * kSlab + cc);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + s * kSlab + cc + 4);
+            y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+            y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+            if (p.res_mode == RES_PRE_ACT) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rrow + chunk);
+              float2 f;
+              f = E::to_f2(r.x); y[0] += f.x; y[1] += f.y;
+              f = E::to_f2(r.y); y[2] += f.x; y[3] += f.y;
+              f = E::to_f2(r.z); y[4] += f.x; y[5] += f.y;
+              f = E::to_f2(r.w); y[6] += f.x; y[7] += f.y;
+            }
+            if (p.act_kind == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+            } else if (p.act_kind == 0) {
+              const float4 s0 = *reinterpret_cast<const float4*>(s_slope + s * kSlab + cc);
+              const float4 s1 = *reinterpret_cast<const float4*>(s_slope + s * kSlab + cc + 4);
+              // leaky(x) = max(x,0) + slope * min(x,0): branch-free, slope 1 = identity, 0 = ReLU
+              y[0] = fmaf(s0.x, fminf(y[0], 0.f), fmaxf(y[0], 0.f)); y[1] = fmaf(s0.y, fminf(y[1], 0.f), fmaxf(y[1], 0.f));
+              y[2] = fmaf(s0.z, fminf(y[2], 0.f), fmaxf(y[2], 0.f)); y[3] = fmaf(s0.w, fminf(y[3], 0.f), fmaxf(y[3], 0.f));
+              y[4] = fmaf(s1.x, fminf(y[4], 0.f), fmaxf(y[4], 0.f)); y[5] = fmaf(s1.y, fminf(y[5], 0.f), fmaxf(y[5], 0.f));
+              y[6] = fmaf(s1.z, fminf(y[6], 0.f), fmaxf(y[6], 0.f)); y[7] = fmaf(s1.w, fminf(y[7], 0.f), fmaxf(y[7], 0.f));
+            }
+            if (p.res_mode == RES_POST_ACT_UPSAMPLE && up_row != nullptr) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(up_row + n0 + cc));
+              float2 f;
+              f = E::to_f2(r.x); y[0] += f.x; y[1] += f.y;
+              f = E::to_f2(r.y); y[2] += f.x; y[3] += f.y;
+              f = E::to_f2(r.z); y[4] += f.x; y[5] += f.y;
+              f = E::to_f2(r.w); y[6] += f.x; y[7] += f.y;
+            }
             uint4 o;
-            o.x = E::from_f2(x[c * 8 + 0], x[c * 8 + 1]);
-            o.y = E::from_f2(x[c * 8 + 2], x[c * 8 + 3]);
-            o.z = E::from_f2(x[c * 8 + 4], x[c * 8 + 5]);
-            o.w = E::from_f2(x[c * 8 + 6], x[c * 8 + 7]);
-            *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(c) ^ sw7) << 4)) = o;
+            o.x = E::from_f2(y[0], y[1]);
+            o.y = E::from_f2(y[2], y[3]);
+            o.z = E::from_f2(y[4], y[5]);
+            o.w = E::from_f2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(orow + chunk) = o;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (threadIdx.x == 0) {
           if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
           else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
@@ -247,7 +259,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       }
     }
     if (threadIdx.x == 0) tma_store_wait<0>();     // stores must land before the CTA (and its smem) goes away
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ============================================================== MMA issuer
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, kBF16 ? 1 : 0);
     int stage = 0;
@@ -307,7 +319,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   // -------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, tmem_cols);
   }

@@ -119,6 +119,9 @@ int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bi
   std::vector<float> slope(L.Cout_pad, 1.f);
   if (h_slope != nullptr)
     for (int n = 0; n < L.Cout; ++n) slope[n] = h_slope[n];
+  bool all0 = true, all1 = true;
+  for (int n = 0; n < L.Cout; ++n) { all0 = all0 && slope[n] == 0.f; all1 = all1 && slope[n] == 1.f; }
+  L.act_kind = all0 ? 1 : (all1 ? 2 : 0);
 
   FRB_CUDA(ctx, cudaMalloc(&L.d_w, w16.size() * 2));
   FRB_CUDA(ctx, cudaMalloc(&L.d_bias, bias.size() * 4));
@@ -200,7 +203,10 @@ static bool tma_path_ok(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io) {
 static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream) {
   ConvTmaArgs a;
   memset(&a, 0, sizeof(a));
-  const int Ho = conv_out_dim(io.H, L.kh, L.sh, L.ph), Wo = conv_out_dim(io.W, L.kw, L.sw, L.pw);
+  // stem over the space-to-depth input: io.H x io.W is the padded s2d grid [H/2, W/2 + 3], every output
+  // pixel reads a 4-row window of 4 consecutive s2d pixels (64 contiguous elements per row)
+  const int Ho = L.special ? io.H : conv_out_dim(io.H, L.kh, L.sh, L.ph);
+  const int Wo = L.special ? io.W - 3 : conv_out_dim(io.W, L.kw, L.sw, L.pw);
   const long long M = static_cast<long long>(io.B) * Ho * Wo;
   if (M <= 0 || M > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv: bad problem size");
   const bool linear = L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0;
@@ -209,7 +215,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.cin_blocks = (L.Cin + kBK - 1) / kBK;
   a.num_kb = L.kh * L.kw * a.cin_blocks;
   a.BN = L.BN; a.n_tiles = L.n_tiles;
-  a.bias = L.d_bias; a.slope = L.d_slope;
+  a.bias = L.d_bias; a.slope = L.d_slope; a.act_kind = L.act_kind;
   a.res_mode = io.res_mode; a.res = io.res; a.res_ld = io.res_ld; a.rH = io.rH; a.rW = io.rW;
   a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M);
   a.watchdog = ctx->wd_dev;
@@ -233,7 +239,14 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     a.tiles_h = (Ho + a.bh - 1) / a.bh;
     m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * ((io.B + a.bb - 1) / a.bb);
     a.a_bytes = a.bw * a.bh * a.bb * 128;
-    if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
+    if (L.special) {
+      // overlapping windows: dim0 = 64 elements starting at s2d pixel w, dim1 steps one s2d pixel (16 elements)
+      const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)io.H, (uint64_t)io.B};
+      const uint64_t str[3] = {32, (uint64_t)io.W * 32, (uint64_t)io.H * io.W * 32};
+      const uint32_t box[4] = {64, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bb};
+      const uint32_t est[4] = {1, 1, 1, 1};
+      if ((rc = encode_nd(ctx, &tmA, io.in, 4, dims, str, box, est)) != FRB_OK) return rc;
+    } else if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
     if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_patch(ctx, &tmR, io.res, L.Cout, Wo, Ho, io.B, io.res_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK)
@@ -243,7 +256,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.total_tiles = static_cast<int>(m_tiles * L.n_tiles);
 
   const int stage_bytes = kAStageBytes + L.BN * 128;
-  const int fixed = 2 * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 6) * 8 + 16 + 1024;
+  const int fixed = 2 * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 8) * 8 + 2048 + 1024;
   const int budget = 226 * 1024 - fixed;
   a.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
@@ -295,7 +308,7 @@ int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t
   if (io.res_mode != RES_NONE && ((reinterpret_cast<uintptr_t>(io.res) & 15) || (io.res_ld % 8) != 0))
     return set_err(ctx, FRB_ERR_INVALID, "conv: residual must be 16-byte aligned with res_ld %% 8 == 0");
 
-  if (tma_path_ok(ctx, L, io)) return conv_launch_tma(ctx, L, io, stream);
+  if (L.special || tma_path_ok(ctx, L, io)) return conv_launch_tma(ctx, L, io, stream);
 
   a.a_tma = (!ctx->force_gather && L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) ? 1 : 0;
   CUtensorMap tmA;

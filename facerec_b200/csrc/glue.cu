@@ -102,6 +102,58 @@ int launch_preprocess(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W
   return check_last(ctx, "preprocess_kernel");
 }
 
+// K1 (space-to-depth variant, feeds the ResNet-50 stem): u8 HWC -> 16-bit [B, H/2, W/2 + 3, 16].
+// Every output pixel holds the 2x2 input block (dy, dx) x (B-104, G-117, R-123, 0); two zero
+// pixels on the left and one on the right are the horizontal padding of the 7x7/s2 stem, which
+// thereby turns into a 4-row x 64-element window conv that TMA can feed directly (nets.cu).
+template <bool kBF16>
+__global__ void preprocess_s2d_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int H2, int Wp,
+                                      int src_is_rgb, uint4* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * H2 * Wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % Wp);
+    long long t = i / Wp;
+    const int y2 = static_cast<int>(t % H2);
+    const int b = static_cast<int>(t / H2);
+    const int x2 = xp - 2;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (x2 >= 0 && 2 * x2 < W) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = 2 * y2 + dy;
+        if (y >= H) continue;
+        const uint8_t* row = in + (static_cast<size_t>(b) * H + y) * W * 3;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int x = 2 * x2 + dx;
+          if (x >= W) continue;
+          const float c0 = __ldg(row + x * 3 + 0), c1 = __ldg(row + x * 3 + 1), c2 = __ldg(row + x * 3 + 2);
+          float* o = v + (dy * 2 + dx) * 4;
+          o[0] = (src_is_rgb ? c2 : c0) - 104.f;
+          o[1] = c1 - 117.f;
+          o[2] = (src_is_rgb ? c0 : c2) - 123.f;
+        }
+      }
+    }
+    out[i * 2] = pack8<kBF16>(v);
+    out[i * 2 + 1] = pack8<kBF16>(v + 8);
+  }
+}
+
+int launch_preprocess_s2d(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out,
+                          cudaStream_t st) {
+  const int H2 = (H + 1) / 2, Wp = (W + 1) / 2 + 3;
+  const long long total = static_cast<long long>(B) * H2 * Wp;
+  const int grid = grid_for(total, 256, ctx->num_sms);
+  if (ctx->use_bf16) preprocess_s2d_kernel<true><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, static_cast<uint4*>(d_out));
+  else preprocess_s2d_kernel<false><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, static_cast<uint4*>(d_out));
+  ctx->launches++;
+  return check_last(ctx, "preprocess_s2d_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ K4
 // Depthwise 3x3 (pad 1, stride 1|2) + bias + activation, NHWC, 8 channels per thread.
 // w: [9][C] fp32 (tap-major), bias [C] fp32.

@@ -55,6 +55,8 @@ int check_last(frb_ctx* ctx, const char* what);
 struct ConvLayer {
   int Cin = 0, Cout = 0, kh = 1, kw = 1, sh = 1, sw = 1, ph = 0, pw = 0;
   int K = 0, K_pad = 0, BN = 0, Cout_pad = 0, n_tiles = 0;
+  int act_kind = 0;          // 0 per-channel slope, 1 ReLU on every channel, 2 linear on every channel
+  int special = 0;           // 1: ResNet stem over the space-to-depth input (window conv, see nets.cu)
   int bn_cap = 0;            // per-layer cap on the N tile (0 = context default); residual layers use 128
   void* d_w = nullptr;       // [Cout_pad, K_pad] 16-bit, K-major, K ordered (r, s, c)
   float* d_bias = nullptr;   // [Cout_pad]
@@ -94,6 +96,7 @@ void conv_release(ConvLayer& L);
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
 
 // ------------------------------------------------------------------ glue kernels (glue.cu)
+int launch_preprocess_s2d(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out, cudaStream_t);
 int launch_preprocess(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int out_c, void* d_out,
                       cudaStream_t);
 int launch_dwconv3x3(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_w9c,

@@ -211,7 +211,40 @@ static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
   const float neck_slope = r50 ? 0.f : 0.1f;   // out_channels <= 64 -> LeakyReLU(0.1), else ReLU
   const int C = r50 ? 256 : 64;
   if (r50) {
-    add_plain(net, blob, "conv1", 0.f, 2, 2, 3, 3, 8);
+    {
+      // 7x7 / stride 2 / pad 3 stem on the space-to-depth input (frb_preprocess_u8, FRB_LAYOUT_S2D16): with the
+      // kernel zero-extended to 8x8 it is a 4x4 stride-1 conv over 2x2 pixel blocks; the four horizontally
+      // adjacent blocks of a window are 64 contiguous elements, so the layer runs as a 4-tap (rows) x 64-channel
+      // conv whose A operand is a TMA box over overlapping windows.  K = 256 instead of 7*7*8 = 392.
+      const BlobEntry& w = blob.get("conv1.w");
+      const BlobEntry& b = blob.get("conv1.b");
+      if (w.dims.size() != 4 || w.dims[0] != 64 || w.dims[1] != 7 || w.dims[2] != 7 || w.dims[3] != 3)
+        throw std::runtime_error("conv1.w must be [64,7,7,3]");
+      HostConv h(64, 4, 1, 64);
+      for (int n = 0; n < 64; ++n) {
+        for (int r = 0; r < 4; ++r)
+          for (int s = 0; s < 4; ++s)
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx) {
+                const int kr = 2 * r + dy - 1, kc = 2 * s + dx - 1;
+                if (kr < 0 || kr > 6 || kc < 0 || kc > 6) continue;
+                for (int c = 0; c < 3; ++c)
+                  h.w[(static_cast<size_t>(n) * 4 + r) * 64 + s * 16 + dy * 8 + dx * 4 + c] =
+                      w.data[((static_cast<size_t>(n) * 7 + kr) * 7 + kc) * 3 + c];
+              }
+        h.b[n] = b.data[n];
+        h.slope[n] = 0.f;
+      }
+      ConvLayer L;
+      L.special = 1;
+      L.Cin = 64; L.Cout = 64; L.kh = 4; L.kw = 1; L.sh = 1; L.sw = 1; L.ph = 2; L.pw = 0;
+      if (conv_prepare(net->ctx, L, h.w.data(), h.b.data(), h.slope.data()) != FRB_OK) {
+        conv_release(L);
+        throw std::runtime_error("conv_prepare('conv1'): " + net->ctx->err);
+      }
+      net->conv_idx["conv1"] = static_cast<int>(net->convs.size());
+      net->convs.push_back(L);
+    }
     for (int l = 0; l < 4; ++l)
       for (int i = 0; i < kR50Blocks[l]; ++i) {
         const int s = (i == 0 && l > 0) ? 2 : 1;
@@ -353,8 +386,8 @@ struct Builder {
     op.out_mode = out_mode; op.P_off = P_off;
     const ConvLayer& L = net->convs[op.layer];
     const TensorInfo& ti = plan->tensors[in.t];
-    if (in.coff + L.Cin > ti.C) throw std::runtime_error("plan: layer '" + name + "' reads past its input tensor");
-    if (out.t >= 0) {
+    if (!L.special && in.coff + L.Cin > ti.C) throw std::runtime_error("plan: layer '" + name + "' reads past its input tensor");
+    if (out.t >= 0 && !L.special) {
       const TensorInfo& to = plan->tensors[out.t];
       if (to.H != conv_out_dim(ti.H, L.kh, L.sh, L.ph) || to.W != conv_out_dim(ti.W, L.kw, L.sw, L.pw) ||
           out.coff + L.Cout > to.C)
@@ -398,10 +431,12 @@ static View V(int t, int coff = 0) {
 static void plan_retina(Net* net, Plan& plan, bool r50) {
   Builder b{net, &plan};
   const int H = plan.H, W = plan.W;
-  const int x0 = b.tensor(H, W, 8, 2, 1);
+  // network input: NHWC8 for MobileNet, padded space-to-depth [H/2, W/2 + 3, 16] for ResNet-50 (glue.cu K1)
+  // (odd frame sizes: the missing row / column of the last 2x2 block is zero, which is exactly the stem's padding)
+  const int x0 = r50 ? b.tensor((H + 1) / 2, (W + 1) / 2 + 3, 16, 2, 1) : b.tensor(H, W, 8, 2, 1);
   int c[3];
   if (r50) {
-    const int H1 = conv_out_dim(H, 7, 2, 3), W1 = conv_out_dim(W, 7, 2, 3);
+    const int H1 = (H + 1) / 2, W1 = (W + 1) / 2;
     const int t1 = b.tensor(H1, W1, 64);
     b.conv("conv1", V(x0), V(t1));
     int h = conv_out_dim(H1, 3, 2, 1), w = conv_out_dim(W1, 3, 2, 1);

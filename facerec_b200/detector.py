@@ -52,8 +52,8 @@ class B200RetinaFaceDetector:
         """frames_u8: [B,H,W,3] uint8 RGB on the GPU.  Returns device tensors (cand [B,C,15], keep [B,C], nkeep [B],
         count [B]); rows cand[b, keep[b,:nkeep[b]]] are the detections of frame b in score order."""
         B, H, W_, _ = frames_u8.shape
-        x16 = ops.preprocess_u8(self.ctx, frames_u8, True)
-        loc, conf, landm = ops.retina_forward(self.ctx, self.model_id, x16)
+        x16 = ops.preprocess_u8(self.ctx, frames_u8, True, ops.input_layout(self.model_id))
+        loc, conf, landm = ops.retina_forward(self.ctx, self.model_id, x16, H, W_)
         cand, count, pidx = ops.prior_decode_filter(self.ctx, loc, conf, landm, H, W_, self.threshold, self.max_candidates)
         keep, nkeep = ops.nms(self.ctx, cand, count, pidx, self.nms_threshold, True)
         return cand, keep, nkeep, count

@@ -42,23 +42,37 @@ def num_priors(H: int, W: int) -> int:
     return int(_lib.load_library().frb_num_priors(H, W))
 
 
-def preprocess_u8(ctx: Context, frames: torch.Tensor, src_is_rgb: bool = True) -> torch.Tensor:
-    """[B,H,W,3] uint8 -> [B,H,W,8] 16-bit (BGR minus mean, 5 zero channels)."""
+def input_layout(model_id: int) -> int:
+    return int(_lib.load_library().frb_input_layout(model_id))
+
+
+def preprocess_u8(ctx: Context, frames: torch.Tensor, src_is_rgb: bool = True, layout: int = _lib.FRB_LAYOUT_NHWC8) -> torch.Tensor:
+    """[B,H,W,3] uint8 -> 16-bit network input (BGR minus mean): [B,H,W,8] or, for FRB_LAYOUT_S2D16,
+    [B,H/2,W/2+3,16] (2x2 space-to-depth blocks with the stem's horizontal zero padding)."""
     _need_cuda(frames, "frames", torch.uint8)
     B, H, W, ch = frames.shape
     if ch != 3:
         raise ValueError("frames must be [B,H,W,3]")
-    out = torch.empty((B, H, W, 8), dtype=act_dtype(ctx), device=frames.device)
-    ctx.check(ctx.lib.frb_preprocess_u8(ctx.handle, ptr(frames), B, H, W, int(src_is_rgb), ptr(out), current_stream()),
-              "frb_preprocess_u8")
+    shape = (B, (H + 1) // 2, (W + 1) // 2 + 3, 16) if layout == _lib.FRB_LAYOUT_S2D16 else (B, H, W, 8)
+    out = torch.empty(shape, dtype=act_dtype(ctx), device=frames.device)
+    ctx.check(ctx.lib.frb_preprocess_u8(ctx.handle, ptr(frames), B, H, W, int(src_is_rgb), layout, ptr(out),
+                                        current_stream()), "frb_preprocess_u8")
     return out
 
 
-def retina_forward(ctx: Context, model_id: int, x16: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def retina_forward(ctx: Context, model_id: int, x16: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None):
+    """x16 = preprocess_u8(..., layout=input_layout(model_id)); H, W = frame size (needed for the S2D layout)."""
     _need_cuda(x16, "x16", act_dtype(ctx))
-    B, H, W, ch = x16.shape
-    if ch != 8:
-        raise ValueError("x16 must be [B,H,W,8]")
+    B = x16.shape[0]
+    if input_layout(model_id) == _lib.FRB_LAYOUT_S2D16:
+        if H is None:
+            H, W = 2 * x16.shape[1], 2 * (x16.shape[2] - 3)
+        if tuple(x16.shape) != (B, (H + 1) // 2, (W + 1) // 2 + 3, 16):
+            raise ValueError("x16 does not have the S2D16 layout of an HxW frame")
+    else:
+        if x16.shape[3] != 8:
+            raise ValueError("x16 must be [B,H,W,8]")
+        H, W = x16.shape[1], x16.shape[2]
     P = num_priors(H, W)
     loc = torch.empty((B, P, 4), dtype=torch.float32, device=x16.device)
     conf = torch.empty((B, P, 2), dtype=torch.float32, device=x16.device)

@@ -70,16 +70,25 @@ int frb_load_model(frb_ctx* ctx, int model_id, const void* h_blob, size_t bytes)
 
 /* ---- per-frame path ----------------------------------------------------------------------- */
 
-/* K1  u8 HWC frames -> 16-bit NHWC with 8 channels (3 real + 5 zero) for the tensor-core stem:
- * RetinaFace input = BGR minus (104,117,123), no scaling.
+/* Layout of the 16-bit network input produced by K1. */
+enum frb_layout {
+  FRB_LAYOUT_NHWC8 = 0, /* [B,H,W,8]: 3 real channels + 5 zero (MobileNet0.25 stem)                        */
+  FRB_LAYOUT_S2D16 = 1  /* [B,H/2,W/2+3,16]: 2x2 space-to-depth blocks (dy,dx,c4), 2 zero pixels left and 1
+                           right = the stem's horizontal padding (ResNet-50 stem; odd H/W round up)           */
+};
+int frb_input_layout(int model_id);                              /* the layout frb_retina_forward expects */
+size_t frb_input_elems(int layout, int B, int H, int W);         /* 16-bit elements of that buffer        */
+
+/* K1  u8 HWC frames -> 16-bit network input: RetinaFace input = BGR minus (104,117,123), no scaling.
  * Replaces the input transform inside RetinaFace.predict (facerec/detector.py:68); frames arrive RGB
  * from facerec/extract.py:300, so src_is_rgb=1 swaps channels back. */
-int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb,
-                      void* d_out16 /*[B,H,W,8]*/, void* stream);
+int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int layout,
+                      void* d_out16, void* stream);
 
 /* K2-K5  RetinaFace forward -> loc [B,P,4], conf [B,P,2] (logits), landm [B,P,10], fp32.
+ * d_in16 is the K1 output in frb_input_layout(model_id); H, W are the FRAME dimensions.
  * Replaces the network inside RetinaFace.predict (facerec/detector.py:64,68). */
-int frb_retina_forward(frb_ctx* ctx, int model_id, const void* d_in16 /*[B,H,W,8]*/, int B, int H, int W,
+int frb_retina_forward(frb_ctx* ctx, int model_id, const void* d_in16, int B, int H, int W,
                        float* d_loc, float* d_conf, float* d_landm, void* stream);
 /* number of priors for an H x W input: 2 * sum over steps {8,16,32} of ceil(H/s)*ceil(W/s) */
 int frb_num_priors(int H, int W);

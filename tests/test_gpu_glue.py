@@ -96,3 +96,18 @@ def test_crop_resize_standardize_matches_cv2_semantics(ctx):
         ref = crop.standardize(crop.resize_linear_u8(frames[f, y:y + h, x:x + w]))
         assert np.array_equal(out[i, :, :, :3], ref), i       # (u8 - 127.5)/128 is exact in fp16
         assert not out[i, :, :, 3:].any()
+
+
+def test_preprocess_space_to_depth_layout(ctx):
+    from facerec_b200 import ops, _lib
+    rng = np.random.RandomState(4)
+    B, H, W = 2, 18, 26
+    fr = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    out = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True, _lib.FRB_LAYOUT_S2D16).float().cpu().numpy()
+    assert out.shape == (B, H // 2, W // 2 + 3, 16)
+    bgr = fr[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32)
+    ref = np.zeros_like(out)
+    for dy in range(2):
+        for dx in range(2):
+            ref[:, :, 2:-1, (dy * 2 + dx) * 4:(dy * 2 + dx) * 4 + 3] = bgr[:, dy::2, dx::2, :]
+    assert np.array_equal(out, ref)

@@ -29,8 +29,9 @@ def test_retina_forward_matches_oracle(ctx, model, backbone, B, H, W):
     ops.load_model(ctx, weights.MODEL_IDS[model], weights.write_blob(w))
     rng = np.random.RandomState(H)
     fr = _frames(rng, B, H, W)
-    x16 = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True)
-    loc, conf, landm = (t.cpu() for t in ops.retina_forward(ctx, weights.MODEL_IDS[model], x16))
+    mid = weights.MODEL_IDS[model]
+    x16 = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True, ops.input_layout(mid))
+    loc, conf, landm = (t.cpu() for t in ops.retina_forward(ctx, mid, x16, H, W))
     P = nets.params_from_weights(w)
     x = torch.from_numpy(fr[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32)).permute(0, 3, 1, 2)
     with torch.no_grad():
