@@ -30,6 +30,7 @@ constexpr int kTmaThreads = kEpiThreads + 64;
 constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
 constexpr int kSlabBytes = kBM * kSlab * 2;
 constexpr int kColsPerWarp = kSlab / (kEpiWarps / 4);   // 16
+constexpr int kOutBufs = 4;                // staging slabs in flight (TMA stores drain asynchronously)
 
 struct ConvTmaArgs {
   int patch;             // 0: linear M tiling (1x1, stride 1, no padding); 1: spatial patch tiling
@@ -63,8 +64,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int b_stage_bytes = p.BN * 128;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
-  uint8_t* smem_o = smem_b + p.stages * b_stage_bytes;          // 2 staging slabs
-  uint8_t* smem_r = smem_o + 2 * kSlabBytes;                    // 2 residual slabs (PRE_ACT only)
+  uint8_t* smem_o = smem_b + p.stages * b_stage_bytes;          // kOutBufs staging slabs
+  uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                    // 2 residual slabs (PRE_ACT only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (p.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
@@ -194,9 +195,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
-        // staging slab `ob` is free once the store issued two slabs ago has finished reading it
-        const uint32_t ob = slab_ctr & 1u;
-        if (threadIdx.x == 0) tma_store_wait_read<1>();
+        // staging slab `ob` is free once the store issued kOutBufs slabs ago has finished reading it
+        const uint32_t ob = slab_ctr % kOutBufs;
+        if (threadIdx.x == 0) tma_store_wait_read<kOutBufs - 1>();
         named_bar_sync(1, kEpiThreads);
 
         if (mine) {

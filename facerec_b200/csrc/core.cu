@@ -256,7 +256,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.total_tiles = static_cast<int>(m_tiles * L.n_tiles);
 
   const int stage_bytes = kAStageBytes + L.BN * 128;
-  const int fixed = 2 * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 8) * 8 + 2048 + 1024;
+  const int fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 8) * 8 + 2048 + 1024;
   const int budget = 226 * 1024 - fixed;
   a.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;

@@ -1,0 +1,105 @@
+"""End-to-end parity on the synthetic clip (north_star tolerances): kept-face sets, box IoU >= 0.99,
+embedding cosine >= 0.999 — CUDA path vs fp32 oracle, same frames, same seeded weights."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _report():
+    spec = importlib.util.spec_from_file_location("parity_report", os.path.join(ROOT, "tools", "parity_report.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("backbone,H,W,n", [("mnet025", 360, 640, 24), ("r50", 1080, 1920, 3)])
+def test_detect_embed_parity_vs_oracle(ctx, backbone, H, W, n):
+    s = _report().run(backbone, H, W, n)
+    print(s)
+    assert s["oracle_faces"] >= n                       # the calibrated heads do fire: the test is not vacuous
+    assert s["face_match_rate"] >= 0.95, s              # >= 95 % of oracle faces reproduced with IoU >= 0.99
+    assert abs(s["gpu_faces"] - s["oracle_faces"]) <= max(1, 0.05 * s["oracle_faces"]), s
+    assert s["cos_n"] > 0 and s["cos_min"] >= 0.999, s
+    assert s["max_landmark_err_px"] < 1.0, s
+
+
+def test_detector_reference_contract(ctx):
+    """detect() result schema of facerec/detector.py:3-13,66-79: JSON-serialisable, ints for keypoints, min-size filter."""
+    import json
+    from facerec_b200 import synth
+    from facerec_b200.detector import B200RetinaFaceDetector
+    det = B200RetinaFaceDetector(min_face_size=20, backbone="mnet025", ctx=ctx)
+    img = synth.frame(1234, 200, 360, 640)
+    faces = det.detect(img)
+    assert len(faces) > 0
+    for f in faces:
+        assert set(f) == {"box", "keypoints"} and len(f["box"]) == 4
+        assert set(f["keypoints"]) == {"left_eye", "right_eye", "nose", "mouth_left", "mouth_right"}
+        assert all(isinstance(v, int) for kp in f["keypoints"].values() for v in kp)
+        assert min(f["box"][2] - f["box"][0], f["box"][3] - f["box"][1]) >= 20
+    json.dumps(faces)
+    batch = det.detect_batch(np.stack([img, synth.frame(1234, 0, 360, 640)]))
+    assert batch[0] == faces and len(batch) == 2
+    big = B200RetinaFaceDetector(min_face_size=10 ** 6, backbone="mnet025", ctx=ctx)
+    assert big.detect(img) == []
+
+
+def test_embedder_reference_contract(ctx):
+    """embeddings(list of crops) of facerec/extract.py:166: any crop size, unit rows, .tolist()-able."""
+    from facerec_b200 import synth
+    from facerec_b200.embedder import B200FaceNet, cropBox
+    emb = B200FaceNet(ctx=ctx)
+    img = synth.frame(1234, 200, 360, 640)
+    crops = [cropBox(img, {"box": [100, 50, 80, 90]}, 16), cropBox(img, {"box": [0, 0, 40, 40]}, 16), img[:7, :300]]
+    assert crops[1].shape == (56, 56, 3)
+    e = emb.embeddings(crops)
+    assert e.shape == (3, 512) and np.allclose(np.linalg.norm(e, axis=1), 1, atol=1e-5)
+    one = emb.embeddings([crops[0]])
+    assert np.abs(one[0] - e[0]).max() < 1e-6 and isinstance(one[0].tolist()[0], float)
+    assert emb.embeddings([]).shape == (0, 512)
+
+
+def test_extract_cluster_classify_pipeline(ctx, tmp_path):
+    """Two frame shards through the extractor, then (host) stitching by concatenation, GPU clustering and kNN."""
+    import contextlib
+    import io
+    import json
+    from facerec_b200 import extract, cluster, classify_knn, formats
+    from facerec_b200.detector import B200RetinaFaceDetector
+    from facerec_b200.embedder import B200FaceNet
+    from facerec_b200.sort import Sort
+    det = B200RetinaFaceDetector(20, "mnet025", ctx=ctx)
+    emb = B200FaceNet(ctx=ctx)
+    out = str(tmp_path / "data")
+    for shard in range(2):
+        ex = extract.Extractor(det, emb, Sort(5, 3, 0.5), out, n_shards=2, shard_i=shard, save_images=False, batch=16)
+        with contextlib.redirect_stdout(io.StringIO()):
+            counts = ex.process_video("synth:100001:120:640x360")
+        assert counts["boxes"] > 0 and counts["traj"] > 0
+    d = os.path.join(out, "100001-data")
+    feats = []
+    for name in sorted(os.listdir(os.path.join(d, "features"))):
+        feats += open(os.path.join(d, "features", name)).read().splitlines()
+    rec = json.loads(feats[0])
+    assert set(rec) == {"frame", "tag", "embeddings", "box", "keypoints", "w", "h"}
+    assert set(rec["embeddings"]) == set(extract.FACENET_KEYS) and len(rec["embeddings"][formats.EMB_NAME]) == 512
+    assert rec["frame"] % 5 == 0 and rec["tag"].startswith("100001:")
+    # shard 0 wrote the overlap frames too (facerec/extract.py:279,330)
+    assert os.path.exists(os.path.join(d, "features", "features_100001_0-60.jsonl"))
+    with open(os.path.join(d, "features.jsonl"), "w") as fh:
+        fh.write("\n".join(feats) + "\n")
+    trajs = []
+    for name in sorted(os.listdir(os.path.join(d, "trajectories"))):
+        trajs += open(os.path.join(d, "trajectories", name)).read().splitlines()
+    with open(os.path.join(d, "trajectories.jsonl"), "w") as fh:
+        fh.write("\n".join(trajs) + "\n")
+    with contextlib.redirect_stdout(io.StringIO()):
+        vm = formats.read_features(d)
+        tr, means = cluster.read_trajectories(d, vm)
+        keep = [i for i, m in enumerate(means) if np.ndim(m) == 1]
+        assert len(keep) >= 2

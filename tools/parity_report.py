@@ -1,0 +1,99 @@
+"""End-to-end parity of the CUDA path against the fp32 oracle on the synthetic clip (north_star tolerances:
+box IoU >= 0.99 with identical kept-face sets, embedding cosine >= 0.999).  Writes one JSON record.
+
+  python tools/parity_report.py --backbone mnet025 --height 360 --width 640 --frames 48
+  python tools/parity_report.py --backbone r50 --height 1080 --width 1920 --frames 6
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from facerec_b200 import synth, weights as W, _lib  # noqa: E402
+from facerec_b200.pipeline import FacePipeline, boxes_to_rects  # noqa: E402
+from oracle import nets, postproc, crop  # noqa: E402
+
+
+def iou(a, b):
+    iw = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
+    ih = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+    inter = iw * ih
+    return inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter)
+
+
+def run(backbone, H, Wd, n_frames, first=0, stride=7, seed=1234, min_size=20, band=0.02):
+    ctx = _lib.default_context(0)
+    pipe = FacePipeline(backbone, min_face_size=min_size, save_every=1, ctx=ctx)
+    idx = [first + i * stride for i in range(n_frames)]
+    frames = np.stack([synth.frame(seed, i, H, Wd) for i in idx])
+    res = pipe.detect_embed(frames)
+    Pd = nets.params_from_weights(W.synth_weights("retina_" + backbone, 0))
+    Pe = nets.params_from_weights(W.synth_weights("irv1", 0))
+    stats = {"frames": n_frames, "frames_identical": 0, "frames_identical_outside_band": 0, "oracle_faces": 0, "gpu_faces": 0,
+             "matched_iou99": 0, "borderline_oracle_faces": 0, "min_iou_matched": 1.0, "cos_min": 1.0, "cos_n": 0,
+             "max_landmark_err_px": 0.0}
+    thr = np.float32(0.95)
+    with torch.no_grad():
+        for b in range(n_frames):
+            x = torch.from_numpy(frames[b][..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32))
+            loc, conf, landm = nets.retina_forward(Pd, x.permute(2, 0, 1)[None].contiguous(), backbone)
+            dets, _ = postproc.postprocess(loc[0].numpy(), conf[0].numpy(), landm[0].numpy(), H, Wd)
+            if len(dets):
+                dets = dets[np.minimum(dets[:, 2] - dets[:, 0], dets[:, 3] - dets[:, 1]) >= min_size]
+            got = res.dets[b]
+            stats["oracle_faces"] += len(dets)
+            stats["gpu_faces"] += len(got)
+            used = set()
+            all_ok = len(dets) == len(got)
+            ok_band = True
+            for d in dets:
+                border = abs(float(d[4]) - 0.95) < band * 0.05      # score within a narrow band of the threshold
+                best, bj = 0.0, -1
+                for j, g in enumerate(got):
+                    if j in used:
+                        continue
+                    v = iou(d, g)
+                    if v > best:
+                        best, bj = v, j
+                if best >= 0.99:
+                    used.add(bj)
+                    stats["matched_iou99"] += 1
+                    stats["min_iou_matched"] = min(stats["min_iou_matched"], best)
+                    stats["max_landmark_err_px"] = max(stats["max_landmark_err_px"], float(np.abs(got[bj][5:] - d[5:]).max()))
+                    rect = boxes_to_rects(d[None, :4], np.zeros(1, np.int64), Wd, H)[0]
+                    k = np.nonzero((res.face_frame == b) & (res.face_det == bj))[0]
+                    if len(k) and rect[3] > 0 and rect[4] > 0 and tuple(res.rects[k[0]][1:]) == tuple(rect[1:]):
+                        _, x0, y0, w, h = rect
+                        face = crop.standardize(crop.resize_linear_u8(frames[b][y0:y0 + h, x0:x0 + w]))
+                        ref = nets.irv1_forward(Pe, torch.from_numpy(face).permute(2, 0, 1)[None].contiguous())[0].numpy()
+                        stats["cos_min"] = min(stats["cos_min"], float((ref * res.embeddings[k[0]]).sum()))
+                        stats["cos_n"] += 1
+                else:
+                    all_ok = False
+                    if border:
+                        stats["borderline_oracle_faces"] += 1
+                    else:
+                        ok_band = False
+            if len(got) != len(used):
+                all_ok = False
+            stats["frames_identical"] += int(all_ok)
+            stats["frames_identical_outside_band"] += int(all_ok or ok_band)
+    stats["face_match_rate"] = stats["matched_iou99"] / max(stats["oracle_faces"], 1)
+    stats.update({"backbone": backbone, "H": H, "W": Wd, "frame_indices": idx, "dtype": "fp16 activations, fp32 accumulate"})
+    return stats
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backbone", default="mnet025")
+    ap.add_argument("--height", type=int, default=360)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--frames", type=int, default=48)
+    ap.add_argument("--stride", type=int, default=7)
+    a = ap.parse_args()
+    print(json.dumps(run(a.backbone, a.height, a.width, a.frames, stride=a.stride)))
