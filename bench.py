@@ -15,7 +15,7 @@ like the reference's --shard-i/--n-shards split (no data-path collective): weak 
 `value`  : frames/s with the batch already resident in HBM when the timed region starts.
 `e2e`    : the same through the host-facing call (FacePipeline.detect_embed) with pinned HOST frames:
            H2D of the batch and D2H of detections + embeddings inside the timed region.
-`roofline`: the RetinaFace-R50 forward (82 conv launches of conv_igemm_kernel + 1 max-pool), timed with
+`roofline`: the RetinaFace-R50 forward (70 launches of conv_tma_kernel after layer fusion + 1 max-pool), timed with
            CUDA events on the launching stream inside the timed region; algorithmic work
            449.71 GFLOP/frame x 64 frames per launch of the forward.
 """
@@ -325,7 +325,7 @@ def run_b200(a):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": fwd_tflops / peak, "traffic": None,
-                         "kernel": f"conv_igemm_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
+                         "kernel": f"conv_tma_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
         if world == 1 and not a.no_cpu_baseline:

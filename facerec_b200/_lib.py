@@ -49,6 +49,7 @@ SIGNATURES = {
     "frb_irv1_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "frb_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _i, _i,
                         _vp, _i, _i, C.POINTER(_f), _vp]),
+    "frb_scene_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "frb_segment_mean": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "frb_pdist": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "frb_knn_topk": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),

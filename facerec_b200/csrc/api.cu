@@ -109,6 +109,15 @@ int frb_irv1_forward(frb_ctx* ctx, const void* d_in16, int F, float* d_emb, void
   return net_forward_irv1(ctx, net, d_in16, F, d_emb, static_cast<cudaStream_t>(stream));
 }
 
+int frb_scene_stats(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, int crop, const uint8_t* d_prev_frame,
+                    const double* d_prev_cdf, uint32_t* d_hist, double* d_cdf, double* d_sums, void* stream) {
+  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_NEED(ctx, d_frames_rgb && d_hist && d_cdf && d_sums, "frb_scene_stats: null pointer");
+  FRB_NEED(ctx, (d_prev_frame == nullptr) == (d_prev_cdf == nullptr), "frb_scene_stats: prev frame and prev cdf go together");
+  return run_scene_stats(ctx, d_frames_rgb, B, H, W, crop, d_prev_frame, d_prev_cdf, d_hist, d_cdf, d_sums,
+                         static_cast<cudaStream_t>(stream));
+}
+
 int frb_segment_mean(frb_ctx* ctx, const float* d_X, const int32_t* d_offsets, int S, int D, float* d_out, void* stream) {
   if (ctx == nullptr) return FRB_ERR_INVALID;
   FRB_NEED(ctx, S == 0 || (d_X && d_offsets && d_out), "frb_segment_mean: null pointer");

@@ -6,11 +6,14 @@
 //   [64 ch, bw (stride sw), bh (stride sh), bb]   at   (c0, w0*sw - pw + s, h0*sh - ph + r, b0)
 // which TMA delivers straight into the 128-byte-swizzled K-major layout tcgen05.mma consumes; padding
 // and ragged image borders are the tensor map's out-of-bounds zero fill.  Weights come the same way
-// (2-D box of the [Cout, K] matrix).  Accumulators live in TMEM (double buffered, 2 x BN columns), and
-// the epilogue (bias, residual, per-channel slope) packs 64-column slabs into a swizzled staging tile
-// that TMA stores back as the same patch box — partial tiles are clipped by the hardware, and every
-// global store is a full 128-byte line.  The residual tile (ResNet / Inception skip) is prefetched by
-// TMA into shared memory while the tile's MMAs are still running.
+// (2-D box of the [Cout, K] matrix); when the whole weight matrix is small (<= 80 KB: the bandwidth-bound
+// early layers) it is loaded ONCE per CTA and stays resident, so the stage ring carries only A and the
+// L2 -> SM traffic drops by the weight re-fetch of every tile.  Accumulators live in TMEM (double
+// buffered, 2 x BN columns), and the epilogue (bias, residual, per-channel slope) packs 64-column slabs
+// into a swizzled staging tile that TMA stores back as the same patch box — partial tiles are clipped by
+// the hardware, and every global store is a full 128-byte line.  The residual tile (ResNet / Inception
+// skip) is a producer-side TMA prefetch, double buffered across tiles, so its latency hides behind the
+// previous tile's epilogue.
 //
 // Warp roles (576 threads): 0-15 epilogue, 16 MMA issuer + TMEM allocator, 17 TMA producer.
 // The epilogue is instruction-issue bound when one warp per scheduler walks a whole 64-column row
@@ -30,7 +33,9 @@ constexpr int kTmaThreads = kEpiThreads + 64;
 constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
 constexpr int kSlabBytes = kBM * kSlab * 2;
 constexpr int kColsPerWarp = kSlab / (kEpiWarps / 4);   // 16
-constexpr int kOutBufs = 4;                // staging slabs in flight (TMA stores drain asynchronously)
+constexpr int kOutBufs = 2;                // staging slabs (TMA stores drain asynchronously)
+constexpr int kResSets = 2;                // residual tiles in flight (each = up to 2 slabs)
+constexpr int kResidentWeightBytes = 80 * 1024;
 
 struct ConvTmaArgs {
   int patch;             // 0: linear M tiling (1x1, stride 1, no padding); 1: spatial patch tiling
@@ -42,6 +47,7 @@ struct ConvTmaArgs {
   int bw, bh, bb;        // patch = bb images x bh rows x bw cols (<= 128 pixels)
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
   int stages;
+  int b_resident;        // whole weight matrix stays in shared memory (n_tiles * num_kb blocks of BN x 64)
   int act_kind;          // 0: per-channel slope (general), 1: ReLU everywhere, 2: linear everywhere
   const float* bias;     // [n_tiles*BN]
   const float* slope;    // [n_tiles*BN]
@@ -62,18 +68,21 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int b_stage_bytes = p.BN * 128;
+  const bool has_res = p.res_mode == RES_PRE_ACT;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;
-  uint8_t* smem_o = smem_b + p.stages * b_stage_bytes;          // kOutBufs staging slabs
-  uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                    // 2 residual slabs (PRE_ACT only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (p.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0));
+  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;                                  // ring (or resident matrix)
+  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages) * b_stage_bytes;
+  uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                                    // kResSets x 2 slabs (PRE_ACT only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (has_res ? kResSets * 2 * kSlabBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]
-  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);    // [256]
+  uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;    // [kResSets]
+  uint64_t* rempty_bar = bars + 2 * kMaxStages + 6;   // [kResSets]
+  uint64_t* bres_bar = bars + 2 * kMaxStages + 8;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 9);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 10);   // [256]
   float* s_slope = s_bias + 256;                                          // [256]
 
   const int warp = threadIdx.x >> 5;
@@ -86,7 +95,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    if (p.res_mode == RES_PRE_ACT) tma_prefetch_desc(&tmR);
+    if (has_res) tma_prefetch_desc(&tmR);
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -97,8 +106,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull_bar[b], 1);
         mbar_init(&tempty_bar[b], kEpiWarps);
-        mbar_init(&res_bar[b], 1);
+        mbar_init(&rfull_bar[b], 1);
+        mbar_init(&rempty_bar[b], 1);
       }
+      mbar_init(bres_bar, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -144,15 +155,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       const int n_base = n_tile * p.BN;
       const int buf = tile_iter & 1;
       const uint32_t tphase = (tile_iter >> 1) & 1;
+      const int rset = tile_iter % kResSets;
+      const uint32_t rphase = (tile_iter / kResSets) & 1;
 
-      if (p.res_mode == RES_PRE_ACT && threadIdx.x == 0) {
-        // both residual slabs were consumed before the last named barrier of the previous tile
-        for (int rs = 0; rs < nslab; ++rs) {
-          mbar_arrive_expect_tx(&res_bar[rs], static_cast<uint32_t>(p.a_bytes));
-          if (p.patch) tma_load_4d(smem_r + rs * kSlabBytes, &tmR, &res_bar[rs], n_base + rs * kSlab, c1, c2, c3);
-          else tma_load_2d(smem_r + rs * kSlabBytes, &tmR, &res_bar[rs], n_base + rs * kSlab, c1);
-        }
-      }
       const typename E::T* up_row = nullptr;
       if (p.res_mode == RES_POST_ACT_UPSAMPLE) {
         const int m = c1 + row;
@@ -177,6 +182,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
+      if (has_res) mbar_wait(&rfull_bar[rset], rphase, p.watchdog, 500 + rset);
 
       for (int s = 0; s < nslab; ++s) {
         const int ncols = min(kSlab, p.BN - s * kSlab);
@@ -201,8 +207,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         named_bar_sync(1, kEpiThreads);
 
         if (mine) {
-          if (p.res_mode == RES_PRE_ACT) mbar_wait(&res_bar[s], tile_iter & 1, p.watchdog, 500 + s);
-          const uint8_t* rrow = smem_r + s * kSlabBytes + row_off;
+          const uint8_t* rrow = smem_r + (rset * 2 + s) * kSlabBytes + row_off;
           uint8_t* orow = smem_o + ob * kSlabBytes + row_off;
 #pragma unroll
           for (int c = 0; c < kColsPerWarp / 8; ++c) {
@@ -213,7 +218,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
             const float4 b1 = *reinterpret_cast<const float4*>(s_bias + s * kSlab + cc + 4);
             y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
             y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
-            if (p.res_mode == RES_PRE_ACT) {
+            if (has_res) {
               const uint4 r = *reinterpret_cast<const uint4*>(rrow + chunk);
               float2 f;
               f = E::to_f2(r.x); y[0] += f.x; y[1] += f.y;
@@ -255,6 +260,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
           else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
           tma_store_commit();
+          // every epilogue thread is past its reads of this tile's residual slabs: give the set back
+          if (has_res && s == nslab - 1) mbar_arrive(&rempty_bar[rset]);
         }
         ++slab_ctr;
       }
@@ -266,9 +273,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     int tile_iter = 0;
+    if (p.b_resident) mbar_wait(bres_bar, 0, p.watchdog, 250);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       const int buf = tile_iter & 1;
       const uint32_t tphase = (tile_iter >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
       mbar_wait(&tempty_bar[buf], tphase ^ 1, p.watchdog, 200 + buf);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
@@ -276,8 +285,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         mbar_wait(&full_bar[stage], phase, p.watchdog, 210 + stage);
         tc_fence_after();
         if (lane == 0) {
+          const uint8_t* bsrc = p.b_resident ? smem_b + (n_tile * p.num_kb + kb) * b_stage_bytes : smem_b + stage * b_stage_bytes;
           const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kAStageBytes));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * b_stage_bytes));
+          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(bsrc));
 #pragma unroll
           for (int k4 = 0; k4 < kBK / 16; ++k4)
             tc_mma_f16(d_tmem, a_desc + static_cast<uint64_t>(k4 * 2), b_desc + static_cast<uint64_t>(k4 * 2), idesc,
@@ -293,17 +303,38 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     // ============================================================ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(b_stage_bytes + p.a_bytes);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int tile_iter = 0;
+    if (p.b_resident && lane == 0) {
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.n_tiles * p.num_kb * b_stage_bytes));
+      for (int nt = 0; nt < p.n_tiles; ++nt)
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
+    }
+    const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
+      if (has_res) {
+        // residual tile of THIS tile into set tile_iter % kResSets, as soon as the epilogue released it
+        const int rset = tile_iter % kResSets;
+        mbar_wait(&rempty_bar[rset], ((tile_iter / kResSets) & 1) ^ 1, p.watchdog, 600 + rset);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&rfull_bar[rset], static_cast<uint32_t>(nslab * p.a_bytes));
+          for (int rs = 0; rs < nslab; ++rs) {
+            uint8_t* dst = smem_r + (rset * 2 + rs) * kSlabBytes;
+            if (p.patch) tma_load_4d(dst, &tmR, &rfull_bar[rset], n_tile * p.BN + rs * kSlab, c1, c2, c3);
+            else tma_load_2d(dst, &tmR, &rfull_bar[rset], n_tile * p.BN + rs * kSlab, c1);
+          }
+        }
+        __syncwarp();
+      }
       const int aw = c1 * p.sw - p.pw, ah = c2 * p.sh - p.ph;
       int tap_r = 0, tap_s = 0, cb = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, p.watchdog, 300 + stage);
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, &full_bar[stage], kb * kBK, n_tile * p.BN);
+          if (!p.b_resident) tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, &full_bar[stage], kb * kBK, n_tile * p.BN);
           if (p.patch) tma_load_4d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBK, aw + tap_s, ah + tap_r, c3);
           else tma_load_2d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], kb * kBK, c1);
         }

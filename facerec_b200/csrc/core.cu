@@ -255,8 +255,12 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (m_tiles * L.n_tiles > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv: too many tiles");
   a.total_tiles = static_cast<int>(m_tiles * L.n_tiles);
 
-  const int stage_bytes = kAStageBytes + L.BN * 128;
-  const int fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? 2 * kSlabBytes : 0) + (2 * kMaxStages + 8) * 8 + 2048 + 1024;
+  // small weight matrices (the bandwidth-bound early layers) stay resident in shared memory for the whole kernel
+  const int w_bytes = L.n_tiles * a.num_kb * L.BN * 128;
+  a.b_resident = w_bytes <= kResidentWeightBytes ? 1 : 0;
+  const int stage_bytes = kAStageBytes + (a.b_resident ? 0 : L.BN * 128);
+  const int fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? kResSets * 2 * kSlabBytes : 0) +
+                    (a.b_resident ? w_bytes : 0) + (2 * kMaxStages + 10) * 8 + 2048 + 1024;
   const int budget = 226 * 1024 - fixed;
   a.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;

@@ -65,8 +65,16 @@ class B200FaceNet:
         outs = []
         for i in range(0, rects.shape[0], self.max_batch):
             r = rects[i:i + self.max_batch].contiguous()
+            # the network plan (arena, tile grids) is cached per batch size: round the face count up to a
+            # power of two (>= 8) by repeating the first rectangle, and drop the padding rows afterwards
+            n = r.shape[0]
+            bucket = 8
+            while bucket < n:
+                bucket *= 2
+            if bucket != n:
+                r = torch.cat([r, r[:1].expand(bucket - n, 5)], 0).contiguous()
             faces = ops.crop_resize_std(self.ctx, frames_u8, r)
-            outs.append(ops.irv1_forward(self.ctx, faces))
+            outs.append(ops.irv1_forward(self.ctx, faces)[:n])
         if not outs:
             return torch.empty((0, 512), dtype=torch.float32, device=self.device)
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

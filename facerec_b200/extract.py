@@ -128,8 +128,20 @@ def trajectory_record(trk, max_w: int, max_h: int) -> dict:
 
 
 def dump_line(obj, file):
-    json.dump(obj, file, indent=None, separators=(",", ":"))
+    # json.dumps takes the C encoder (json.dump walks the object in Python); the text is identical
+    file.write(json.dumps(obj, indent=None, separators=(",", ":")))
     file.write("\n")
+
+
+def feature_line(rec: dict, vec, keys) -> str:
+    """One features.jsonl line (facerec/extract.py:186-195), byte-identical to
+    json.dump({...,"embeddings": {k: vec for k in keys},...}, separators=(",", ":")): the 512-float vector is
+    serialised once and spliced in under every key instead of being encoded len(keys) times."""
+    d = lambda o: json.dumps(o, indent=None, separators=(",", ":"))
+    v = d(vec)
+    emb = ",".join(d(k) + ":" + v for k in keys)
+    return ('{"frame":' + d(rec["frame"]) + ',"tag":' + d(rec["tag"]) + ',"embeddings":{' + emb + '},"box":' + d(rec["box"]) +
+            ',"keypoints":' + d(rec["keypoints"]) + ',"w":' + d(rec["w"]) + ',"h":' + d(rec["h"]) + "}")
 
 
 def save_thumbnail(img_np, filtered_box, d_width, d_height, path):
@@ -162,7 +174,7 @@ class Extractor:
         import torch
         from .pipeline import bbox_float_to_int
         from .embedder import crop_rect
-        from .scene import SceneChangeDetector
+        from .scene import SceneChangeDetector, B200SceneChangeDetector
 
         synthetic = file.startswith("synth:")
         src = SyntheticSource(file) if synthetic else VideoSource(file, self.display_width, self.display_height)
@@ -181,7 +193,11 @@ class Extractor:
         print(f"Shard {self.shard_i + 1} / {self.n_shards}: frames {beg} - {end} (+{end_overlap - end} overlap) of "
               f"{src.n_frames}, {d_width}x{d_height}, batches of {self.batch}, saving every 1/{self.save_every} frames")
 
-        scene = SceneChangeDetector(grayscale=False, crop=True, movie_id=movie_id)
+        device = self.embedder.device
+        # scene cuts: batched on the GPU when the frames live there, else the host restatement
+        gpu_scene = device.type == "cuda"
+        scene = (B200SceneChangeDetector(False, True, movie_id, ctx=getattr(self.embedder, "ctx", None)) if gpu_scene
+                 else SceneChangeDetector(grayscale=False, crop=True, movie_id=movie_id))
         tracker = self.tracker
         scene_changes: List[int] = []
         buf = []                      # frames waiting for their tracker verdict (min_trajectory delay)
@@ -219,10 +235,10 @@ class Extractor:
                     raise ValueError("empty face crop (the reference would fail in cv2.resize here)")
                 emb = self.embedder.embed_boxes(frames_d, rects)
                 for i, e in zip(idx, emb):
-                    vec = e.tolist()
-                    pending[i][2]["embeddings"] = {k: vec for k in self.emb_keys}
+                    pending[i][2]["embeddings"] = e.tolist()
             for _, _, rec in pending:
-                dump_line(rec, features_file)
+                features_file.write(feature_line(rec, rec["embeddings"], self.emb_keys))
+                features_file.write("\n")
             pending.clear()
 
         f = beg
@@ -241,10 +257,11 @@ class Extractor:
             frames_h = np.stack(frames)
             frames_d = torch.from_numpy(frames_h).to(device)
             dets = self.detector.detect_batch_raw(frames_d)
+            cuts = scene.update_batch(frames_d) if gpu_scene else None
             pending = []
             for b in range(len(frames)):
                 fi = f + b
-                cut = scene.update(frames_h[b])
+                cut = cuts[b] if gpu_scene else scene.update(frames_h[b])
                 faces = self.detector.format(dets[b])
                 buf.append({"index": fi, "img_np": frames_h[b], "faces": faces, "tag": f"{movie_id}:{fi}", "slot": (batch_id, b)})
                 if cut:

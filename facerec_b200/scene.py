@@ -63,3 +63,58 @@ class SceneChangeDetector:
         self.prev_img = y
         self.prev_img_eq = y_eq
         return cut
+
+
+class B200SceneChangeDetector:
+    """Batched GPU version: the pixel work of `update` runs in libfacerec_b200.so (frb_scene_stats) on frames already
+    resident in HBM; the scalar recurrences (SDMAFD, ADFV) and the threshold cascade stay on the host.
+    `update_batch(frames_u8_cuda)` returns one bool per frame, equal to calling `update` frame by frame."""
+
+    def __init__(self, grayscale: bool = False, crop: bool = True, movie_id: int = 0, ctx=None):
+        import torch
+        from ._lib import default_context
+        if grayscale:
+            raise ValueError("grayscale=True is not implemented on the GPU path (the extractor uses grayscale=False)")
+        self.crop = crop
+        self.movie_id = movie_id
+        self.ctx = ctx if ctx is not None else default_context(0)
+        self.frame_counter = 0
+        self.prev_frame = None      # last frame of the previous batch (device)
+        self.prev_cdf = None
+        self.prev_mafd_eq = None
+        self.prev_fv_eq = None
+        self._torch = torch
+
+    def update_batch(self, frames):
+        torch = self._torch
+        from ._lib import ptr, current_stream
+        B, H, W, _ = frames.shape
+        dev = frames.device
+        hist = torch.empty((B, 256), dtype=torch.int32, device=dev)
+        cdf = torch.empty((B, 256), dtype=torch.float64, device=dev)
+        sums = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        self.ctx.check(self.ctx.lib.frb_scene_stats(self.ctx.handle, ptr(frames), B, H, W, int(self.crop), ptr(self.prev_frame),
+                                                    ptr(self.prev_cdf), ptr(hist), ptr(cdf), ptr(sums), current_stream()),
+                       "frb_scene_stats")
+        h = hist.cpu().numpy().astype(np.float64)
+        c = cdf.cpu().numpy()
+        s = sums.cpu().numpy()
+        n = h[0].sum()
+        cuts = []
+        for b in range(B):
+            self.frame_counter += 1
+            cut = False
+            if self.frame_counter > 1:
+                mafd = s[b, 0] / n
+                mafd_eq = s[b, 1] / n
+                sdmafd_eq = None if self.prev_mafd_eq is None else mafd_eq - self.prev_mafd_eq
+                fv_eq = float((h[b] * np.abs(c[b] * 255 - mafd_eq)).sum() / n)     # mean |eq - mafd_eq| via the histogram
+                adfv_eq = None if self.prev_fv_eq is None else abs(fv_eq - self.prev_fv_eq)
+                self.prev_fv_eq = fv_eq
+                self.prev_mafd_eq = mafd_eq
+                if sdmafd_eq is not None and adfv_eq is not None:
+                    cut = SceneChangeDetector.check(mafd, mafd_eq, sdmafd_eq, adfv_eq)
+            cuts.append(bool(cut))
+        self.prev_frame = frames[B - 1].clone()
+        self.prev_cdf = cdf[B - 1].clone()
+        return cuts

@@ -137,6 +137,16 @@ int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, c
                int res_mode, int rH, int rW, void* d_out, int out_fp32, int iters, float* h_ms /*nullable*/,
                void* stream);
 
+/* Scene-cut statistics of a batch of RGB frames (the per-frame work of SceneChangeDetector.update,
+ * facerec/scene.py:81-133, called at facerec/extract.py:301).  Per frame b: d_hist[b] = 256-bin histogram of
+ * floor(luminance) over the centre 2:1 crop (crop != 0), d_cdf[b] = its float64 cumulative distribution,
+ * d_sums[b] = { sum |Y_b - Y_(b-1)|, sum |eq_b - eq_(b-1)| } over the cropped pixels, eq = cdf[floor(Y)] * 255.
+ * Frame 0 is compared with d_prev_frame / d_prev_cdf (last frame of the previous batch; both NULL at the
+ * start of a shard, then d_sums[0] stays 0).  The threshold cascade (scene.py:65-79) stays on the host. */
+int frb_scene_stats(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, int crop, const uint8_t* d_prev_frame,
+                    const double* d_prev_cdf, uint32_t* d_hist /*[B,256]*/, double* d_cdf /*[B,256]*/,
+                    double* d_sums /*[B,2]*/, void* stream);
+
 /* ---- embedding-distance stage ------------------------------------------------------------- */
 
 /* K12  per-trajectory mean of per-frame embeddings (facerec/cluster.py:26-29). */

@@ -111,3 +111,30 @@ def test_preprocess_space_to_depth_layout(ctx):
         for dx in range(2):
             ref[:, :, 2:-1, (dy * 2 + dx) * 4:(dy * 2 + dx) * 4 + 3] = bgr[:, dy::2, dx::2, :]
     assert np.array_equal(out, ref)
+
+
+def test_scene_stats_match_host_detector(ctx):
+    """GPU scene-cut statistics vs the host restatement (itself pinned to facerec/scene.py by tests/golden/scene_cuts.json)."""
+    from facerec_b200 import synth, scene
+    H, W = 180, 320
+    frames = np.stack([synth.frame(77, i, H, W, vary_level=True, scene_len=7) for i in range(60)])
+    host = scene.SceneChangeDetector(False, True, 1)
+    ref, ref_stats = [], []
+    for f in frames:
+        ref.append(bool(host.update(f)))
+        ref_stats.append((host.prev_mafd_eq or 0.0, host.prev_fv_eq or 0.0))
+    gpu = scene.B200SceneChangeDetector(False, True, 1, ctx=ctx)
+    got, got_stats = [], []
+    for lo, hi in ((0, 1), (1, 17), (17, 18), (18, 60)):          # ragged batches, state carried across calls
+        got += gpu.update_batch(torch.from_numpy(frames[lo:hi]).cuda())
+        got_stats.append((gpu.prev_mafd_eq or 0.0, gpu.prev_fv_eq or 0.0))
+    assert got == ref and sum(ref) >= 3
+    for (lo, hi), g in zip(((0, 1), (1, 17), (17, 18), (18, 60)), got_stats):
+        r = ref_stats[hi - 1]
+        assert abs(g[0] - r[0]) <= 1e-9 * max(1.0, abs(r[0])) and abs(g[1] - r[1]) <= 1e-9 * max(1.0, abs(r[1]))
+    # no crop needed for a 2:1 frame, and the wide-frame path takes all rows
+    wide = np.stack([synth.frame(5, i, 100, 200) for i in range(3)])
+    h2 = scene.SceneChangeDetector(False, True, 1)
+    g2 = scene.B200SceneChangeDetector(False, True, 1, ctx=ctx)
+    assert g2.update_batch(torch.from_numpy(wide).cuda()) == [bool(h2.update(f)) for f in wide]
+    assert abs(g2.prev_mafd_eq - h2.prev_mafd_eq) < 1e-9

@@ -197,3 +197,17 @@ def test_shard_arithmetic_and_movie_id():
     assert shard_range(721, 8, 0, 5) == (0, 91, 96)
     assert movie_id_from_path("/x/100001-synthA.avi") == 100001
     assert movie_id_from_path("film-12-part-7.mp4") == 127
+
+
+def test_feature_line_is_byte_identical_to_json_dump():
+    import io as _io
+    from facerec_b200.extract import feature_line, FACENET_KEYS
+    rng = np.random.RandomState(0)
+    vec = rng.standard_normal(512).astype(np.float32).tolist()
+    rec = {"frame": 35, "tag": "100001:35:10_20_110_140", "box": [10, 20, 110, 140],
+           "keypoints": {"left_eye": (30, 50), "right_eye": (70, 51), "nose": (50, 80), "mouth_left": (35, 110), "mouth_right": (66, 111)},
+           "w": 640, "h": 360}
+    ref = _io.StringIO()
+    json.dump({"frame": rec["frame"], "tag": rec["tag"], "embeddings": {k: vec for k in FACENET_KEYS}, "box": rec["box"],
+               "keypoints": rec["keypoints"], "w": 640, "h": 360}, ref, indent=None, separators=(",", ":"))
+    assert feature_line(rec, vec, FACENET_KEYS) == ref.getvalue()
