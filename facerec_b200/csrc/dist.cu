@@ -21,9 +21,11 @@ namespace frb {
 constexpr int kDM = 128;       // tile rows (UMMA M)
 constexpr int kDN = 128;       // tile cols (UMMA N)
 constexpr int kDK = 64;        // K elements per stage
-constexpr int kDStages = 5;
+constexpr int kDStages = 4;
 constexpr int kDStageBytes = (kDM + kDN) * kDK * 2;
-constexpr int kDThreads = 192;
+constexpr int kDEpiWarps = 16;   // 4 warps per TMEM lane quarter, 32 tile columns each (the epilogue is issue-bound)
+constexpr int kDSub = kDEpiWarps / 4;
+constexpr int kDThreads = (kDEpiWarps + 2) * 32;
 constexpr int kTopK = 16;      // per-row candidates kept in registers (k <= 16)
 
 enum DistMode : int { DIST_SQUARE_F32 = 0, DIST_CONDENSED_F32 = 1, DIST_CONDENSED_F64 = 2, DIST_KNN = 3 };
@@ -39,7 +41,7 @@ struct DistArgs {
   const float* na;       // |a|^2 indexed by global A row
   const float* nb;       // |b|^2
   void* out;
-  float* part_d;         // kNN partial lists [Qrows, chunks, kTopK]
+  float* part_d;         // kNN partial lists [Qrows, chunks, kDSub, kTopK]
   int32_t* part_i;
   int* watchdog;
 };
@@ -109,8 +111,8 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kDStages * kDM * kDK * 2;
-  float* tr = reinterpret_cast<float*>(smem + kDStages * kDStageBytes);        // [4][32][33]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tr + 4 * 32 * 33);
+  float* tr = reinterpret_cast<float*>(smem + kDStages * kDStageBytes);        // [kDEpiWarps][32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tr + kDEpiWarps * 32 * 33);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kDStages;
   uint64_t* tfull_bar = bars + 2 * kDStages;
@@ -121,11 +123,11 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * kDN;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kDEpiWarps + 1 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 4) {
+  if (warp == kDEpiWarps) {
     if (lane == 0) {
       for (int s = 0; s < kDStages; ++s) {
         mbar_init(&full_bar[s], 1);
@@ -133,7 +135,7 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tfull_bar[b], 1);
-        mbar_init(&tempty_bar[b], 4);
+        mbar_init(&tempty_bar[b], kDEpiWarps);
       }
       fence_mbar_init();
     }
@@ -148,13 +150,15 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
   const int kb_per_seg = p.Dp / kDK;
   const int num_kb = 3 * kb_per_seg;
 
-  if (warp < 4) {
+  if (warp < kDEpiWarps) {
     // ================================================================ epilogue
+    const int quarter = warp & 3;            // TMEM lane quarter
+    const int csub = warp >> 2;              // 32-column sub-block of the 128-column tile
     float* mytr = tr + warp * 32 * 33;
     int tile_iter = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const ItemRange ir = item_range(p, item);
-      const int li = ir.m_tile * kDM + warp * 32 + lane;   // local A row of this thread
+      const int li = ir.m_tile * kDM + quarter * 32 + lane;   // local A row of this thread
       const int gi = p.row0 + li;                          // global A row
       const bool row_ok = li < p.rows;
       const float na = row_ok ? __ldg(p.na + gi) : 0.f;
@@ -171,10 +175,10 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
         const uint32_t tphase = (tile_iter >> 1) & 1;
         mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kDN);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kDN);
         const int n_base = n_tile * kDN;
         if (p.mode == DIST_KNN) {
-          for (int n0 = 0; n0 < kDN; n0 += 16) {
+          for (int n0 = csub * 32; n0 < csub * 32 + 32; n0 += 16) {
             uint32_t v[16];
             __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the data-dependent inserts
             tmem_ld16(taddr + n0, v);
@@ -189,7 +193,8 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
             }
           }
         } else {
-          for (int n0 = 0; n0 < kDN; n0 += 32) {
+          {
+            const int n0 = csub * 32;
             uint32_t v[32];
             __syncwarp();
             tmem_ld16(taddr + n0, v);
@@ -206,7 +211,7 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
             const int j = n_base + n0 + lane;
             for (int r = 0; r < 32; ++r) {
               const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
-              const int rli = ir.m_tile * kDM + warp * 32 + r;
+              const int rli = ir.m_tile * kDM + quarter * 32 + r;
               const int rgi = p.row0 + rli;
               const bool ok = rli < p.rows && j < p.N && (p.mode == DIST_SQUARE_F32 || j > rgi);
               if (ok) {
@@ -223,12 +228,12 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       }
       if (p.mode == DIST_KNN && row_ok && ir.n_end > ir.n_begin) {
-        const size_t o = (static_cast<size_t>(li) * p.chunks + ir.chunk) * kTopK;
+        const size_t o = ((static_cast<size_t>(li) * p.chunks + ir.chunk) * kDSub + csub) * kTopK;
 #pragma unroll
         for (int t = 0; t < kTopK; ++t) { p.part_d[o + t] = td[t]; p.part_i[o + t] = tid[t]; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kDEpiWarps) {
     // ============================================================== MMA issuer
     const uint32_t idesc = make_idesc_f16(kDM, kDN, 1);
     int stage = 0;
@@ -287,7 +292,7 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kDEpiWarps) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, kTmemCols);
   }
@@ -371,7 +376,7 @@ static int split_rows(frb_ctx* ctx, const float* d_x, int n, int D, int Dp, void
   return check_last(ctx, "split_rows_kernel");
 }
 
-static size_t dist_smem_bytes() { return static_cast<size_t>(kDStages) * kDStageBytes + 4 * 32 * 33 * 4 + (2 * kDStages + 4) * 8 + 16 + 1024; }
+static size_t dist_smem_bytes() { return static_cast<size_t>(kDStages) * kDStageBytes + kDEpiWarps * 32 * 33 * 4 + (2 * kDStages + 4) * 8 + 16 + 1024; }
 
 static int launch_dist(frb_ctx* ctx, const DistArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
   static bool attr_set = false;
@@ -449,7 +454,7 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   const long long items = static_cast<long long>(a.m_tiles) * a.chunks;
   if (items > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "knn_topk: too many items");
   a.items = static_cast<int>(items);
-  const size_t part = static_cast<size_t>(Q) * a.chunks * kTopK;
+  const size_t part = static_cast<size_t>(Q) * a.chunks * kDSub * kTopK;
   if ((rc = ctx_scratch(ctx, 4, part * 4, &pd)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 5, part * 4, &pi)) != FRB_OK) return rc;
   if ((rc = split_rows(ctx, d_DB, M, D, Dp, ds, static_cast<float*>(dn), st)) != FRB_OK) return rc;
@@ -463,7 +468,7 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   a.part_i = static_cast<int32_t*>(pi);
   a.watchdog = ctx->wd_dev;
   if ((rc = launch_dist(ctx, a, tmA, tmB, st)) != FRB_OK) return rc;
-  knn_merge_kernel<<<(Q + 127) / 128, 128, 0, st>>>(a.part_d, a.part_i, Q, a.chunks, k, a.na, d_idx, d_dist);
+  knn_merge_kernel<<<(Q + 127) / 128, 128, 0, st>>>(a.part_d, a.part_i, Q, a.chunks * kDSub, k, a.na, d_idx, d_dist);
   ctx->launches++;
   return check_last(ctx, "knn_merge_kernel");
 }
