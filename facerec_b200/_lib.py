@@ -65,6 +65,12 @@ def load_library() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        try:                                  # fresh checkout: compile in-tree with nvcc (no GPU needed to build)
+            from . import build as _build
+            _build.build()
+        except Exception as e:                # noqa: BLE001
+            raise RuntimeError(f"{LIB_PATH} is missing and could not be built: {e}") from e
+    if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(facerec_b200 has no CPU fallback)")
