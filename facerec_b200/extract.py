@@ -176,8 +176,11 @@ class Extractor:
         from .embedder import crop_rect
         from .scene import SceneChangeDetector, B200SceneChangeDetector
 
-        synthetic = file.startswith("synth:")
-        src = SyntheticSource(file) if synthetic else VideoSource(file, self.display_width, self.display_height)
+        if not isinstance(file, str):      # any object with the VideoSource interface (+ movie_id), e.g. preloaded frames
+            src, synthetic = file, True
+        else:
+            synthetic = file.startswith("synth:")
+            src = SyntheticSource(file) if synthetic else VideoSource(file, self.display_width, self.display_height)
         movie_id = src.movie_id if synthetic else movie_id_from_path(file)
         d_width, d_height = src.width, src.height
         beg, end, end_overlap = shard_range(src.n_frames, self.n_shards, self.shard_i, self.max_trajectory_age)
@@ -241,21 +244,48 @@ class Extractor:
                 features_file.write("\n")
             pending.clear()
 
+        # Frame ingest: a reader thread decodes the next batches into (pinned) host buffers while the
+        # GPU works on the current one; cv2 releases the GIL while decoding.
+        import queue
+        import threading
+        n_to_read = end_overlap - beg
+        batches_q: "queue.Queue" = queue.Queue(maxsize=2)
+        pin = device.type == "cuda"
+
+        def reader():
+            left = n_to_read
+            try:
+                while left > 0:
+                    frames = []
+                    while len(frames) < self.batch and len(frames) < left:
+                        fr = src.read()
+                        if fr is None:
+                            left = len(frames)
+                            break
+                        frames.append(fr)
+                    if not frames:
+                        break
+                    arr = np.stack(frames)
+                    t = torch.from_numpy(arr)
+                    batches_q.put((arr, t.pin_memory() if pin else t))
+                    left -= len(frames)
+            except BaseException as e:      # noqa: BLE001 - surface decode errors on the consumer side
+                batches_q.put(e)
+                return
+            batches_q.put(None)
+
+        threading.Thread(target=reader, daemon=True).start()
         f = beg
         batch_id = 0
-        done = False
-        while f < end_overlap and not done:
-            frames = []
-            while len(frames) < self.batch and f + len(frames) < end_overlap:
-                fr = src.read()
-                if fr is None:
-                    done = True
-                    break
-                frames.append(fr)
-            if not frames:
+        while True:
+            item = batches_q.get()
+            if item is None:
                 break
-            frames_h = np.stack(frames)
-            frames_d = torch.from_numpy(frames_h).to(device)
+            if isinstance(item, BaseException):
+                raise item
+            frames_h, frames_t = item
+            frames = frames_h
+            frames_d = frames_t.to(device, non_blocking=True)
             dets = self.detector.detect_batch_raw(frames_d)
             cuts = scene.update_batch(frames_d) if gpu_scene else None
             pending = []
