@@ -52,6 +52,7 @@ SIGNATURES = {
     "frb_scene_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "frb_segment_mean": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "frb_pdist": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "frb_linkage_complete": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "frb_knn_topk": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "frb_knn_vote": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
 }

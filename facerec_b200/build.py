@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfacerec_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["core.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu", "api.cu"]
+SOURCES = ["core.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu", "linkage.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",

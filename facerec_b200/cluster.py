@@ -33,13 +33,15 @@ def read_trajectories(data_dir: str, vector_map, emb_name: str = EMB_NAME):
     return trajectories, np.array(means)
 
 
-def cluster_once(vectors: np.ndarray, n_clusters: int, pdist_fn: Callable[[np.ndarray], np.ndarray]) -> np.ndarray:
-    """Complete-linkage clustering cut at n_clusters (facerec/cluster.py:33-45), distances from pdist_fn."""
+def cluster_once(vectors: np.ndarray, n_clusters: int, pdist_fn: Optional[Callable[[np.ndarray], np.ndarray]],
+                 linkage_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None) -> np.ndarray:
+    """Complete-linkage clustering cut at n_clusters (facerec/cluster.py:33-45).  `linkage_fn(vectors) -> Z` does
+    distances + linkage in one go (GPU: distance.gpu_linkage_complete); otherwise scipy links `pdist_fn(vectors)`."""
     if vectors.shape[0] == 0:
         return np.array([], dtype=np.int32)
     if vectors.shape[0] == 1:
         return np.array([1], dtype=np.int32)
-    link = hierarchy.linkage(pdist_fn(vectors), method="complete")
+    link = linkage_fn(vectors) if linkage_fn is not None else hierarchy.linkage(pdist_fn(vectors), method="complete")
     return hierarchy.fcluster(link, t=n_clusters, criterion="maxclust")
 
 
@@ -76,19 +78,21 @@ def relabel(clusters: np.ndarray) -> np.ndarray:
 
 
 def cluster_trajectories(trajectories, embeddings: np.ndarray, size: int, min_size: int, max_size: int,
-                         pdist_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None) -> np.ndarray:
-    """facerec/cluster.py:163-214: N//size clusters, re-cluster the oversize ones, label by descending size."""
-    if pdist_fn is None:
-        from .distance import gpu_pdist
-        pdist_fn = gpu_pdist
+                         pdist_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None,
+                         linkage_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None) -> np.ndarray:
+    """facerec/cluster.py:163-214: N//size clusters, re-cluster the oversize ones, label by descending size.
+    Default: distance matrix AND complete linkage on the GPU; pass pdist_fn to keep scipy's linkage on the host."""
+    if pdist_fn is None and linkage_fn is None:
+        from .distance import gpu_linkage_complete
+        linkage_fn = gpu_linkage_complete
     n = len(trajectories)
     n_clusters = n // size
     print(f"N={n} size={size} n_clusters={n_clusters}")
-    clusters = cluster_once(embeddings, n_clusters, pdist_fn)
+    clusters = cluster_once(embeddings, n_clusters, pdist_fn, linkage_fn)
     for ci, cnt in zip(*np.unique(clusters, return_counts=True)):
         if cnt > max_size:
             idx = np.where(ci == clusters)[0]
-            sub = cluster_once(embeddings[idx], (cnt + max_size - 1) // max_size, pdist_fn)
+            sub = cluster_once(embeddings[idx], (cnt + max_size - 1) // max_size, pdist_fn, linkage_fn)
             sub = split_and_merge(sub, min_size, max_size)
             clusters[idx] = clusters.max() + 1 + sub
     clusters = relabel(clusters)

@@ -130,6 +130,12 @@ int frb_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, 
   return run_pdist(ctx, d_X, N, D, row0, rows, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int frb_linkage_complete(frb_ctx* ctx, float* d_D, int N, int32_t* d_merge_pairs, float* d_merge_dist, void* stream) {
+  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_NEED(ctx, d_D && d_merge_pairs && d_merge_dist, "frb_linkage_complete: null pointer");
+  return run_linkage_complete(ctx, d_D, N, d_merge_pairs, d_merge_dist, static_cast<cudaStream_t>(stream));
+}
+
 int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k, int32_t* d_idx,
                  float* d_dist, void* stream) {
   if (ctx == nullptr) return FRB_ERR_INVALID;

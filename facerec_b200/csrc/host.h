@@ -123,6 +123,9 @@ int run_knn_vote(frb_ctx*, const int32_t* d_idx, const int32_t* d_label_idx, int
                  cudaStream_t);
 int run_segment_mean(frb_ctx*, const float* d_X, const int32_t* d_offsets, int S, int D, float* d_out, cudaStream_t);
 
+// ------------------------------------------------------------------ clustering (linkage.cu)
+int run_linkage_complete(frb_ctx*, float* d_D, int n, int32_t* d_zxy, float* d_zd, cudaStream_t);
+
 // ------------------------------------------------------------------ scene cuts (scene.cu)
 int run_scene_stats(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int crop, const uint8_t* d_prev_frame,
                     const double* d_prev_cdf, uint32_t* d_hist, double* d_cdf, double* d_sums, cudaStream_t);

@@ -132,3 +132,47 @@ class B200KNeighborsClassifier:
 
     def predict(self, V) -> np.ndarray:
         return self.classes_[np.argmax(self.predict_proba(V), axis=1)]
+
+
+def _label_merges(pairs: np.ndarray, dist: np.ndarray, n: int) -> np.ndarray:
+    """Raw NN-chain merges -> scipy's linkage matrix Z: stable sort by height, then union-find relabelling of the
+    two children to cluster ids (new clusters are numbered n, n+1, ... in sorted order; lower id first)."""
+    order = np.argsort(dist, kind="mergesort")
+    pairs, dist = pairs[order], dist[order]
+    parent = np.arange(2 * n - 1)
+    size = np.ones(2 * n - 1, dtype=np.int64)
+    Z = np.empty((n - 1, 4), dtype=np.float64)
+
+    def find(x):
+        root = x
+        while parent[root] != root:
+            root = parent[root]
+        while parent[x] != root:
+            parent[x], x = root, parent[x]
+        return root
+
+    nxt = n
+    for k in range(n - 1):
+        a, b = find(int(pairs[k, 0])), find(int(pairs[k, 1]))
+        if a > b:
+            a, b = b, a
+        parent[a] = parent[b] = nxt
+        size[nxt] = size[a] + size[b]
+        Z[k] = (a, b, dist[k], size[nxt])
+        nxt += 1
+    return Z
+
+
+def gpu_linkage_complete(vectors: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
+    """scipy.cluster.hierarchy.linkage(vectors, method="complete") with both the distance matrix and the clustering on
+    the GPU (facerec/cluster.py:41): returns the float64 linkage matrix Z that `fcluster` consumes.  Identical to
+    scipy's Z for the same (fp32) distances, ties included."""
+    ctx = _ctx(ctx)
+    X = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(torch.device("cuda", ctx.device))
+    n = X.shape[0]
+    D = ops.pdist(ctx, X, layout=_lib.FRB_SQUARE_F32)
+    pairs = torch.empty((n - 1, 2), dtype=torch.int32, device=X.device)
+    dist = torch.empty((n - 1,), dtype=torch.float32, device=X.device)
+    ctx.check(ctx.lib.frb_linkage_complete(ctx.handle, D.data_ptr(), n, pairs.data_ptr(), dist.data_ptr(),
+                                           _lib.current_stream()), "frb_linkage_complete")
+    return _label_merges(pairs.cpu().numpy(), dist.cpu().numpy().astype(np.float64), n)

@@ -159,6 +159,15 @@ int frb_segment_mean(frb_ctx* ctx, const float* d_X /*[n,D]*/, const int32_t* d_
  * Replaces the implicit pdist inside scipy linkage (facerec/cluster.py:41,199). */
 int frb_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, void* stream);
 
+/* Complete-linkage clustering of the N x N fp32 distance matrix d_D (FRB_SQUARE_F32 output of frb_pdist; it is
+ * overwritten), nearest-neighbour-chain algorithm with scipy's tie rules.  Outputs the N-1 merges in the order
+ * they are found: d_merge_pairs[k] = (dying cluster, surviving cluster) as ORIGINAL point indices with
+ * pairs[k][0] < pairs[k][1], d_merge_dist[k] = merge height.  The host sorts them by height (stable) and
+ * relabels to get scipy's Z (facerec_b200/distance.py::gpu_linkage_complete).
+ * Replaces the host side of scipy.cluster.hierarchy.linkage(y, "complete") (facerec/cluster.py:41,199). */
+int frb_linkage_complete(frb_ctx* ctx, float* d_D /*[N,N]*/, int N, int32_t* d_merge_pairs /*[N-1,2]*/,
+                         float* d_merge_dist /*[N-1]*/, void* stream);
+
 /* K14  k smallest Euclidean distances, never materialising Q x M.  Ties -> lower DB index.
  * Replaces KNeighborsClassifier.fit/kneighbors (facerec/classify_knn.py:212,227). */
 int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k,

@@ -126,3 +126,29 @@ def test_segment_mean_matches_numpy(ctx):
     got = ops.segment_mean(ctx, torch.from_numpy(x).cuda(), torch.from_numpy(off).cuda()).cpu().numpy()
     ref = np.stack([x[off[i]:off[i + 1]].mean(axis=0) for i in range(len(lens))])
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n,d,dup", [(2, 8, False), (37, 16, False), (700, 512, False), (1500, 512, False), (400, 4, True)])
+def test_gpu_linkage_equals_scipy_on_same_distances(ctx, n, d, dup):
+    """frb_linkage_complete + host relabelling == scipy linkage(method='complete') fed the SAME fp32 distances
+    (bit-identical Z, ties included: `dup` plants duplicate points and a coarse grid so many distances tie)."""
+    from scipy.cluster.hierarchy import linkage, fcluster
+    from facerec_b200 import ops, _lib, distance
+    rng = np.random.RandomState(n)
+    if dup:
+        x = rng.randint(0, 4, (n, d)).astype(np.float32)
+    else:
+        x = _mixture(rng, n, d, centres=max(2, n // 18), unit=False)
+    Z = distance.gpu_linkage_complete(x, ctx)
+    cond = ops.pdist(ctx, torch.from_numpy(x).cuda(), layout=_lib.FRB_CONDENSED_F32).cpu().numpy().astype(np.float64)
+    ref = linkage(cond, method="complete")
+    assert np.array_equal(Z, ref)
+    if n >= 36:
+        k = n // 18
+        assert np.array_equal(fcluster(Z, t=k, criterion="maxclust"), fcluster(ref, t=k, criterion="maxclust"))
+
+
+def test_label_merges_matches_scipy_convention():   # (host-only logic, runs with the gpu-marked module)
+    from facerec_b200.distance import _label_merges
+    Z = _label_merges(np.array([[0, 3], [1, 2], [2, 3]], np.int32), np.array([0.5, 0.2, 0.9]), 4)
+    assert Z.tolist() == [[1.0, 2.0, 0.2, 2.0], [0.0, 3.0, 0.5, 2.0], [4.0, 5.0, 0.9, 4.0]]

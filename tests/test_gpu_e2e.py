@@ -103,3 +103,34 @@ def test_extract_cluster_classify_pipeline(ctx, tmp_path):
         tr, means = cluster.read_trajectories(d, vm)
         keep = [i for i, m in enumerate(means) if np.ndim(m) == 1]
         assert len(keep) >= 2
+
+
+def test_cluster_and_classify_on_gpu_reproduce_reference_outputs(ctx, tmp_path):
+    """The golden film (reference cluster.py + classify_knn.py outputs, tools/make_golden.py) through the GPU distance,
+    GPU linkage and GPU kNN: clusters.json and predictions.json must come out byte-identical."""
+    import contextlib
+    import io
+    import json
+    import zipfile
+    from facerec_b200 import cluster, classify_knn, formats
+    film = json.load(open(os.path.join(ROOT, "tests", "golden", "film_small.json")))
+    d = tmp_path / "100001-data"
+    d.mkdir()
+    with open(d / "features.jsonl", "w") as fh:
+        for o in film["features"]:
+            fh.write(json.dumps(o, separators=(",", ":")) + "\n")
+    with open(d / "trajectories.jsonl", "w") as fh:
+        for o in film["trajectories"]:
+            fh.write(json.dumps(o, separators=(",", ":")) + "\n")
+    with zipfile.ZipFile(d / "actor-images.zip", "w") as z:
+        for i, a in enumerate(film["actors"]):
+            z.writestr(f"img{i:04d}.json", json.dumps(a))
+    d = str(d)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vm = formats.read_features(d)
+        traj, means = cluster.read_trajectories(d, vm)
+        cluster.write_clusters(cluster.cluster_trajectories(traj, means, 18, 12, 24), d, 100001)
+        X, y = classify_knn.get_class_data(classify_knn.read_actor_embeddings(os.path.join(d, "actor-images.zip")), 20)
+        classify_knn.classify(d, X, y, 10)
+    assert open(os.path.join(d, "clusters.json")).read() == film["clusters_json"]
+    assert open(os.path.join(d, "predictions.json")).read() == film["predictions_json"]

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--q", type=int, default=50000)
     ap.add_argument("--m", type=int, default=1000000)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--link-n", type=int, default=50000)
     a = ap.parse_args()
     ctx = _lib.Context(0)
     out = {}
@@ -71,7 +72,29 @@ def main():
     ms = timed(lambda: ops.knn_topk(ctx, Q, DB, 10), iters=2)
     fl = 2.0 * a.q * a.m * 512
     out["knn"] = {"Q": a.q, "M": a.m, "k": 10, "ms": ms, "algorithmic_tflops": fl / ms / 1e9, "tensor_tflops_issued": 3 * fl / ms / 1e9}
+    # complete linkage on the GPU at a size whose square fp32 matrix we also want to time end to end
+    from facerec_b200 import distance
+    n_l = min(a.n, a.link_n)
+    Xl = X[:n_l].contiguous()
+    t0 = time.time()
+    D = ops.pdist(ctx, Xl, layout=_lib.FRB_SQUARE_F32)
+    pairs = torch.empty((n_l - 1, 2), dtype=torch.int32, device="cuda")
+    dist_ = torch.empty((n_l - 1,), dtype=torch.float32, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ctx.check(ctx.lib.frb_linkage_complete(ctx.handle, D.data_ptr(), n_l, pairs.data_ptr(), dist_.data_ptr(), _lib.current_stream()), "linkage")
+    e1.record(); torch.cuda.synchronize()
+    Z = distance._label_merges(pairs.cpu().numpy(), dist_.cpu().numpy().astype(np.float64), n_l)
+    out["linkage"] = {"N": n_l, "kernel_ms": e0.elapsed_time(e1), "wall_s_incl_pdist_and_relabel": time.time() - t0,
+                      "max_height": float(Z[-1, 2])}
+    del D
     if a.cpu:
+        from scipy.cluster.hierarchy import linkage as sp_linkage
+        n_c = 8000
+        cpd = ops.pdist(ctx, X[:n_c].contiguous(), layout=_lib.FRB_CONDENSED_F64).cpu().numpy()
+        t0 = time.time(); sp_linkage(cpd, method="complete"); dt = time.time() - t0
+        out["linkage"]["cpu_scipy_linkage_s_at_n8000"] = dt
+        out["linkage"]["cpu_scipy_linkage_s_extrapolated"] = dt * (n_l / n_c) ** 2
         from scipy.spatial.distance import pdist
         from sklearn.neighbors import KNeighborsClassifier
         n_s = 4000
