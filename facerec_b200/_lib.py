@@ -18,6 +18,7 @@ FRB_IRV1 = 2
 FRB_CONDENSED_F32 = 0
 FRB_CONDENSED_F64 = 1
 FRB_SQUARE_F32 = 2
+FRB_SQUARE_SYM_F32 = 3
 
 FRB_LAYOUT_NHWC8 = 0
 FRB_LAYOUT_S2D16 = 1

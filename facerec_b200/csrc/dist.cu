@@ -28,7 +28,7 @@ constexpr int kDSub = kDEpiWarps / 4;
 constexpr int kDThreads = (kDEpiWarps + 2) * 32;
 constexpr int kTopK = 16;      // per-row candidates kept in registers (k <= 16)
 
-enum DistMode : int { DIST_SQUARE_F32 = 0, DIST_CONDENSED_F32 = 1, DIST_CONDENSED_F64 = 2, DIST_KNN = 3 };
+enum DistMode : int { DIST_SQUARE_F32 = 0, DIST_CONDENSED_F32 = 1, DIST_CONDENSED_F64 = 2, DIST_KNN = 3, DIST_SQUARE_SYM_F32 = 4 };
 
 struct DistArgs {
   int mode;
@@ -86,7 +86,9 @@ __device__ __forceinline__ ItemRange item_range(const DistArgs& p, int item) {
     r.n_begin = item - r.m_tile * p.n_tiles;
     r.n_end = r.n_begin + 1;
     // condensed layouts only hold j > i: drop tiles entirely on or below the diagonal
-    if (p.mode != DIST_SQUARE_F32 && (r.n_begin + 1) * kDN <= p.row0 + r.m_tile * kDM + 1) r.n_end = r.n_begin;
+    if (p.mode == DIST_SQUARE_SYM_F32) {
+      if ((r.n_begin + 1) * kDN <= p.row0 + r.m_tile * kDM) r.n_end = r.n_begin;   // keep tiles touching j >= i
+    } else if (p.mode != DIST_SQUARE_F32 && (r.n_begin + 1) * kDN <= p.row0 + r.m_tile * kDM + 1) r.n_end = r.n_begin;
   }
   return r;
 }
@@ -167,7 +169,7 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
 #pragma unroll
       for (int t = 0; t < kTopK; ++t) { td[t] = INFINITY; tid[t] = 0x7fffffff; }
       long long rowoff = 0;
-      if (p.mode == DIST_SQUARE_F32) rowoff = static_cast<long long>(li) * p.N;
+      if (p.mode == DIST_SQUARE_F32 || p.mode == DIST_SQUARE_SYM_F32) rowoff = static_cast<long long>(li) * p.N;
       else rowoff = static_cast<long long>(gi) * p.N - (static_cast<long long>(gi) * (gi + 1)) / 2 - gi - 1;
 
       for (int n_tile = ir.n_begin; n_tile < ir.n_end; ++n_tile, ++tile_iter) {
@@ -213,11 +215,22 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
               const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
               const int rli = ir.m_tile * kDM + quarter * 32 + r;
               const int rgi = p.row0 + rli;
-              const bool ok = rli < p.rows && j < p.N && (p.mode == DIST_SQUARE_F32 || j > rgi);
+              const bool ok = rli < p.rows && j < p.N &&
+                              (p.mode == DIST_SQUARE_F32 || j > rgi || (p.mode == DIST_SQUARE_SYM_F32 && j == rgi));
               if (ok) {
                 const float val = j == rgi ? 0.f : mytr[r * 33 + lane];   // exact zero diagonal (square layout)
                 if (p.mode == DIST_CONDENSED_F64) static_cast<double*>(p.out)[ro + j] = static_cast<double>(val);
                 else static_cast<float*>(p.out)[ro + j] = val;
+              }
+            }
+            if (p.mode == DIST_SQUARE_SYM_F32) {
+              // mirror: D[j][i] = D[i][j] from the SAME value, so the matrix is exactly symmetric and equal to
+              // the condensed (upper-triangle) distances; lanes walk i, so these stores are coalesced too
+              const int gi_l = p.row0 + ir.m_tile * kDM + quarter * 32 + lane;
+              for (int c = 0; c < 32; ++c) {
+                const int jj = n_base + n0 + c;
+                if (jj < p.N && gi_l < p.N && jj > gi_l)
+                  static_cast<float*>(p.out)[static_cast<long long>(jj) * p.N + gi_l] = mytr[lane * 33 + c];
               }
             }
             __syncwarp();
@@ -393,7 +406,9 @@ static int launch_dist(frb_ctx* ctx, const DistArgs& a, const CUtensorMap& tmA, 
 
 int run_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, cudaStream_t st) {
   if (N <= 0 || D <= 0 || row0 < 0 || rows < 0 || row0 + rows > N) return set_err(ctx, FRB_ERR_INVALID, "pdist: bad shape");
-  if (layout < 0 || layout > 2) return set_err(ctx, FRB_ERR_INVALID, "pdist: bad layout %d", layout);
+  if (layout < 0 || layout > 3) return set_err(ctx, FRB_ERR_INVALID, "pdist: bad layout %d", layout);
+  if (layout == FRB_SQUARE_SYM_F32 && (row0 != 0 || rows != N))
+    return set_err(ctx, FRB_ERR_INVALID, "pdist: the symmetric square layout covers all rows (row0 = 0, rows = N)");
   if (rows == 0) return FRB_OK;
   const int Dp = (D + kDK - 1) / kDK * kDK;
   void* d_split = nullptr;
@@ -406,7 +421,9 @@ int run_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, 
   if ((rc = encode_bf16_rows(ctx, &tm, d_split, N, Dp)) != FRB_OK) return rc;
   DistArgs a;
   memset(&a, 0, sizeof(a));
-  a.mode = layout == FRB_SQUARE_F32 ? DIST_SQUARE_F32 : (layout == FRB_CONDENSED_F32 ? DIST_CONDENSED_F32 : DIST_CONDENSED_F64);
+  a.mode = layout == FRB_SQUARE_F32 ? DIST_SQUARE_F32
+           : (layout == FRB_SQUARE_SYM_F32 ? DIST_SQUARE_SYM_F32
+              : (layout == FRB_CONDENSED_F32 ? DIST_CONDENSED_F32 : DIST_CONDENSED_F64));
   a.rows = rows; a.row0 = row0; a.N = N; a.Dp = Dp;
   a.m_tiles = (rows + kDM - 1) / kDM;
   a.n_tiles = (N + kDN - 1) / kDN;

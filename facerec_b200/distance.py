@@ -128,7 +128,9 @@ class B200KNeighborsClassifier:
     def predict_proba(self, V) -> np.ndarray:
         Q = torch.from_numpy(np.ascontiguousarray(V, dtype=np.float32)).to(self.device)
         idx, _ = ops.knn_topk(self.ctx, Q, self._db, self.n_neighbors)
-        return ops.knn_vote(self.ctx, idx, self._labels, len(self.classes_)).cpu().numpy().astype(np.float64)
+        p32 = ops.knn_vote(self.ctx, idx, self._labels, len(self.classes_)).cpu().numpy()
+        # the kernel returns count/k in fp32; sklearn's value is the float64 quotient of the same integer count
+        return np.rint(p32.astype(np.float64) * self.n_neighbors) / self.n_neighbors
 
     def predict(self, V) -> np.ndarray:
         return self.classes_[np.argmax(self.predict_proba(V), axis=1)]
@@ -170,7 +172,7 @@ def gpu_linkage_complete(vectors: np.ndarray, ctx: Optional[Context] = None) -> 
     ctx = _ctx(ctx)
     X = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(torch.device("cuda", ctx.device))
     n = X.shape[0]
-    D = ops.pdist(ctx, X, layout=_lib.FRB_SQUARE_F32)
+    D = ops.pdist(ctx, X, layout=_lib.FRB_SQUARE_SYM_F32)
     pairs = torch.empty((n - 1, 2), dtype=torch.int32, device=X.device)
     dist = torch.empty((n - 1,), dtype=torch.float32, device=X.device)
     ctx.check(ctx.lib.frb_linkage_complete(ctx.handle, D.data_ptr(), n, pairs.data_ptr(), dist.data_ptr(),

@@ -180,7 +180,7 @@ def pdist(ctx: Context, X: torch.Tensor, row0: int = 0, rows: Optional[int] = No
     N, D = X.shape
     rows = N - row0 if rows is None else rows
     if out is None:
-        if layout == _lib.FRB_SQUARE_F32:
+        if layout in (_lib.FRB_SQUARE_F32, _lib.FRB_SQUARE_SYM_F32):
             out = torch.empty((rows, N), dtype=torch.float32, device=X.device)
         else:
             dt = torch.float64 if layout == _lib.FRB_CONDENSED_F64 else torch.float32

@@ -45,7 +45,8 @@ enum frb_model {
 enum frb_pdist_layout {
   FRB_CONDENSED_F32 = 0,  /* scipy pdist order, float  */
   FRB_CONDENSED_F64 = 1,  /* scipy pdist order, double */
-  FRB_SQUARE_F32 = 2      /* rows x N row-major, float */
+  FRB_SQUARE_F32 = 2,     /* rows x N row-major, float */
+  FRB_SQUARE_SYM_F32 = 3  /* N x N, only j >= i computed and mirrored: exactly symmetric (input of frb_linkage_complete) */
 };
 
 enum frb_option {

@@ -77,7 +77,7 @@ def main():
     n_l = min(a.n, a.link_n)
     Xl = X[:n_l].contiguous()
     t0 = time.time()
-    D = ops.pdist(ctx, Xl, layout=_lib.FRB_SQUARE_F32)
+    D = ops.pdist(ctx, Xl, layout=_lib.FRB_SQUARE_SYM_F32)
     pairs = torch.empty((n_l - 1, 2), dtype=torch.int32, device="cuda")
     dist_ = torch.empty((n_l - 1,), dtype=torch.float32, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
