@@ -345,7 +345,11 @@ def run_b200(a):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": fwd_tflops / peak, "traffic": None,
+                         "frac": fwd_tflops / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum over the 71 launches of one forward (64 x 1080p,
+                         # R50), ncu metrics pass of tools/forward_once.py: profiles/r01_ncu_conv_tma_v5.md
+                         "traffic": 157.0e9 if (a.backbone, B, H, W) == ("r50", 64, 1080, 1920) else None,
+                         "traffic_unit": "bytes per forward (94.5 GB read + 62.5 GB write; algorithmic minimum 2.60 GB/frame x 64 = 166 GB)",
                          "kernel": f"conv_tma_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
