@@ -15,6 +15,13 @@
 // skip) is a producer-side TMA prefetch, double buffered across tiles, so its latency hides behind the
 // previous tile's epilogue.
 //
+// Halo mode (stride-1 k x k convs): instead of one A box per filter tap (k*k reads of the same pixels through
+// L2), the producer loads ONE (bh+kh-1) x (bw+kw-1) halo tile per 64-channel block and the MMA issuer points
+// the A descriptor of tap (r, s) at pixel (r, s) of that tile: 8-row groups are 8 consecutive pixels of a halo
+// row (bw = 8), the stride between groups is the halo row pitch.  The 128-byte swizzle is a function of the
+// shared-memory ADDRESS (tools/umma_shift_probe.cu: any 128-byte row offset and any group stride read back
+// exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.
+//
 // Warp roles (576 threads): 0-15 epilogue, 16 MMA issuer + TMEM allocator, 17 TMA producer.
 // The epilogue is instruction-issue bound when one warp per scheduler walks a whole 64-column row
 // (ncu: ~2 400 cycles per slab, issue slots mostly idle), so each TMEM lane quarter (warp % 4) is
@@ -48,6 +55,11 @@ struct ConvTmaArgs {
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
   int stages;
   int b_resident;        // whole weight matrix stays in shared memory (n_tiles * num_kb blocks of BN x 64)
+  int halo;              // 1: stride-1 k x k conv fed from ONE halo tile per 64-channel block (see below)
+  int kh;                // filter rows (halo mode walks taps itself)
+  int halo_w, halo_h;    // halo tile = (bh + kh - 1) x (bw + kw - 1) pixels of 128 B
+  int halo_bytes;        // bytes of one halo buffer (1024-aligned)
+  int a_stages;          // halo buffers in the ring
   int act_kind;          // 0: per-channel slope (general), 1: ReLU everywhere, 2: linear everywhere
   const float* bias;     // [n_tiles*BN]
   const float* slope;    // [n_tiles*BN]
@@ -55,7 +67,19 @@ struct ConvTmaArgs {
   const void* res;       // POST_ACT_UPSAMPLE source
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
+  long long* trace;      // debug: (event, tile_iter, clock64) records of CTA 0, or null
 };
+
+// Timeline probe (FRB_OPT_TRACE): CTA 0 appends (event id, tile_iter, clock) triples; trace[0] is the record count.
+__device__ __forceinline__ void trace_event(long long* trace, int event, int tile_iter) {
+  if (trace == nullptr || blockIdx.x != 0) return;
+  const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ULL);
+  if (i < 4000) {
+    trace[1 + 3 * i] = event;
+    trace[2 + 3 * i] = tile_iter;
+    trace[3 + 3 * i] = clock64();
+  }
+}
 
 template <bool kBF16>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -70,7 +94,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int b_stage_bytes = p.BN * 128;
   const bool has_res = p.res_mode == RES_PRE_ACT;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + p.stages * kAStageBytes;                                  // ring (or resident matrix)
+  uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * kAStageBytes);   // ring (or resident matrix)
   uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages) * b_stage_bytes;
   uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                                    // kResSets x 2 slabs (PRE_ACT only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (has_res ? kResSets * 2 * kSlabBytes : 0));
@@ -81,8 +105,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;    // [kResSets]
   uint64_t* rempty_bar = bars + 2 * kMaxStages + 6;   // [kResSets]
   uint64_t* bres_bar = bars + 2 * kMaxStages + 8;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 9);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 10);   // [256]
+  uint64_t* afull_bar = bars + 2 * kMaxStages + 9;    // [kMaxStages] halo ring
+  uint64_t* aempty_bar = bars + 3 * kMaxStages + 9;   // [kMaxStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 9);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 10);   // [256]
   float* s_slope = s_bias + 256;                                          // [256]
 
   const int warp = threadIdx.x >> 5;
@@ -110,6 +136,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         mbar_init(&rempty_bar[b], 1);
       }
       mbar_init(bres_bar, 1);
+      for (int s = 0; s < kMaxStages; ++s) {
+        mbar_init(&afull_bar[s], 1);
+        mbar_init(&aempty_bar[s], 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -179,8 +209,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         s_slope[t] = __ldg(p.slope + n_base + t);
       }
 
+      if (threadIdx.x == 0) trace_event(p.trace, 10, tile_iter);        // epilogue ready for this tile
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
       tc_fence_after();
+      if (threadIdx.x == 0) trace_event(p.trace, 11, tile_iter);        // accumulator available
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
       if (has_res) mbar_wait(&rfull_bar[rset], rphase, p.watchdog, 500 + rset);
 
@@ -203,7 +235,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         }
         // staging slab `ob` is free once the store issued kOutBufs slabs ago has finished reading it
         const uint32_t ob = slab_ctr % kOutBufs;
-        if (threadIdx.x == 0) tma_store_wait_read<kOutBufs - 1>();
+        if (threadIdx.x == 0) {
+          trace_event(p.trace, 13, tile_iter);                              // TMEM read out, waiting for a staging slab
+          tma_store_wait_read<kOutBufs - 1>();
+          trace_event(p.trace, 14, tile_iter);
+        }
         named_bar_sync(1, kEpiThreads);
 
         if (mine) {
@@ -260,6 +296,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
           else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
           tma_store_commit();
+          if (s == nslab - 1) trace_event(p.trace, 12, tile_iter);        // last store of the tile issued
           // every epilogue thread is past its reads of this tile's residual slabs: give the set back
           if (has_res && s == nslab - 1) mbar_arrive(&rempty_bar[rset]);
         }
@@ -269,40 +306,103 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     if (threadIdx.x == 0) tma_store_wait<0>();     // stores must land before the CTA (and its smem) goes away
   } else if (warp == kMmaWarp) {
     // ============================================================== MMA issuer
+    // Everything here is warp-uniform and incremental: descriptor LOW words (start address >> 4) advance by
+    // constant steps, high words are constants, barriers are 32-bit shared addresses, and only the tcgen05
+    // instructions sit under the elected lane.  (Measured before this rewrite: ~600 cycles of dependent
+    // single-warp instructions per k-block in both this loop and the producer's, i.e. the pipeline could not
+    // deliver a k-block faster than that whatever the tile shape — 4 MMAs are 225-512 cycles of tensor time.)
     const uint32_t idesc = make_idesc_f16(kBM, p.BN, kBF16 ? 1 : 0);
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+    const uint32_t a_step = kAStageBytes >> 4, b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
+    const uint32_t halo_step = static_cast<uint32_t>(p.halo_bytes) >> 4;
+    const uint32_t hi1024 = desc_hi(1024), hi_halo = desc_hi(static_cast<uint32_t>(p.halo_w) * 128u);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), afull0 = smem_u32(afull_bar),
+                   aempty0 = smem_u32(aempty_bar), tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+    int stage = 0, astage = 0;
+    uint32_t phase = 0, aphase = 0;
+    uint32_t a_ring = a_lo0, b_ring = b_lo0;          // descriptor low words of the current ring slots
     int tile_iter = 0;
     if (p.b_resident) mbar_wait(bres_bar, 0, p.watchdog, 250);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       const int buf = tile_iter & 1;
       const uint32_t tphase = (tile_iter >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
-      mbar_wait(&tempty_bar[buf], tphase ^ 1, p.watchdog, 200 + buf);
+      mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf);
       tc_fence_after();
+      if (lane == 0) trace_event(p.trace, 21, tile_iter);                 // TMEM buffer free
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase, p.watchdog, 210 + stage);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint8_t* bsrc = p.b_resident ? smem_b + (n_tile * p.num_kb + kb) * b_stage_bytes : smem_b + stage * b_stage_bytes;
-          const uint64_t a_desc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kAStageBytes));
-          const uint64_t b_desc = make_sw128_kmajor_desc(smem_u32(bsrc));
-#pragma unroll
-          for (int k4 = 0; k4 < kBK / 16; ++k4)
-            tc_mma_f16(d_tmem, a_desc + static_cast<uint64_t>(k4 * 2), b_desc + static_cast<uint64_t>(k4 * 2), idesc,
-                       (kb | k4) != 0 ? 1u : 0u);
-          tc_commit(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);
+      const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
+      if (p.halo) {
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          tc_fence_after();
+          uint32_t a_tap = a_lo0 + static_cast<uint32_t>(astage) * halo_step;          // pixel (0,0) of the halo tile
+          uint32_t b_tap = b_res + static_cast<uint32_t>(cb) * b_step;                   // resident: block (tap 0, cb)
+          uint32_t acc = cb != 0 ? 1u : 0u;
+          for (int tr = 0; tr < p.kh; ++tr) {
+            for (int ts = 0; ts < p.kw; ++ts) {
+              if (!p.b_resident) {
+                mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+                tc_fence_after();
+                b_tap = b_ring;
+              }
+              const bool last_tap = tr == p.kh - 1 && ts == p.kw - 1;
+              if (elect_one()) {
+                tc_mma_f16(d_tmem, pack_desc(a_tap, hi_halo), pack_desc(b_tap, hi1024), idesc, acc);
+                tc_mma_f16(d_tmem, pack_desc(a_tap + 2, hi_halo), pack_desc(b_tap + 2, hi1024), idesc, 1u);
+                tc_mma_f16(d_tmem, pack_desc(a_tap + 4, hi_halo), pack_desc(b_tap + 4, hi1024), idesc, 1u);
+                tc_mma_f16(d_tmem, pack_desc(a_tap + 6, hi_halo), pack_desc(b_tap + 6, hi1024), idesc, 1u);
+                if (!p.b_resident) tc_commit_a(empty0 + stage * 8);
+                if (last_tap) {
+                  tc_commit_a(aempty0 + astage * 8);
+                  if (cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+                }
+              }
+              __syncwarp();
+              acc = 1u;
+              a_tap += 8;                                                // next pixel of the halo row (128 B)
+              if (p.b_resident) {
+                b_tap += static_cast<uint32_t>(p.cin_blocks) * b_step;
+              } else {
+                b_ring += b_step;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; b_ring = b_lo0; }
+              }
+            }
+            a_tap += static_cast<uint32_t>(p.halo_w - p.kw) * 8;         // first pixel of the next halo row
+          }
+          if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      } else {
+        uint32_t b_cur = b_res;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          tc_fence_after();
+          if (!p.b_resident) b_cur = b_ring;
+          if (elect_one()) {
+            tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, kb != 0 ? 1u : 0u);
+            tc_mma_f16(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
+            tc_mma_f16(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
+            tc_mma_f16(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
+            tc_commit_a(empty0 + stage * 8);
+            if (kb == p.num_kb - 1) tc_commit_a(tfull0 + buf * 8);
+          }
+          __syncwarp();
+          b_cur += b_step;
+          a_ring += a_step;
+          b_ring += b_step;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
+        }
       }
+      if (lane == 0) trace_event(p.trace, 23, tile_iter);                 // all MMAs of the tile issued
     }
   } else {
     // ============================================================ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t a_s0 = smem_u32(smem_a), b_s0 = smem_u32(smem_b), r_s0 = smem_u32(smem_r);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), afull0 = smem_u32(afull_bar),
+                   aempty0 = smem_u32(aempty_bar), rfull0 = smem_u32(rfull_bar), rempty0 = smem_u32(rempty_bar);
+    int stage = 0, astage = 0;
+    uint32_t phase = 0, aphase = 0;
+    uint32_t a_dst = a_s0, b_dst = b_s0;
     int tile_iter = 0;
     if (p.b_resident && lane == 0) {
       mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.n_tiles * p.num_kb * b_stage_bytes));
@@ -311,39 +411,73 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
     }
     const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
+    const uint32_t halo_tx = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
+      const int n_coord = n_tile * p.BN;
       if (has_res) {
         // residual tile of THIS tile into set tile_iter % kResSets, as soon as the epilogue released it
         const int rset = tile_iter % kResSets;
-        mbar_wait(&rempty_bar[rset], ((tile_iter / kResSets) & 1) ^ 1, p.watchdog, 600 + rset);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&rfull_bar[rset], static_cast<uint32_t>(nslab * p.a_bytes));
+        mbar_wait_a(rempty0 + rset * 8, ((tile_iter / kResSets) & 1) ^ 1, p.watchdog, 600 + rset);
+        if (elect_one()) {
+          mbar_expect_tx_a(rfull0 + rset * 8, static_cast<uint32_t>(nslab * p.a_bytes));
           for (int rs = 0; rs < nslab; ++rs) {
-            uint8_t* dst = smem_r + (rset * 2 + rs) * kSlabBytes;
-            if (p.patch) tma_load_4d(dst, &tmR, &rfull_bar[rset], n_tile * p.BN + rs * kSlab, c1, c2, c3);
-            else tma_load_2d(dst, &tmR, &rfull_bar[rset], n_tile * p.BN + rs * kSlab, c1);
+            const uint32_t dst = r_s0 + static_cast<uint32_t>((rset * 2 + rs) * kSlabBytes);
+            if (p.patch) tma_load_4d_a(dst, &tmR, rfull0 + rset * 8, n_coord + rs * kSlab, c1, c2, c3);
+            else tma_load_2d_a(dst, &tmR, rfull0 + rset * 8, n_coord + rs * kSlab, c1);
           }
         }
         __syncwarp();
       }
-      const int aw = c1 * p.sw - p.pw, ah = c2 * p.sh - p.ph;
-      int tap_r = 0, tap_s = 0, cb = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, p.watchdog, 300 + stage);
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          if (!p.b_resident) tma_load_2d(smem_b + stage * b_stage_bytes, &tmB, &full_bar[stage], kb * kBK, n_tile * p.BN);
-          if (p.patch) tma_load_4d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBK, aw + tap_s, ah + tap_r, c3);
-          else tma_load_2d(smem_a + stage * kAStageBytes, &tmA, &full_bar[stage], kb * kBK, c1);
+      if (p.halo) {
+        const int taps = p.kh * p.kw;
+        for (int hb = 0; hb < p.cin_blocks; ++hb) {
+          mbar_wait_a(aempty0 + astage * 8, aphase ^ 1, p.watchdog, 320 + astage);
+          if (elect_one()) {
+            mbar_expect_tx_a(afull0 + astage * 8, halo_tx);
+            tma_load_4d_a(a_s0 + static_cast<uint32_t>(astage * p.halo_bytes), &tmA, afull0 + astage * 8, hb * kBK, c1 - p.pw,
+                          c2 - p.ph, c3);
+          }
+          __syncwarp();
+          if (lane == 0) trace_event(p.trace, 30, tile_iter);             // halo load issued
+          if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+          if (!p.b_resident) {
+            int kcoord = hb * kBK;                                        // K coordinate of (tap 0, hb)
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
+              if (elect_one()) {
+                mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(b_stage_bytes));
+                tma_load_2d_a(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
+              }
+              __syncwarp();
+              kcoord += p.cin_blocks * kBK;
+              b_dst += static_cast<uint32_t>(b_stage_bytes);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; b_dst = b_s0; }
+            }
+          }
         }
-        __syncwarp();
-        if (++cb == p.cin_blocks) {
-          cb = 0;
-          if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
+      } else {
+        const int aw = c1 * p.sw - p.pw, ah = c2 * p.sh - p.ph;
+        int tap_r = 0, tap_s = 0, cb = 0, kcoord = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, tx_bytes);
+            if (!p.b_resident) tma_load_2d_a(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
+            if (p.patch) tma_load_4d_a(a_dst, &tmA, full0 + stage * 8, cb * kBK, aw + tap_s, ah + tap_r, c3);
+            else tma_load_2d_a(a_dst, &tmA, full0 + stage * 8, kcoord, c1);
+          }
+          __syncwarp();
+          kcoord += kBK;
+          if (++cb == p.cin_blocks) {
+            cb = 0;
+            if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
+          }
+          a_dst += kAStageBytes;
+          b_dst += static_cast<uint32_t>(b_stage_bytes);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; a_dst = a_s0; b_dst = b_s0; }
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   }

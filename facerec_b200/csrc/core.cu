@@ -219,6 +219,8 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.res_mode = io.res_mode; a.res = io.res; a.res_ld = io.res_ld; a.rH = io.rH; a.rW = io.rW;
   a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M);
   a.watchdog = ctx->wd_dev;
+  a.trace = ctx->trace_dev;
+  if (a.trace) cudaMemsetAsync(a.trace, 0, 8, stream);
 
   CUtensorMap tmA, tmO, tmR;
   memset(&tmR, 0, sizeof(tmR));
@@ -235,6 +237,20 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       return rc;
   } else {
     pick_patch(io.B, Ho, Wo, L.sw, L.sh, a.bw, a.bh, a.bb);
+    // halo mode: stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide x 16 tall)
+    if (!L.special && ctx->halo_mode && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
+      const double eff_patch = static_cast<double>(io.B) * Ho * Wo /
+                               (128.0 * ((Wo + a.bw - 1) / a.bw) * ((Ho + a.bh - 1) / a.bh) * ((io.B + a.bb - 1) / a.bb));
+      const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
+      if (eff_halo >= 0.85 * eff_patch) {
+        a.halo = 1;
+        a.bw = 8; a.bh = 16; a.bb = 1;
+        a.kh = L.kh;
+        a.halo_w = 8 + L.kw - 1;
+        a.halo_h = 16 + L.kh - 1;
+        a.halo_bytes = (a.halo_w * a.halo_h * 128 + 1023) & ~1023;
+      }
+    }
     a.tiles_w = (Wo + a.bw - 1) / a.bw;
     a.tiles_h = (Ho + a.bh - 1) / a.bh;
     m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * ((io.B + a.bb - 1) / a.bb);
@@ -246,6 +262,8 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       const uint32_t box[4] = {64, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bb};
       const uint32_t est[4] = {1, 1, 1, 1};
       if ((rc = encode_nd(ctx, &tmA, io.in, 4, dims, str, box, est)) != FRB_OK) return rc;
+    } else if (a.halo) {
+      if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.halo_w, a.halo_h, 1, 1, 1)) != FRB_OK) return rc;
     } else if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
     if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
     if (io.res_mode == RES_PRE_ACT &&
@@ -258,12 +276,21 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   // small weight matrices (the bandwidth-bound early layers) stay resident in shared memory for the whole kernel
   const int w_bytes = L.n_tiles * a.num_kb * L.BN * 128;
   a.b_resident = w_bytes <= kResidentWeightBytes ? 1 : 0;
-  const int stage_bytes = kAStageBytes + (a.b_resident ? 0 : L.BN * 128);
-  const int fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? kResSets * 2 * kSlabBytes : 0) +
-                    (a.b_resident ? w_bytes : 0) + (2 * kMaxStages + 10) * 8 + 2048 + 1024;
+  const int base_fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? kResSets * 2 * kSlabBytes : 0) +
+                         (a.b_resident ? w_bytes : 0) + (4 * kMaxStages + 10) * 8 + 2048 + 1024;
+  const int total_budget = 226 * 1024 - base_fixed;
+  const int stage_bytes = (a.halo ? 0 : kAStageBytes) + (a.b_resident ? 0 : L.BN * 128);
+  if (a.halo) {
+    // TMA latency is hidden by bytes in flight: with resident weights the whole budget goes to halo buffers,
+    // otherwise the halo ring gets about a third and the weight ring the rest
+    const int for_a = a.b_resident ? total_budget : std::max(2 * a.halo_bytes, total_budget / 3);
+    a.a_stages = std::max(2, std::min(kMaxStages, for_a / a.halo_bytes));
+  }
+  const int fixed = base_fixed + a.a_stages * a.halo_bytes;
   const int budget = 226 * 1024 - fixed;
-  a.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+  a.stages = stage_bytes > 0 ? std::max(2, std::min(kMaxStages, budget / stage_bytes)) : 2;
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
+  if (smem > 227 * 1024) return set_err(ctx, FRB_ERR_INVALID, "conv: shared-memory plan does not fit (%zu bytes)", smem);
   const int grid = std::min(a.total_tiles, ctx->num_sms);
   if (ctx->use_bf16) {
     FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -399,11 +426,29 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       ctx->bn_cap = value;
       return FRB_OK;
     case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_HALO: ctx->halo_mode = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_TRACE:
+      if (value && ctx->trace_dev == nullptr) {
+        if (cudaMalloc(&ctx->trace_dev, (1 + 3 * 4000) * sizeof(long long)) != cudaSuccess) return set_err(ctx, FRB_ERR_CUDA, "trace alloc failed");
+      } else if (!value && ctx->trace_dev != nullptr) {
+        cudaFree(ctx->trace_dev);
+        ctx->trace_dev = nullptr;
+      }
+      return FRB_OK;
   }
   return set_err(ctx, FRB_ERR_INVALID, "unknown option %d", option);
 }
 
 long long frb_launch_count(frb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records) {
+  if (ctx == nullptr || h_out == nullptr || ctx->trace_dev == nullptr) return FRB_ERR_INVALID;
+  if (cudaDeviceSynchronize() != cudaSuccess) return FRB_ERR_CUDA;
+  const int n = std::min(max_records, 4000);
+  if (cudaMemcpy(h_out, ctx->trace_dev, (1 + 3 * static_cast<size_t>(n)) * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return FRB_ERR_CUDA;
+  return FRB_OK;
+}
 
 int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, const float* h_w, const float* h_bias,
                int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int act, float slope, const void* d_res16,

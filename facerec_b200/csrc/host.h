@@ -28,6 +28,9 @@ struct frb_ctx {
   int use_bf16 = 0;            // 0: fp16 activations/weights (default), 1: bf16
   int bn_cap = 256;            // largest conv tile N the planner may pick
   int force_gather = 0;        // debugging: never use the TMA A path
+  long long* trace_dev = nullptr;  // FRB_OPT_TRACE: device buffer for conv_tma timeline records
+  int halo_mode = 0;           // 1: stride-1 k x k convs read A from one halo tile per channel block (measured: not faster
+                               //    than one box per tap, the small-N layers are bound by MMA operand reads, see profiles/)
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
   int* wd_dev = nullptr;

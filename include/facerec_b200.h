@@ -52,7 +52,9 @@ enum frb_pdist_layout {
 enum frb_option {
   FRB_OPT_BF16 = 0,        /* 1: bf16 activations/weights instead of fp16 (set before frb_load_model) */
   FRB_OPT_BN_CAP = 1,      /* largest conv tile N (multiple of 16, <= 256)                           */
-  FRB_OPT_FORCE_GATHER = 2 /* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
+  FRB_OPT_FORCE_GATHER = 2,/* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
+  FRB_OPT_HALO = 3,        /* 0: one TMA box per filter tap instead of one halo tile per channel block    */
+  FRB_OPT_TRACE = 4        /* 1: CTA 0 of every conv_tma launch records a (event, tile, clock) timeline    */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -62,6 +64,8 @@ int frb_destroy(frb_ctx* ctx);
 const char* frb_last_error(frb_ctx* ctx); /* valid until the next call on ctx */
 int frb_set_option(frb_ctx* ctx, int option, int value);
 long long frb_launch_count(frb_ctx* ctx); /* kernels launched through ctx so far */
+/* FRB_OPT_TRACE: copies the timeline of the LAST conv_tma launch: h_out[0] = record count, then (event, tile, clock) triples */
+int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records);
 
 /* Weights.  `h_blob` is the self-describing fp32 blob written by facerec_b200/weights.py
  * (magic "FRBW", entry table of name/shape/offset, then data): one "<layer>.w" [Cout,kh,kw,Cin]

@@ -45,6 +45,11 @@ CASES = [
     (3, 17, 17, 192, 256, 3, 3, (2, 2), (0, 0), 1, 0, False),    # Mixed_6a stride-2 reduction 17 -> 8
     (2, 40, 56, 256, 80, 1, 1, (1, 1), (0, 0), 2, 0, False),     # Cout = 80: partial last store slab
     (1, 135, 240, 64, 256, 1, 1, (1, 1), (0, 0), 1, 1, False),   # ResNet conv3 + skip, 254 M-tiles x 2 N-tiles
+    (2, 48, 64, 128, 128, 3, 3, (1, 1), (1, 1), 1, 1, False),    # halo mode: 2 channel blocks, streamed weights, residual
+    (1, 47, 61, 64, 64, 3, 3, (1, 1), (1, 1), 2, 0, False),      # halo mode, ragged in both dims, resident weights
+    (1, 32, 64, 128, 128, 1, 7, (1, 1), (0, 3), 1, 0, False),    # halo mode with a 1x7 filter (14 x 16 halo)
+    (1, 32, 48, 256, 256, 3, 3, (1, 1), (1, 1), 1, 0, False),    # halo mode: 4 channel blocks x 9 taps, BN = 256
+    (3, 270, 480, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),    # ResNet layer1 conv2 at full 1080p/4 size
 ]
 
 
@@ -71,6 +76,29 @@ def test_conv2d_matches_torch(ctx, case):
     err = (got - ref).abs()
     tol = 2e-3 * ref.abs() + 2e-3
     assert bool((err <= tol).all()), f"max err {err.max().item():.4g} at ref {ref.flatten()[err.argmax()].item():.4g}"
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[5] * c[6] > 1 and c[7] == (1, 1) and c[3] % 64 == 0],
+                         ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}")
+def test_conv2d_halo_mode_matches_torch(case):
+    """FRB_OPT_HALO: stride-1 k x k convs fed from one halo tile per channel block (shifted UMMA descriptors)."""
+    from facerec_b200 import ops, _lib
+    c = _lib.Context(0)
+    try:
+        c.set_option(_lib.FRB_OPT_HALO, 1)
+        B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32 = case
+        g = torch.Generator().manual_seed(99 + Cin + Cout)
+        x16 = torch.randn(B, H, W, Cin, generator=g).half().cuda()
+        w = (torch.randn(Cout, kh, kw, Cin, generator=g) / np.sqrt(kh * kw * Cin)).numpy().astype(np.float32)
+        b = (torch.randn(Cout, generator=g) * 0.1).numpy().astype(np.float32)
+        res16 = torch.randn(B, H, W, Cout, generator=g).half().cuda() if res_mode == 1 else None
+        out, _ = ops.conv2d(c, x16, w, b, stride, pad, act, 0.1, res16, res_mode, out_fp32)
+        torch.cuda.synchronize()
+        ref = _ref(x16, w, b, stride, pad, act, 0.1, res16, res_mode)
+        err = (out.float().cpu() - ref).abs()
+        assert bool((err <= 2e-3 * ref.abs() + 2e-3).all()), err.max().item()
+    finally:
+        c.close()
 
 
 def test_conv2d_bf16_option():
