@@ -28,6 +28,8 @@ FRB_OPT_BN_CAP = 1
 FRB_OPT_FORCE_GATHER = 2
 FRB_OPT_HALO = 3
 FRB_OPT_TRACE = 4
+FRB_OPT_KBPS2 = 5
+FRB_OPT_LAYER_TIMES = 6
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -40,6 +42,7 @@ SIGNATURES = {
     "frb_set_option": (_i, [_vp, _i, _i]),
     "frb_launch_count": (C.c_longlong, [_vp]),
     "frb_debug_trace": (_i, [_vp, _vp, _i]),
+    "frb_debug_layer_times": (_i, [_vp, _vp, _i]),
     "frb_load_model": (_i, [_vp, _i, _vp, _sz]),
     "frb_input_layout": (_i, [_i]),
     "frb_input_elems": (_sz, [_i, _i, _i, _i]),

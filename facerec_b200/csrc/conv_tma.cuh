@@ -54,6 +54,7 @@ struct ConvTmaArgs {
   int bw, bh, bb;        // patch = bb images x bh rows x bw cols (<= 128 pixels)
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
   int stages;
+  int kbps;              // 64-wide k-blocks per pipeline stage (2 halves the barrier round trips per unit of K)
   int b_resident;        // whole weight matrix stays in shared memory (n_tiles * num_kb blocks of BN x 64)
   int halo;              // 1: stride-1 k x k conv fed from ONE halo tile per 64-channel block (see below)
   int kh;                // filter rows (halo mode walks taps itself)
@@ -68,6 +69,16 @@ struct ConvTmaArgs {
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
   long long* trace;      // debug: (event, tile_iter, clock64) records of CTA 0, or null
+  long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
+};
+
+// Stall accounting (FRB_OPT_TRACE = 2): clock64 deltas around the blocking waits of one thread per role, summed in
+// registers and written once at the end (cheap enough not to move the timing, unlike the timeline below).
+struct StallClock {
+  bool on;
+  long long t0;
+  __device__ __forceinline__ void start() { if (on) t0 = clock64(); }
+  __device__ __forceinline__ void stop(long long& acc) { if (on) acc += clock64() - t0; }
 };
 
 // Timeline probe (FRB_OPT_TRACE): CTA 0 appends (event id, tile_iter, clock) triples; trace[0] is the record count.
@@ -94,8 +105,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int b_stage_bytes = p.BN * 128;
   const bool has_res = p.res_mode == RES_PRE_ACT;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * kAStageBytes);   // ring (or resident matrix)
-  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages) * b_stage_bytes;
+  uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * p.kbps * kAStageBytes);   // ring (or resident matrix)
+  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages * (p.halo ? 1 : p.kbps)) * b_stage_bytes;
   uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                                    // kResSets x 2 slabs (PRE_ACT only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (has_res ? kResSets * 2 * kSlabBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
@@ -179,6 +190,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     const int col0 = csub * kColsPerWarp;
     int tile_iter = 0;
     uint32_t slab_ctr = 0;
+    StallClock sc{p.stall != nullptr && threadIdx.x == 0, 0};
+    long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
+    const long long st_begin = sc.on ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
@@ -210,11 +224,15 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       }
 
       if (threadIdx.x == 0) trace_event(p.trace, 10, tile_iter);        // epilogue ready for this tile
+      sc.start();
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
+      sc.stop(st_tfull);
       tc_fence_after();
       if (threadIdx.x == 0) trace_event(p.trace, 11, tile_iter);        // accumulator available
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
+      sc.start();
       if (has_res) mbar_wait(&rfull_bar[rset], rphase, p.watchdog, 500 + rset);
+      sc.stop(st_res);
 
       for (int s = 0; s < nslab; ++s) {
         const int ncols = min(kSlab, p.BN - s * kSlab);
@@ -237,10 +255,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         const uint32_t ob = slab_ctr % kOutBufs;
         if (threadIdx.x == 0) {
           trace_event(p.trace, 13, tile_iter);                              // TMEM read out, waiting for a staging slab
+          sc.start();
           tma_store_wait_read<kOutBufs - 1>();
+          sc.stop(st_slab);
           trace_event(p.trace, 14, tile_iter);
         }
+        sc.start();
         named_bar_sync(1, kEpiThreads);
+        sc.stop(st_bar);
 
         if (mine) {
           const uint8_t* rrow = smem_r + (rset * 2 + s) * kSlabBytes + row_off;
@@ -291,7 +313,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           }
         }
         fence_proxy_async_smem();
+        sc.start();
         named_bar_sync(1, kEpiThreads);
+        sc.stop(st_bar);
         if (threadIdx.x == 0) {
           if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
           else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
@@ -302,6 +326,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         }
         ++slab_ctr;
       }
+    }
+    if (sc.on) {
+      long long* o = p.stall + 1 + blockIdx.x * 16;
+      o[0] = clock64() - st_begin; o[1] = st_tfull; o[2] = st_res; o[3] = st_slab; o[4] = st_bar; o[5] = tile_iter;
     }
     if (threadIdx.x == 0) tma_store_wait<0>();     // stores must land before the CTA (and its smem) goes away
   } else if (warp == kMmaWarp) {
@@ -322,19 +350,26 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     uint32_t phase = 0, aphase = 0;
     uint32_t a_ring = a_lo0, b_ring = b_lo0;          // descriptor low words of the current ring slots
     int tile_iter = 0;
+    StallClock sc{p.stall != nullptr, 0};
+    long long st_tempty = 0, st_full = 0;
+    const long long st_begin = sc.on ? clock64() : 0;
     if (p.b_resident) mbar_wait(bres_bar, 0, p.watchdog, 250);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
       const int buf = tile_iter & 1;
       const uint32_t tphase = (tile_iter >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
+      sc.start();
       mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf);
+      sc.stop(st_tempty);
       tc_fence_after();
       if (lane == 0) trace_event(p.trace, 21, tile_iter);                 // TMEM buffer free
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
       const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
       if (p.halo) {
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          sc.start();
           mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          sc.stop(st_full);
           tc_fence_after();
           uint32_t a_tap = a_lo0 + static_cast<uint32_t>(astage) * halo_step;          // pixel (0,0) of the halo tile
           uint32_t b_tap = b_res + static_cast<uint32_t>(cb) * b_step;                   // resident: block (tap 0, cb)
@@ -342,7 +377,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           for (int tr = 0; tr < p.kh; ++tr) {
             for (int ts = 0; ts < p.kw; ++ts) {
               if (!p.b_resident) {
+                sc.start();
                 mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+                sc.stop(st_full);
                 tc_fence_after();
                 b_tap = b_ring;
               }
@@ -374,26 +411,40 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         }
       } else {
         uint32_t b_cur = b_res;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kbps) {
+          const bool two = p.kbps == 2 && kb0 + 1 < p.num_kb;            // this stage carries two k-blocks
+          sc.start();
           mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          sc.stop(st_full);
           tc_fence_after();
           if (!p.b_resident) b_cur = b_ring;
           if (elect_one()) {
-            tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, kb != 0 ? 1u : 0u);
+            tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, kb0 != 0 ? 1u : 0u);
             tc_mma_f16(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
             tc_mma_f16(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
             tc_mma_f16(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
+            if (two) {
+              const uint32_t a2 = a_ring + a_step, b2 = b_cur + b_step;
+              tc_mma_f16(d_tmem, pack_desc(a2, hi1024), pack_desc(b2, hi1024), idesc, 1u);
+              tc_mma_f16(d_tmem, pack_desc(a2 + 2, hi1024), pack_desc(b2 + 2, hi1024), idesc, 1u);
+              tc_mma_f16(d_tmem, pack_desc(a2 + 4, hi1024), pack_desc(b2 + 4, hi1024), idesc, 1u);
+              tc_mma_f16(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
+            }
             tc_commit_a(empty0 + stage * 8);
-            if (kb == p.num_kb - 1) tc_commit_a(tfull0 + buf * 8);
+            if (kb0 + p.kbps >= p.num_kb) tc_commit_a(tfull0 + buf * 8);
           }
           __syncwarp();
-          b_cur += b_step;
-          a_ring += a_step;
-          b_ring += b_step;
+          b_cur += static_cast<uint32_t>(p.kbps) * b_step;
+          a_ring += static_cast<uint32_t>(p.kbps) * a_step;
+          b_ring += static_cast<uint32_t>(p.kbps) * b_step;
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
         }
       }
       if (lane == 0) trace_event(p.trace, 23, tile_iter);                 // all MMAs of the tile issued
+    }
+    if (sc.on && lane == 0) {
+      long long* o = p.stall + 1 + blockIdx.x * 16;
+      o[6] = clock64() - st_begin; o[7] = st_tempty; o[8] = st_full;
     }
   } else {
     // ============================================================ TMA producer
@@ -404,6 +455,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     uint32_t phase = 0, aphase = 0;
     uint32_t a_dst = a_s0, b_dst = b_s0;
     int tile_iter = 0;
+    StallClock sc{p.stall != nullptr, 0};
+    long long st_empty = 0, st_rempty = 0;
+    const long long st_begin = sc.on ? clock64() : 0;
     if (p.b_resident && lane == 0) {
       mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.n_tiles * p.num_kb * b_stage_bytes));
       for (int nt = 0; nt < p.n_tiles; ++nt)
@@ -419,7 +473,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       if (has_res) {
         // residual tile of THIS tile into set tile_iter % kResSets, as soon as the epilogue released it
         const int rset = tile_iter % kResSets;
+        sc.start();
         mbar_wait_a(rempty0 + rset * 8, ((tile_iter / kResSets) & 1) ^ 1, p.watchdog, 600 + rset);
+        sc.stop(st_rempty);
         if (elect_one()) {
           mbar_expect_tx_a(rfull0 + rset * 8, static_cast<uint32_t>(nslab * p.a_bytes));
           for (int rs = 0; rs < nslab; ++rs) {
@@ -433,7 +489,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       if (p.halo) {
         const int taps = p.kh * p.kw;
         for (int hb = 0; hb < p.cin_blocks; ++hb) {
+          sc.start();
           mbar_wait_a(aempty0 + astage * 8, aphase ^ 1, p.watchdog, 320 + astage);
+          sc.stop(st_empty);
           if (elect_one()) {
             mbar_expect_tx_a(afull0 + astage * 8, halo_tx);
             tma_load_4d_a(a_s0 + static_cast<uint32_t>(astage * p.halo_bytes), &tmA, afull0 + astage * 8, hb * kBK, c1 - p.pw,
@@ -445,7 +503,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (!p.b_resident) {
             int kcoord = hb * kBK;                                        // K coordinate of (tap 0, hb)
             for (int tap = 0; tap < taps; ++tap) {
+              sc.start();
               mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
+              sc.stop(st_empty);
               if (elect_one()) {
                 mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(b_stage_bytes));
                 tma_load_2d_a(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
@@ -460,25 +520,34 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       } else {
         const int aw = c1 * p.sw - p.pw, ah = c2 * p.sh - p.ph;
         int tap_r = 0, tap_s = 0, cb = 0, kcoord = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kbps) {
+          const int nk = min(p.kbps, p.num_kb - kb0);
+          sc.start();
           mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
-          if (elect_one()) {
-            mbar_expect_tx_a(full0 + stage * 8, tx_bytes);
-            if (!p.b_resident) tma_load_2d_a(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
-            if (p.patch) tma_load_4d_a(a_dst, &tmA, full0 + stage * 8, cb * kBK, aw + tap_s, ah + tap_r, c3);
-            else tma_load_2d_a(a_dst, &tmA, full0 + stage * 8, kcoord, c1);
+          sc.stop(st_empty);
+          if (elect_one()) mbar_expect_tx_a(full0 + stage * 8, tx_bytes * static_cast<uint32_t>(nk));
+          for (int j = 0; j < nk; ++j) {
+            if (elect_one()) {
+              if (!p.b_resident) tma_load_2d_a(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, full0 + stage * 8, kcoord, n_coord);
+              if (p.patch) tma_load_4d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, cb * kBK, aw + tap_s, ah + tap_r, c3);
+              else tma_load_2d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, kcoord, c1);
+            }
+            kcoord += kBK;
+            if (++cb == p.cin_blocks) {
+              cb = 0;
+              if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
+            }
           }
           __syncwarp();
-          kcoord += kBK;
-          if (++cb == p.cin_blocks) {
-            cb = 0;
-            if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
-          }
-          a_dst += kAStageBytes;
-          b_dst += static_cast<uint32_t>(b_stage_bytes);
+          a_dst += static_cast<uint32_t>(p.kbps) * kAStageBytes;
+          b_dst += static_cast<uint32_t>(p.kbps * b_stage_bytes);
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_dst = a_s0; b_dst = b_s0; }
         }
       }
+    }
+    if (sc.on && lane == 0) {
+      long long* o = p.stall + 1 + blockIdx.x * 16;
+      o[9] = clock64() - st_begin; o[10] = st_empty; o[11] = st_rempty;
     }
   }
 

@@ -219,8 +219,9 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.res_mode = io.res_mode; a.res = io.res; a.res_ld = io.res_ld; a.rH = io.rH; a.rW = io.rW;
   a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M);
   a.watchdog = ctx->wd_dev;
-  a.trace = ctx->trace_dev;
-  if (a.trace) cudaMemsetAsync(a.trace, 0, 8, stream);
+  a.trace = ctx->trace_mode == 1 ? ctx->trace_dev : nullptr;
+  a.stall = ctx->trace_mode == 2 ? ctx->trace_dev : nullptr;
+  if (ctx->trace_dev) cudaMemsetAsync(ctx->trace_dev, 0, 8, stream);
 
   CUtensorMap tmA, tmO, tmR;
   memset(&tmR, 0, sizeof(tmR));
@@ -279,7 +280,12 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   const int base_fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? kResSets * 2 * kSlabBytes : 0) +
                          (a.b_resident ? w_bytes : 0) + (4 * kMaxStages + 10) * 8 + 2048 + 1024;
   const int total_budget = 226 * 1024 - base_fixed;
-  const int stage_bytes = (a.halo ? 0 : kAStageBytes) + (a.b_resident ? 0 : L.BN * 128);
+  a.kbps = (!a.halo && a.num_kb >= 2 && ctx->kbps2) ? 2 : 1;
+  int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? 1 : a.kbps) * L.BN * 128);
+  if (a.kbps == 2 && total_budget / stage_bytes < 3) {   // too few double stages to cover the TMA latency
+    a.kbps = 1;
+    stage_bytes /= 2;
+  }
   if (a.halo) {
     // TMA latency is hidden by bytes in flight: with resident weights the whole budget goes to halo buffers,
     // otherwise the halo ring gets about a third and the weight ring the rest
@@ -409,6 +415,8 @@ int frb_destroy(frb_ctx* ctx) {
   for (auto& kv : ctx->nets) destroy_net(kv.second);
   ctx->nets.clear();
   if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
+  for (cudaEvent_t e : ctx->lt_events) cudaEventDestroy(e);
+  if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   delete ctx;
@@ -427,7 +435,10 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       return FRB_OK;
     case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_HALO: ctx->halo_mode = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_KBPS2: ctx->kbps2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_TRACE:
+      ctx->trace_mode = value;
       if (value && ctx->trace_dev == nullptr) {
         if (cudaMalloc(&ctx->trace_dev, (1 + 3 * 4000) * sizeof(long long)) != cudaSuccess) return set_err(ctx, FRB_ERR_CUDA, "trace alloc failed");
       } else if (!value && ctx->trace_dev != nullptr) {
@@ -448,6 +459,20 @@ int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records) {
   if (cudaMemcpy(h_out, ctx->trace_dev, (1 + 3 * static_cast<size_t>(n)) * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return FRB_ERR_CUDA;
   return FRB_OK;
+}
+
+int frb_debug_layer_times(frb_ctx* ctx, double* h_rows, int max_rows) {
+  if (ctx == nullptr || h_rows == nullptr) return -FRB_ERR_INVALID;
+  const int n = std::min<int>(max_rows, static_cast<int>(ctx->lt_info.size() / 6));
+  if (n <= 0 || ctx->lt_events.size() < static_cast<size_t>(n) + 1) return 0;
+  if (cudaEventSynchronize(ctx->lt_events[n]) != cudaSuccess) return -FRB_ERR_CUDA;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->lt_events[i], ctx->lt_events[i + 1]);
+    for (int j = 0; j < 5; ++j) h_rows[i * 6 + j] = ctx->lt_info[i * 6 + j];
+    h_rows[i * 6 + 5] = ms;
+  }
+  return n;
 }
 
 int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, const float* h_w, const float* h_bias,

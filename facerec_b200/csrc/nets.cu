@@ -651,6 +651,20 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
                             : (t.ext == 2 ? reinterpret_cast<uint8_t*>(ep.emb) : static_cast<uint8_t*>(net->arena) + t.off);
     return p + static_cast<size_t>(v.coff) * t.elem;
   };
+  const bool timed = ctx->layer_times != 0;
+  size_t ev = 0;
+  auto mark = [&]() {
+    if (ev >= ctx->lt_events.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ctx->lt_events.push_back(e);
+    }
+    cudaEventRecord(ctx->lt_events[ev++], st);
+  };
+  if (timed) {
+    ctx->lt_info.clear();
+    mark();
+  }
   for (const Op& op : plan.ops) {
     int rc = FRB_OK;
     const TensorInfo& ti = plan.tensors[op.in.t];
@@ -686,6 +700,22 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
         break;
     }
     if (rc != FRB_OK) return rc;
+    if (timed) {
+      double M = 0, N = 0, K = 0;
+      if (op.kind == OP_CONV) {
+        const ConvLayer& L = net->convs[op.layer];
+        M = L.special ? static_cast<double>(plan.B) * ti.H * (ti.W - 3)
+                      : static_cast<double>(plan.B) * conv_out_dim(ti.H, L.kh, L.sh, L.ph) * conv_out_dim(ti.W, L.kw, L.sw, L.pw);
+        N = L.Cout;
+        K = static_cast<double>(L.kh) * L.kw * L.Cin;
+      } else {
+        M = static_cast<double>(plan.B) * ti.H * ti.W;
+        N = ti.C;
+      }
+      const double row[6] = {static_cast<double>(op.kind), M, N, K, 2.0 * M * N * K, 0.0};
+      ctx->lt_info.insert(ctx->lt_info.end(), row, row + 6);
+      mark();
+    }
   }
   return FRB_OK;
 }

@@ -40,11 +40,15 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="", help="substring filter on the layer name")
     ap.add_argument("--no-halo", action="store_true")
+    ap.add_argument("--halo", action="store_true")
+    ap.add_argument("--kbps1", action="store_true")
     a = ap.parse_args()
     ctx = _lib.Context(0)
     ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
-    if a.no_halo:
-        ctx.set_option(_lib.FRB_OPT_HALO, 0)
+    if a.halo:
+        ctx.set_option(_lib.FRB_OPT_HALO, 1)
+    if a.kbps1:
+        ctx.set_option(_lib.FRB_OPT_KBPS2, 0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))

@@ -1,0 +1,46 @@
+"""Where one conv_tma launch waits (FRB_OPT_TRACE = 2): stall cycles of the epilogue (thread 0), MMA issuer and TMA
+producer, averaged over CTAs, as fractions of each role's lifetime.
+Usage: python tools/stall_conv.py --shape B,H,W,Cin,Cout,k,stride,pad [--res] [--bn-cap 128]"""
+import argparse, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from facerec_b200 import ops, _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--shape", action="append", default=[])
+ap.add_argument("--res", action="store_true")
+ap.add_argument("--bn-cap", type=int, default=256)
+ap.add_argument("--halo", action="store_true")
+a = ap.parse_args()
+for shape in a.shape:
+    B, H, W, Cin, Cout, k, s, p = (int(v) for v in shape.split(","))
+    x = torch.randn(B, H, W, Cin, device="cuda").half()
+    w = (np.random.RandomState(0).standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(B, Ho, Wo, Cout, device="cuda").half() if a.res else None
+    plain = _lib.Context(0)
+    plain.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
+    if a.halo:
+        plain.set_option(_lib.FRB_OPT_HALO, 1)
+    _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=5)
+    plain.close()
+    ctx = _lib.Context(0)
+    ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
+    ctx.set_option(_lib.FRB_OPT_TRACE, 2)
+    if a.halo:
+        ctx.set_option(_lib.FRB_OPT_HALO, 1)
+    _, ms = ops.conv2d(ctx, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=1)
+    buf = np.zeros(1 + 3 * 4000, np.int64)
+    ctx.check(ctx.lib.frb_debug_trace(ctx.handle, buf.ctypes.data, 4000), "trace")
+    c = buf[1:1 + 148 * 16].reshape(148, 16).astype(np.float64)
+    c = c[c[:, 0] > 0]
+    m = c.mean(0)
+    fl = 2.0 * B * Ho * Wo * Cout * k * k * Cin
+    print(f"== {shape}{' +res' if a.res else ''}: {ms0:.3f} ms plain ({fl / ms0 / 1e9:.0f} TFLOP/s), {ms:.3f} ms counted; "
+          f"{m[5]:.1f} tiles per CTA, {m[0] / max(m[5], 1):.0f} cycles per tile")
+    print(f"   epilogue t0 : accumulator wait {m[1] / m[0] * 100:5.1f}%  residual wait {m[2] / m[0] * 100:5.1f}%  "
+          f"staging-slab (store drain) wait {m[3] / m[0] * 100:5.1f}%  barriers {m[4] / m[0] * 100:5.1f}%")
+    print(f"   MMA issuer  : TMEM-buffer wait {m[7] / m[6] * 100:5.1f}%  operand (full) wait {m[8] / m[6] * 100:5.1f}%")
+    print(f"   TMA producer: ring-slot (empty) wait {m[10] / m[9] * 100:5.1f}%  residual-set wait {m[11] / m[9] * 100:5.1f}%", flush=True)
+    ctx.close()
