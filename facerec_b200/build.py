@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfacerec_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["core.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu", "linkage.cu", "api.cu"]
+SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "conv_tma_stall.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
+           "linkage.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
@@ -65,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(10, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     r = subprocess.run([nvcc, "-shared", "-o", OUT, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:

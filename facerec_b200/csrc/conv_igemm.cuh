@@ -77,6 +77,10 @@ struct Elem16<false> {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  static __device__ __forceinline__ uint32_t relu2(uint32_t u) {
+    __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&u), __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
 };
 template <>
 struct Elem16<true> {
@@ -87,6 +91,10 @@ struct Elem16<true> {
   }
   static __device__ __forceinline__ uint32_t from_f2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t relu2(uint32_t u) {
+    __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u), __float2bfloat162_rn(0.f));
     return *reinterpret_cast<uint32_t*>(&h);
   }
 };

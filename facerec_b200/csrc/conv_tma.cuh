@@ -8,12 +8,15 @@
 // and ragged image borders are the tensor map's out-of-bounds zero fill.  Weights come the same way
 // (2-D box of the [Cout, K] matrix); when the whole weight matrix is small (<= 80 KB: the bandwidth-bound
 // early layers) it is loaded ONCE per CTA and stays resident, so the stage ring carries only A and the
-// L2 -> SM traffic drops by the weight re-fetch of every tile.  Accumulators live in TMEM (double
-// buffered, 2 x BN columns), and the epilogue (bias, residual, per-channel slope) packs 64-column slabs
-// into a swizzled staging tile that TMA stores back as the same patch box — partial tiles are clipped by
-// the hardware, and every global store is a full 128-byte line.  The residual tile (ResNet / Inception
-// skip) is a producer-side TMA prefetch, double buffered across tiles, so its latency hides behind the
-// previous tile's epilogue.
+// L2 -> SM traffic drops by the weight re-fetch of every tile.  Accumulators live in TMEM (four buffers of BN
+// columns for BN <= 128, two above), and the epilogue (bias, residual, per-channel slope) packs 64-column slabs
+// into swizzled staging slabs that TMA stores back as the same patch box — partial tiles are clipped by
+// the hardware, and every global store is a full 128-byte line.  A pre-activation residual (ResNet / Inception
+// skip) is added BY THE TENSOR CORE: after the last weight k-block the producer sends each 64-channel residual slab
+// of the tile through the same stage ring as one more A block, and the issuer multiplies it by a resident 64 x 64
+// identity into the slab's accumulator columns (16-bit x 1.0 is exact in the fp32 accumulator).  The skip tensor
+// thus gets the deep TMA prefetch of the main loop and costs the epilogue nothing — as per-thread global loads it
+// left the epilogue groups waiting on HBM latency (profiles/r01_ncu_epilogue_v7.md).
 //
 // Halo mode (stride-1 k x k convs): instead of one A box per filter tap (k*k reads of the same pixels through
 // L2), the producer loads ONE (bh+kh-1) x (bw+kw-1) halo tile per 64-channel block and the MMA issuer points
@@ -22,11 +25,11 @@
 // shared-memory ADDRESS (tools/umma_shift_probe.cu: any 128-byte row offset and any group stride read back
 // exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.
 //
-// Warp roles (576 threads): 0-15 epilogue, 16 MMA issuer + TMEM allocator, 17 TMA producer.
-// The epilogue is instruction-issue bound when one warp per scheduler walks a whole 64-column row
-// (ncu: ~2 400 cycles per slab, issue slots mostly idle), so each TMEM lane quarter (warp % 4) is
-// served by four warps that take 16 columns of the slab each: four warps per scheduler hide each
-// other's dependent-issue latency.
+// Warp roles (448 threads, 14 warps = at most 4 per scheduler so the epilogue may hold 128 registers without
+// spilling — with ~227 KB of shared memory there is no L1 left and a spill is an L2 round trip): warps 0-11 are
+// three independent epilogue groups (one warp per TMEM lane quarter each), 12 the MMA issuer + TMEM allocator,
+// 13 the TMA producer.  Profiles that led here: profiles/r01_stall_counters_v6.txt (16 warps sharing every slab
+// behind two 512-thread barriers: 2 000 cycles per slab, the MMA issuer waiting for a TMEM buffer 78 % of the time).
 // Persistent: one CTA per SM walks tiles round-robin (n fastest, so CTAs running at the same time
 // share the A patch through L2).
 #pragma once
@@ -34,15 +37,17 @@
 
 namespace frb {
 
-constexpr int kEpiWarps = 16;
+constexpr int kEpiWarps = 12;             // 14 warps in all: at most 4 per scheduler, so every thread may hold 128 registers
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTmaThreads = kEpiThreads + 64;
 constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
 constexpr int kSlabBytes = kBM * kSlab * 2;
-constexpr int kColsPerWarp = kSlab / (kEpiWarps / 4);   // 16
-constexpr int kOutBufs = 2;                // staging slabs (TMA stores drain asynchronously)
-constexpr int kResSets = 2;                // residual tiles in flight (each = up to 2 slabs)
+constexpr int kEpiGroups = kEpiWarps / 4;  // independent epilogue groups: one warp per TMEM lane quarter each
+constexpr int kGroupThreads = 128;
+constexpr int kOutBufs = kEpiGroups;       // one staging slab per group (doubles as its residual slab)
+constexpr int kMaxAcc = 4;                 // TMEM accumulator buffers: 4 for BN <= 128, else 2
 constexpr int kResidentWeightBytes = 80 * 1024;
+constexpr int kIdentBytes = 64 * 128;      // identity B operand of the residual MMAs
 
 struct ConvTmaArgs {
   int patch;             // 0: linear M tiling (1x1, stride 1, no padding); 1: spatial patch tiling
@@ -50,6 +55,7 @@ struct ConvTmaArgs {
   int cin_blocks;        // 64-channel blocks per filter tap
   int num_kb;            // kh*kw*cin_blocks
   int BN, n_tiles, total_tiles;
+  uint32_t fd_n[2], fd_w[2], fd_h[2];   // fast-division (multiplier, shift) pairs for n_tiles, tiles_w, tiles_h
   int tiles_w, tiles_h;  // patch grid inside an image group
   int bw, bh, bb;        // patch = bb images x bh rows x bw cols (<= 128 pixels)
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
@@ -64,75 +70,86 @@ struct ConvTmaArgs {
   int act_kind;          // 0: per-channel slope (general), 1: ReLU everywhere, 2: linear everywhere
   const float* bias;     // [n_tiles*BN]
   const float* slope;    // [n_tiles*BN]
-  int res_mode;          // ConvRes: PRE_ACT comes through tmR; POST_ACT_UPSAMPLE (linear tiling only) from global
-  const void* res;       // POST_ACT_UPSAMPLE source
+  int res_mode;          // ConvRes: both kinds are read from global by the epilogue threads (PRE_ACT one slab ahead)
+  const void* res;       // residual tensor [B, Ho, Wo, res_ld] (PRE_ACT) or [B, rH, rW, res_ld] (POST_ACT_UPSAMPLE)
+  int B;                 // images (patch tiling bounds check of the residual rows)
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
-  long long* trace;      // debug: (event, tile_iter, clock64) records of CTA 0, or null
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
 };
 
+// Host entry points (conv_tma_f16.cu / conv_tma_bf16.cu / conv_tma_stall.cu): pick the kernel variant for
+// (res = ConvRes, act = 0 per-channel slope / 1 ReLU / 2 linear) and launch it.
+cudaError_t conv_tma_launch_f16(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+    const CUtensorMap& tmI);
+cudaError_t conv_tma_launch_bf16(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                 const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+    const CUtensorMap& tmI);
+cudaError_t conv_tma_launch_stall(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                  const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+    const CUtensorMap& tmI);
+
 // Stall accounting (FRB_OPT_TRACE = 2): clock64 deltas around the blocking waits of one thread per role, summed in
 // registers and written once at the end (cheap enough not to move the timing, unlike the timeline below).
+template <bool kOn>
 struct StallClock {
   bool on;
   long long t0;
-  __device__ __forceinline__ void start() { if (on) t0 = clock64(); }
-  __device__ __forceinline__ void stop(long long& acc) { if (on) acc += clock64() - t0; }
+  __device__ __forceinline__ void start() { if (kOn && on) t0 = clock64(); }
+  __device__ __forceinline__ void stop(long long& acc) { if (kOn && on) acc += clock64() - t0; }
 };
 
-// Timeline probe (FRB_OPT_TRACE): CTA 0 appends (event id, tile_iter, clock) triples; trace[0] is the record count.
-__device__ __forceinline__ void trace_event(long long* trace, int event, int tile_iter) {
-  if (trace == nullptr || blockIdx.x != 0) return;
-  const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ULL);
-  if (i < 4000) {
-    trace[1 + 3 * i] = event;
-    trace[2 + 3 * i] = tile_iter;
-    trace[3 + 3 * i] = clock64();
-  }
+// n / d for n < 2^31 with (mul, shift) from fastdiv_make (host): three instructions instead of ~25
+__device__ __forceinline__ int fastdiv(int n, const uint32_t* fd) {
+  return static_cast<int>((__umulhi(static_cast<uint32_t>(n), fd[0]) + static_cast<uint32_t>(n)) >> fd[1]);
 }
 
-template <bool kBF16>
+// kRes: 0 no residual, 1 residual added before the activation (ResNet / Inception skip), 2 nearest-upsampled
+// residual added after it (FPN top-down).  kAct: 0 per-channel slope, 1 ReLU everywhere, 2 linear everywhere.
+template <bool kBF16, bool kStall, int kRes, int kAct>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ CUtensorMap tmA,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
-                const __grid_constant__ CUtensorMap tmR) {
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmI) {
   using E = Elem16<kBF16>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int b_stage_bytes = p.BN * 128;
-  const bool has_res = p.res_mode == RES_PRE_ACT;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * p.kbps * kAStageBytes);   // ring (or resident matrix)
   uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages * (p.halo ? 1 : p.kbps)) * b_stage_bytes;
-  uint8_t* smem_r = smem_o + kOutBufs * kSlabBytes;                                    // kResSets x 2 slabs (PRE_ACT only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (has_res ? kResSets * 2 * kSlabBytes : 0));
+  uint8_t* smem_i = smem_o + kOutBufs * kSlabBytes;                                    // 64 x 64 identity (kRes = 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_i + (kRes == 1 ? kIdentBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]
-  uint64_t* rfull_bar = bars + 2 * kMaxStages + 4;    // [kResSets]
-  uint64_t* rempty_bar = bars + 2 * kMaxStages + 6;   // [kResSets]
-  uint64_t* bres_bar = bars + 2 * kMaxStages + 8;     // [1]
-  uint64_t* afull_bar = bars + 2 * kMaxStages + 9;    // [kMaxStages] halo ring
-  uint64_t* aempty_bar = bars + 3 * kMaxStages + 9;   // [kMaxStages]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 9);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 10);   // [256]
-  float* s_slope = s_bias + 256;                                          // [256]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [kMaxAcc]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 4;   // [kMaxAcc]
+  uint64_t* bres_bar = bars + 2 * kMaxStages + 16;    // [1] resident weights + identity have landed
+  uint64_t* afull_bar = bars + 2 * kMaxStages + 17;   // [kMaxStages] halo ring
+  uint64_t* aempty_bar = bars + 3 * kMaxStages + 17;  // [kMaxStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 17);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 18);   // [kEpiGroups][kSlab]
+  float* s_slope = s_bias + kEpiGroups * kSlab;                           // [kEpiGroups][kSlab]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
+  const int nslab = (p.BN + kSlab - 1) / kSlab;
+  const int nacc = p.BN <= 128 ? kMaxAcc : 2;          // accumulator buffers in TMEM (nacc * BN <= 512 columns)
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(2 * p.BN)) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(nacc * p.BN)) tmem_cols <<= 1;
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    if (has_res) tma_prefetch_desc(&tmR);
+    if (kRes == 1) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmI);
+    }
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -140,11 +157,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < kMaxAcc; ++b) {
         mbar_init(&tfull_bar[b], 1);
-        mbar_init(&tempty_bar[b], kEpiWarps);
-        mbar_init(&rfull_bar[b], 1);
-        mbar_init(&rempty_bar[b], 1);
+        mbar_init(&tempty_bar[b], 4 * nslab);          // every warp of the nslab groups that read the buffer
       }
       mbar_init(bres_bar, 1);
       for (int s = 0; s < kMaxStages; ++s) {
@@ -161,18 +176,17 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nslab = (p.BN + kSlab - 1) / kSlab;
 
   // tile -> coordinates of its first pixel
   auto decode = [&](int tile, int& n_tile, int& c1, int& c2, int& c3) {
-    const int m_tile = tile / p.n_tiles;
+    const int m_tile = fastdiv(tile, p.fd_n);
     n_tile = tile - m_tile * p.n_tiles;
     if (p.patch) {
-      const int tw = m_tile % p.tiles_w;
-      const int t = m_tile / p.tiles_w;
-      c1 = tw * p.bw;
-      c2 = (t % p.tiles_h) * p.bh;
-      c3 = (t / p.tiles_h) * p.bb;
+      const int t = fastdiv(m_tile, p.fd_w);
+      const int tb = fastdiv(t, p.fd_h);
+      c1 = (m_tile - t * p.tiles_w) * p.bw;
+      c2 = (t - tb * p.tiles_h) * p.bh;
+      c3 = tb * p.bb;
     } else {
       c1 = m_tile * kBM;
       c2 = 0;
@@ -182,29 +196,60 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
 
   if (warp < kEpiWarps) {
     // ================================================================ epilogue
+    // Independent groups of four warps (one warp per TMEM lane quarter).  Group g owns staging slab g, named
+    // barrier 1 + g and every 64-column output slab whose running index q (= tile_iter * nslab + slab) has
+    // q % kEpiGroups == g, so several slabs — of different tiles when BN = 64 — are in flight at once and nothing
+    // in here synchronises more than 128 threads.  The bias / slope values of a slab are fetched ONE SLAB AHEAD,
+    // right after the previous slab's math.  A pre-activation residual never shows up here: the MMA issuer has
+    // already added it into the accumulator (see there).  Residual kind and activation are template parameters:
+    // as run-time flags they cost ~450 predicated-off or branch instructions per warp and slab
+    // (profiles/r01_ncu_epilogue_v7.md).
     const int quarter = warp & 3;              // TMEM lane quarter this warp may read
-    const int csub = warp >> 2;                // which 16 columns of every 64-column slab
+    const int grp = warp >> 2;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
+    const bool leader = gtid == 0;
     const int row = quarter * 32 + lane;
-    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw7 = static_cast<uint32_t>(row & 7);
-    const int col0 = csub * kColsPerWarp;
-    int tile_iter = 0;
-    uint32_t slab_ctr = 0;
-    StallClock sc{p.stall != nullptr && threadIdx.x == 0, 0};
+    uint8_t* const orow = smem_o + grp * kSlabBytes + static_cast<uint32_t>(row) * 128u;
+    float* const g_bias = s_bias + grp * kSlab;
+    float* const g_slope = s_slope + grp * kSlab;
+    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int my_slabs = my_tiles * nslab;
+    StallClock<kStall> sc{kStall && p.stall != nullptr && threadIdx.x == 0, 0};
     long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
-    const long long st_begin = sc.on ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
-      int n_tile, c1, c2, c3;
-      decode(tile, n_tile, c1, c2, c3);
-      const int n_base = n_tile * p.BN;
-      const int buf = tile_iter & 1;
-      const uint32_t tphase = (tile_iter >> 1) & 1;
-      const int rset = tile_iter % kResSets;
-      const uint32_t rphase = (tile_iter / kResSets) & 1;
+    const long long st_begin = kStall && sc.on ? clock64() : 0;
+
+    struct Slab { int tile_iter, s, n0, ncols, c1, c2, c3; };
+    auto slab_at = [&](int ti, int s2) {
+      Slab sl;
+      int nt;
+      decode(blockIdx.x + ti * gridDim.x, nt, sl.c1, sl.c2, sl.c3);
+      sl.tile_iter = ti;
+      sl.s = s2;
+      sl.n0 = nt * p.BN + s2 * kSlab;
+      sl.ncols = min(kSlab, p.BN - s2 * kSlab);
+      return sl;
+    };
+    float next_bs = 0.f;                       // bias (threads 0-63 of the group) / slope (64-127) of the next slab
+    auto prefetch = [&](const Slab& sl) {
+      const int col = gtid & (kSlab - 1);
+      next_bs = 0.f;
+      if (col < sl.ncols && (kAct == 0 || gtid < kSlab)) next_bs = __ldg((gtid < kSlab ? p.bias : p.slope) + sl.n0 + col);
+    };
+    int ti = grp / nslab, s_in = grp - ti * nslab;
+    Slab cur = {};
+    if (grp < my_slabs) {
+      cur = slab_at(ti, s_in);
+      prefetch(cur);
+    }
+    for (int q = grp; q < my_slabs; q += kEpiGroups) {
+      const int buf = cur.tile_iter % nacc;
+      const uint32_t tphase = static_cast<uint32_t>(cur.tile_iter / nacc) & 1u;
+      const int ncols = cur.ncols;
 
       const typename E::T* up_row = nullptr;
-      if (p.res_mode == RES_POST_ACT_UPSAMPLE) {
-        const int m = c1 + row;
+      if constexpr (kRes == 2) {
+        const int m = cur.c1 + row;
         if (m < p.M) {
           const int ow = m % p.Wo;
           const int t = m / p.Wo;
@@ -213,125 +258,119 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           const int rh = (oh * p.rH) / p.Ho;   // nearest: floor(dst * in / out)
           const int rw = (ow * p.rW) / p.Wo;
           up_row = static_cast<const typename E::T*>(p.res) +
-                   (static_cast<size_t>(b) * p.rH * p.rW + static_cast<size_t>(rh) * p.rW + rw) * p.res_ld;
+                   (static_cast<size_t>(b) * p.rH * p.rW + static_cast<size_t>(rh) * p.rW + rw) * p.res_ld + cur.n0;
         }
       }
-      // bias / slope of this N tile -> shared memory (broadcast reads below); the previous tile's readers
-      // are all past their slab barriers, and the first slab barrier below orders these writes before use
-      for (int t = threadIdx.x; t < p.BN; t += kEpiThreads) {
-        s_bias[t] = __ldg(p.bias + n_base + t);
-        s_slope[t] = __ldg(p.slope + n_base + t);
-      }
+      // bias / slope of this slab -> the group's shared copy (broadcast reads below); the group's previous readers
+      // are past barrier B of the previous slab, barrier A below orders these writes before use
+      if (gtid < kSlab) g_bias[gtid] = next_bs;
+      else if (kAct == 0) g_slope[gtid - kSlab] = next_bs;
 
-      if (threadIdx.x == 0) trace_event(p.trace, 10, tile_iter);        // epilogue ready for this tile
       sc.start();
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
       sc.stop(st_tfull);
       tc_fence_after();
-      if (threadIdx.x == 0) trace_event(p.trace, 11, tile_iter);        // accumulator available
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN);
-      sc.start();
-      if (has_res) mbar_wait(&rfull_bar[rset], rphase, p.watchdog, 500 + rset);
-      sc.stop(st_res);
-
-      for (int s = 0; s < nslab; ++s) {
-        const int ncols = min(kSlab, p.BN - s * kSlab);
-        const int n0 = n_base + s * kSlab;
-        const bool mine = col0 < ncols;            // warp-uniform (BN is a multiple of 16)
-        float x[kColsPerWarp];
-        if (mine) {
-          uint32_t v[kColsPerWarp];
-          tmem_ld16(taddr + s * kSlab + col0, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < kColsPerWarp; ++c) x[c] = __uint_as_float(v[c]);
-        }
-        if (s == nslab - 1) {                     // accumulator fully read: hand the TMEM buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        }
-        // staging slab `ob` is free once the store issued kOutBufs slabs ago has finished reading it
-        const uint32_t ob = slab_ctr % kOutBufs;
-        if (threadIdx.x == 0) {
-          trace_event(p.trace, 13, tile_iter);                              // TMEM read out, waiting for a staging slab
-          sc.start();
-          tma_store_wait_read<kOutBufs - 1>();
-          sc.stop(st_slab);
-          trace_event(p.trace, 14, tile_iter);
-        }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.BN + cur.s * kSlab);
+      uint32_t v0[16], v1[16];
+      tmem_ld16(taddr, v0);                    // in flight while the staging slab is being secured
+      if (leader) {
         sc.start();
-        named_bar_sync(1, kEpiThreads);
-        sc.stop(st_bar);
+        tma_store_wait_read<0>();              // the previous store of this group has finished reading the slab
+        sc.stop(st_slab);
+      }
+      sc.start();
+      named_bar_sync(1 + grp, kGroupThreads);  // barrier A
+      sc.stop(st_bar);
 
-        if (mine) {
-          const uint8_t* rrow = smem_r + (rset * 2 + s) * kSlabBytes + row_off;
-          uint8_t* orow = smem_o + ob * kSlabBytes + row_off;
+      auto finish16 = [&](const uint32_t* v, int cbase) {
 #pragma unroll
-          for (int c = 0; c < kColsPerWarp / 8; ++c) {
-            float* y = x + c * 8;
-            const int cc = col0 + c * 8;                                   // column inside the slab
-            const uint32_t chunk = (static_cast<uint32_t>(cc >> 3) ^ sw7) << 4;
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + s * kSlab + cc);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + s * kSlab + cc + 4);
-            y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
-            y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
-            if (has_res) {
-              const uint4 r = *reinterpret_cast<const uint4*>(rrow + chunk);
+        for (int c = 0; c < 2; ++c) {
+          float y[8];
+          const int cc = cbase + c * 8;                                  // column inside the slab
+          uint8_t* const dst = orow + ((static_cast<uint32_t>(cc >> 3) ^ sw7) << 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(g_bias + cc);
+          const float4 b1 = *reinterpret_cast<const float4*>(g_bias + cc + 4);
+          y[0] = __uint_as_float(v[c * 8 + 0]) + b0.x; y[1] = __uint_as_float(v[c * 8 + 1]) + b0.y;
+          y[2] = __uint_as_float(v[c * 8 + 2]) + b0.z; y[3] = __uint_as_float(v[c * 8 + 3]) + b0.w;
+          y[4] = __uint_as_float(v[c * 8 + 4]) + b1.x; y[5] = __uint_as_float(v[c * 8 + 5]) + b1.y;
+          y[6] = __uint_as_float(v[c * 8 + 6]) + b1.z; y[7] = __uint_as_float(v[c * 8 + 7]) + b1.w;
+          if constexpr (kAct == 0) {
+            const float4 s0 = *reinterpret_cast<const float4*>(g_slope + cc);
+            const float4 s1 = *reinterpret_cast<const float4*>(g_slope + cc + 4);
+            // leaky(x) = max(x,0) + slope * min(x,0): branch-free, slope 1 = identity, 0 = ReLU
+            y[0] = fmaf(s0.x, fminf(y[0], 0.f), fmaxf(y[0], 0.f)); y[1] = fmaf(s0.y, fminf(y[1], 0.f), fmaxf(y[1], 0.f));
+            y[2] = fmaf(s0.z, fminf(y[2], 0.f), fmaxf(y[2], 0.f)); y[3] = fmaf(s0.w, fminf(y[3], 0.f), fmaxf(y[3], 0.f));
+            y[4] = fmaf(s1.x, fminf(y[4], 0.f), fmaxf(y[4], 0.f)); y[5] = fmaf(s1.y, fminf(y[5], 0.f), fmaxf(y[5], 0.f));
+            y[6] = fmaf(s1.z, fminf(y[6], 0.f), fmaxf(y[6], 0.f)); y[7] = fmaf(s1.w, fminf(y[7], 0.f), fmaxf(y[7], 0.f));
+          }
+          if constexpr (kRes == 2) {
+            if (up_row != nullptr) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(up_row + cc));
               float2 f;
               f = E::to_f2(r.x); y[0] += f.x; y[1] += f.y;
               f = E::to_f2(r.y); y[2] += f.x; y[3] += f.y;
               f = E::to_f2(r.z); y[4] += f.x; y[5] += f.y;
               f = E::to_f2(r.w); y[6] += f.x; y[7] += f.y;
             }
-            if (p.act_kind == 1) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
-            } else if (p.act_kind == 0) {
-              const float4 s0 = *reinterpret_cast<const float4*>(s_slope + s * kSlab + cc);
-              const float4 s1 = *reinterpret_cast<const float4*>(s_slope + s * kSlab + cc + 4);
-              // leaky(x) = max(x,0) + slope * min(x,0): branch-free, slope 1 = identity, 0 = ReLU
-              y[0] = fmaf(s0.x, fminf(y[0], 0.f), fmaxf(y[0], 0.f)); y[1] = fmaf(s0.y, fminf(y[1], 0.f), fmaxf(y[1], 0.f));
-              y[2] = fmaf(s0.z, fminf(y[2], 0.f), fmaxf(y[2], 0.f)); y[3] = fmaf(s0.w, fminf(y[3], 0.f), fmaxf(y[3], 0.f));
-              y[4] = fmaf(s1.x, fminf(y[4], 0.f), fmaxf(y[4], 0.f)); y[5] = fmaf(s1.y, fminf(y[5], 0.f), fmaxf(y[5], 0.f));
-              y[6] = fmaf(s1.z, fminf(y[6], 0.f), fmaxf(y[6], 0.f)); y[7] = fmaf(s1.w, fminf(y[7], 0.f), fmaxf(y[7], 0.f));
-            }
-            if (p.res_mode == RES_POST_ACT_UPSAMPLE && up_row != nullptr) {
-              const uint4 r = __ldg(reinterpret_cast<const uint4*>(up_row + n0 + cc));
-              float2 f;
-              f = E::to_f2(r.x); y[0] += f.x; y[1] += f.y;
-              f = E::to_f2(r.y); y[2] += f.x; y[3] += f.y;
-              f = E::to_f2(r.z); y[4] += f.x; y[5] += f.y;
-              f = E::to_f2(r.w); y[6] += f.x; y[7] += f.y;
-            }
-            uint4 o;
-            o.x = E::from_f2(y[0], y[1]);
-            o.y = E::from_f2(y[2], y[3]);
-            o.z = E::from_f2(y[4], y[5]);
-            o.w = E::from_f2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(orow + chunk) = o;
+          }
+          uint4 o;
+          o.x = E::from_f2(y[0], y[1]);
+          o.y = E::from_f2(y[2], y[3]);
+          o.z = E::from_f2(y[4], y[5]);
+          o.w = E::from_f2(y[6], y[7]);
+          if constexpr (kAct == 1) {
+            // ReLU on the packed 16-bit pairs: rounding is monotonic and keeps the sign, so this is max(x, 0) rounded
+            o.x = E::relu2(o.x); o.y = E::relu2(o.y); o.z = E::relu2(o.z); o.w = E::relu2(o.w);
+          }
+          *reinterpret_cast<uint4*>(dst) = o;
+        }
+      };
+      // 16 columns at a time, the next tcgen05.ld in flight while the current chunk is finished (ncols % 16 == 0;
+      // columns past ncols of a partial last slab are never stored: the output tensor map clips them)
+      tc_wait_ld16(v0);
+      if (ncols > 16) tmem_ld16(taddr + 16, v1);
+      finish16(v0, 0);
+      if (ncols > 16) {
+        tc_wait_ld16(v1);
+        if (ncols > 32) tmem_ld16(taddr + 32, v0);
+        finish16(v1, 16);
+        if (ncols > 32) {
+          tc_wait_ld16(v0);
+          if (ncols > 48) tmem_ld16(taddr + 48, v1);
+          finish16(v0, 32);
+          if (ncols > 48) {
+            tc_wait_ld16(v1);
+            finish16(v1, 48);
           }
         }
-        fence_proxy_async_smem();
-        sc.start();
-        named_bar_sync(1, kEpiThreads);
-        sc.stop(st_bar);
-        if (threadIdx.x == 0) {
-          if (p.patch) tma_store_4d(&tmO, smem_o + ob * kSlabBytes, n0, c1, c2, c3);
-          else tma_store_2d(&tmO, smem_o + ob * kSlabBytes, n0, c1);
-          tma_store_commit();
-          if (s == nslab - 1) trace_event(p.trace, 12, tile_iter);        // last store of the tile issued
-          // every epilogue thread is past its reads of this tile's residual slabs: give the set back
-          if (has_res && s == nslab - 1) mbar_arrive(&rempty_bar[rset]);
-        }
-        ++slab_ctr;
+      }
+      // this warp's part of the accumulator slab is in registers / staged: hand the TMEM buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      // global reads of the group's next slab
+      s_in += kEpiGroups;
+      while (s_in >= nslab) { s_in -= nslab; ++ti; }
+      const Slab done = cur;
+      if (q + kEpiGroups < my_slabs) {
+        cur = slab_at(ti, s_in);
+        prefetch(cur);
+      }
+      fence_proxy_async_smem();
+      sc.start();
+      named_bar_sync(1 + grp, kGroupThreads);  // barrier B
+      sc.stop(st_bar);
+      if (leader) {
+        if (p.patch) tma_store_4d(&tmO, smem_o + grp * kSlabBytes, done.n0, done.c1, done.c2, done.c3);
+        else tma_store_2d(&tmO, smem_o + grp * kSlabBytes, done.n0, done.c1);
+        tma_store_commit();
       }
     }
-    if (sc.on) {
+    if (kStall && sc.on) {
       long long* o = p.stall + 1 + blockIdx.x * 16;
-      o[0] = clock64() - st_begin; o[1] = st_tfull; o[2] = st_res; o[3] = st_slab; o[4] = st_bar; o[5] = tile_iter;
+      o[0] = clock64() - st_begin; o[1] = st_tfull; o[2] = st_res; o[3] = st_slab; o[4] = st_bar; o[5] = my_tiles;
     }
-    if (threadIdx.x == 0) tma_store_wait<0>();     // stores must land before the CTA (and its smem) goes away
+    if (leader) tma_store_wait<0>();           // stores must land before the CTA (and its smem) goes away
   } else if (warp == kMmaWarp) {
     // ============================================================== MMA issuer
     // Everything here is warp-uniform and incremental: descriptor LOW words (start address >> 4) advance by
@@ -350,19 +389,19 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     uint32_t phase = 0, aphase = 0;
     uint32_t a_ring = a_lo0, b_ring = b_lo0;          // descriptor low words of the current ring slots
     int tile_iter = 0;
-    StallClock sc{p.stall != nullptr, 0};
+    StallClock<kStall> sc{kStall && p.stall != nullptr, 0};
     long long st_tempty = 0, st_full = 0;
-    const long long st_begin = sc.on ? clock64() : 0;
-    if (p.b_resident) mbar_wait(bres_bar, 0, p.watchdog, 250);
+    const long long st_begin = kStall && sc.on ? clock64() : 0;
+    if (p.b_resident || kRes == 1) mbar_wait(bres_bar, 0, p.watchdog, 250);
+    const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
-      const int buf = tile_iter & 1;
-      const uint32_t tphase = (tile_iter >> 1) & 1;
+      const int buf = tile_iter % nacc;
+      const uint32_t tphase = static_cast<uint32_t>(tile_iter / nacc) & 1u;
       const int n_tile = tile % p.n_tiles;
       sc.start();
       mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf);
       sc.stop(st_tempty);
       tc_fence_after();
-      if (lane == 0) trace_event(p.trace, 21, tile_iter);                 // TMEM buffer free
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
       const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
       if (p.halo) {
@@ -392,7 +431,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
                 if (!p.b_resident) tc_commit_a(empty0 + stage * 8);
                 if (last_tap) {
                   tc_commit_a(aempty0 + astage * 8);
-                  if (cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+                  if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
                 }
               }
               __syncwarp();
@@ -431,7 +470,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               tc_mma_f16(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
             }
             tc_commit_a(empty0 + stage * 8);
-            if (kb0 + p.kbps >= p.num_kb) tc_commit_a(tfull0 + buf * 8);
+            if (kRes != 1 && kb0 + p.kbps >= p.num_kb) tc_commit_a(tfull0 + buf * 8);
           }
           __syncwarp();
           b_cur += static_cast<uint32_t>(p.kbps) * b_step;
@@ -440,29 +479,54 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
         }
       }
-      if (lane == 0) trace_event(p.trace, 23, tile_iter);                 // all MMAs of the tile issued
+      if constexpr (kRes == 1) {
+        // residual slabs: accumulator columns [rs * 64, rs * 64 + ncols) += residual slab (A, from the ring) x identity
+        for (int rs = 0; rs < nslab; ++rs) {
+          const uint32_t idesc_r = make_idesc_f16(kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
+          const uint32_t d_r = d_tmem + static_cast<uint32_t>(rs * kSlab);
+          sc.start();
+          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          sc.stop(st_full);
+          tc_fence_after();
+          if (elect_one()) {
+            tc_mma_f16(d_r, pack_desc(a_ring, hi1024), pack_desc(ident_lo, hi1024), idesc_r, 1u);
+            tc_mma_f16(d_r, pack_desc(a_ring + 2, hi1024), pack_desc(ident_lo + 2, hi1024), idesc_r, 1u);
+            tc_mma_f16(d_r, pack_desc(a_ring + 4, hi1024), pack_desc(ident_lo + 4, hi1024), idesc_r, 1u);
+            tc_mma_f16(d_r, pack_desc(a_ring + 6, hi1024), pack_desc(ident_lo + 6, hi1024), idesc_r, 1u);
+            tc_commit_a(empty0 + stage * 8);
+            if (rs == nslab - 1) tc_commit_a(tfull0 + buf * 8);
+          }
+          __syncwarp();
+          a_ring += a_step;
+          b_ring += b_step;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
+        }
+      }
     }
-    if (sc.on && lane == 0) {
+    if (kStall && sc.on && lane == 0) {
       long long* o = p.stall + 1 + blockIdx.x * 16;
       o[6] = clock64() - st_begin; o[7] = st_tempty; o[8] = st_full;
     }
   } else {
     // ============================================================ TMA producer
-    const uint32_t a_s0 = smem_u32(smem_a), b_s0 = smem_u32(smem_b), r_s0 = smem_u32(smem_r);
+    const uint32_t a_s0 = smem_u32(smem_a), b_s0 = smem_u32(smem_b);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), afull0 = smem_u32(afull_bar),
-                   aempty0 = smem_u32(aempty_bar), rfull0 = smem_u32(rfull_bar), rempty0 = smem_u32(rempty_bar);
+                   aempty0 = smem_u32(aempty_bar);
     int stage = 0, astage = 0;
     uint32_t phase = 0, aphase = 0;
     uint32_t a_dst = a_s0, b_dst = b_s0;
     int tile_iter = 0;
-    StallClock sc{p.stall != nullptr, 0};
+    StallClock<kStall> sc{kStall && p.stall != nullptr, 0};
     long long st_empty = 0, st_rempty = 0;
-    const long long st_begin = sc.on ? clock64() : 0;
-    if (p.b_resident && lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.n_tiles * p.num_kb * b_stage_bytes));
-      for (int nt = 0; nt < p.n_tiles; ++nt)
-        for (int kb = 0; kb < p.num_kb; ++kb)
-          tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
+    const long long st_begin = kStall && sc.on ? clock64() : 0;
+    if ((p.b_resident || kRes == 1) && lane == 0) {
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? p.n_tiles * p.num_kb * b_stage_bytes : 0) +
+                                                            (kRes == 1 ? kIdentBytes : 0)));
+      if (p.b_resident)
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
+      if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
     }
     const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
     const uint32_t halo_tx = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
@@ -470,22 +534,6 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
       const int n_coord = n_tile * p.BN;
-      if (has_res) {
-        // residual tile of THIS tile into set tile_iter % kResSets, as soon as the epilogue released it
-        const int rset = tile_iter % kResSets;
-        sc.start();
-        mbar_wait_a(rempty0 + rset * 8, ((tile_iter / kResSets) & 1) ^ 1, p.watchdog, 600 + rset);
-        sc.stop(st_rempty);
-        if (elect_one()) {
-          mbar_expect_tx_a(rfull0 + rset * 8, static_cast<uint32_t>(nslab * p.a_bytes));
-          for (int rs = 0; rs < nslab; ++rs) {
-            const uint32_t dst = r_s0 + static_cast<uint32_t>((rset * 2 + rs) * kSlabBytes);
-            if (p.patch) tma_load_4d_a(dst, &tmR, rfull0 + rset * 8, n_coord + rs * kSlab, c1, c2, c3);
-            else tma_load_2d_a(dst, &tmR, rfull0 + rset * 8, n_coord + rs * kSlab, c1);
-          }
-        }
-        __syncwarp();
-      }
       if (p.halo) {
         const int taps = p.kh * p.kw;
         for (int hb = 0; hb < p.cin_blocks; ++hb) {
@@ -498,7 +546,6 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
                           c2 - p.ph, c3);
           }
           __syncwarp();
-          if (lane == 0) trace_event(p.trace, 30, tile_iter);             // halo load issued
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
           if (!p.b_resident) {
             int kcoord = hb * kBK;                                        // K coordinate of (tap 0, hb)
@@ -544,8 +591,25 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_dst = a_s0; b_dst = b_s0; }
         }
       }
+      if constexpr (kRes == 1) {
+        // the tile's residual slabs ride the same ring as extra A blocks (host: one k-block per stage, no halo)
+        for (int rs = 0; rs < nslab; ++rs) {
+          sc.start();
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
+          sc.stop(st_empty);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(p.a_bytes));
+            if (p.patch) tma_load_4d_a(a_dst, &tmR, full0 + stage * 8, n_coord + rs * kSlab, c1, c2, c3);
+            else tma_load_2d_a(a_dst, &tmR, full0 + stage * 8, n_coord + rs * kSlab, c1);
+          }
+          __syncwarp();
+          a_dst += kAStageBytes;
+          b_dst += static_cast<uint32_t>(b_stage_bytes);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; a_dst = a_s0; b_dst = b_s0; }
+        }
+      }
     }
-    if (sc.on && lane == 0) {
+    if (kStall && sc.on && lane == 0) {
       long long* o = p.stall + 1 + blockIdx.x * 16;
       o[9] = clock64() - st_begin; o[10] = st_empty; o[11] = st_rempty;
     }

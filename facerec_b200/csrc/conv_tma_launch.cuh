@@ -1,0 +1,33 @@
+// Instantiation + dispatch of conv_tma_kernel over (residual kind, activation kind).  Included by one translation
+// unit per (element type, stall accounting) pair so the variants compile in parallel.
+#pragma once
+#include "conv_tma.cuh"
+
+namespace frb {
+
+template <bool kBF16, bool kStall, int kRes, int kAct>
+static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a, const CUtensorMap& tmA,
+                                       const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
+  auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, kTmaThreads, smem, st>>>(a, tmA, tmB, tmO, tmR, tmI);
+  return cudaSuccess;
+}
+
+// res: ConvRes of the launch; act: 0 per-channel slope, 1 ReLU, 2 linear (an upsampled residual always takes 0)
+template <bool kBF16, bool kStall>
+static cudaError_t conv_tma_dispatch(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                     const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
+  if (res == RES_POST_ACT_UPSAMPLE) return conv_tma_launch_one<kBF16, kStall, 2, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  if (res == RES_PRE_ACT) {
+    if (act == 1) return conv_tma_launch_one<kBF16, kStall, 1, 1>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+    if (act == 2) return conv_tma_launch_one<kBF16, kStall, 1, 2>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+    return conv_tma_launch_one<kBF16, kStall, 1, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  }
+  if (act == 1) return conv_tma_launch_one<kBF16, kStall, 0, 1>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  if (act == 2) return conv_tma_launch_one<kBF16, kStall, 0, 2>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  return conv_tma_launch_one<kBF16, kStall, 0, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+}
+
+}  // namespace frb

@@ -190,13 +190,22 @@ static void pick_patch(int B, int Ho, int Wo, int sw, int sh, int& bw, int& bh, 
   }
 }
 
+// (multiplier, shift) with n / d == (umulhi(n, mul) + n) >> shift for every 0 <= n < 2^31 (Granlund-Montgomery)
+static void fastdiv_make(int d, uint32_t* fd) {
+  uint32_t l = 0;
+  while ((1ull << l) < static_cast<uint64_t>(d)) ++l;
+  fd[0] = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - static_cast<uint64_t>(d))) / static_cast<uint64_t>(d) + 1);
+  fd[1] = l;
+}
+
 static bool tma_path_ok(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io) {
   if (ctx->force_gather || io.out_mode != OUT_16BIT) return false;
   const bool linear = L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0;
   if (!linear && (L.Cin % kBK) != 0) return false;                 // taps are fetched as whole 64-channel blocks
   if (!linear && io.res_mode == RES_POST_ACT_UPSAMPLE) return false;
   if (L.n_tiles > 1 && (L.BN % kSlab) != 0) return false;          // store slabs must not spill into the next N tile
-  if (io.res_mode == RES_PRE_ACT && L.BN > 2 * kSlab) return false;  // two residual slabs are staged per tile
+  if (io.res_mode == RES_PRE_ACT && ((io.res_ld % 8) != 0 || (reinterpret_cast<uintptr_t>(io.res) & 15) != 0))
+    return false;                                                    // the residual is a TMA operand too
   return true;
 }
 
@@ -215,16 +224,28 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.cin_blocks = (L.Cin + kBK - 1) / kBK;
   a.num_kb = L.kh * L.kw * a.cin_blocks;
   a.BN = L.BN; a.n_tiles = L.n_tiles;
+  fastdiv_make(a.n_tiles, a.fd_n);
   a.bias = L.d_bias; a.slope = L.d_slope; a.act_kind = L.act_kind;
   a.res_mode = io.res_mode; a.res = io.res; a.res_ld = io.res_ld; a.rH = io.rH; a.rW = io.rW;
-  a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M);
+  a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M); a.B = io.B;
   a.watchdog = ctx->wd_dev;
-  a.trace = ctx->trace_mode == 1 ? ctx->trace_dev : nullptr;
-  a.stall = ctx->trace_mode == 2 ? ctx->trace_dev : nullptr;
+  a.stall = ctx->trace_mode != 0 ? ctx->trace_dev : nullptr;
   if (ctx->trace_dev) cudaMemsetAsync(ctx->trace_dev, 0, 8, stream);
 
-  CUtensorMap tmA, tmO, tmR;
-  memset(&tmR, 0, sizeof(tmR));
+  CUtensorMap tmA, tmO, tmR, tmI;
+  memset(&tmI, 0, sizeof(tmI));
+  if (io.res_mode == RES_PRE_ACT) {
+    // 64 x 64 identity in the activation type: B operand of the MMAs that add the residual into the accumulator
+    void*& ident = ctx->d_ident[ctx->use_bf16 ? 1 : 0];
+    if (ident == nullptr) {
+      std::vector<uint16_t> h(64 * 64, 0);
+      for (int i = 0; i < 64; ++i) h[i * 64 + i] = ctx->use_bf16 ? 0x3F80 : 0x3C00;   // 1.0
+      FRB_CUDA(ctx, cudaMalloc(&ident, h.size() * 2));
+      FRB_CUDA(ctx, cudaMemcpy(ident, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    }
+    int irc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64);
+    if (irc != FRB_OK) return irc;
+  }
   int rc;
   long long m_tiles;
   if (linear) {
@@ -233,13 +254,14 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     a.bw = kBM; a.bh = 1; a.bb = 1; a.tiles_w = 1; a.tiles_h = 1;
     if ((rc = encode_2d(ctx, &tmA, io.in, L.Cin, M, static_cast<uint64_t>(io.in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
     if ((rc = encode_2d(ctx, &tmO, io.out, L.Cout, M, static_cast<uint64_t>(io.out_ld) * 2, kSlab, kBM)) != FRB_OK) return rc;
+    tmR = tmO;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_2d(ctx, &tmR, io.res, L.Cout, M, static_cast<uint64_t>(io.res_ld) * 2, kSlab, kBM)) != FRB_OK)
       return rc;
   } else {
     pick_patch(io.B, Ho, Wo, L.sw, L.sh, a.bw, a.bh, a.bb);
     // halo mode: stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide x 16 tall)
-    if (!L.special && ctx->halo_mode && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
+    if (!L.special && ctx->halo_mode && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
       const double eff_patch = static_cast<double>(io.B) * Ho * Wo /
                                (128.0 * ((Wo + a.bw - 1) / a.bw) * ((Ho + a.bh - 1) / a.bh) * ((io.B + a.bb - 1) / a.bb));
       const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
@@ -267,20 +289,24 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.halo_w, a.halo_h, 1, 1, 1)) != FRB_OK) return rc;
     } else if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
     if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
+    tmR = tmO;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_patch(ctx, &tmR, io.res, L.Cout, Wo, Ho, io.B, io.res_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK)
       return rc;
   }
   if (m_tiles * L.n_tiles > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv: too many tiles");
   a.total_tiles = static_cast<int>(m_tiles * L.n_tiles);
+  fastdiv_make(a.tiles_w, a.fd_w);
+  fastdiv_make(a.tiles_h, a.fd_h);
 
   // small weight matrices (the bandwidth-bound early layers) stay resident in shared memory for the whole kernel
   const int w_bytes = L.n_tiles * a.num_kb * L.BN * 128;
   a.b_resident = w_bytes <= kResidentWeightBytes ? 1 : 0;
-  const int base_fixed = kOutBufs * kSlabBytes + (io.res_mode == RES_PRE_ACT ? kResSets * 2 * kSlabBytes : 0) +
-                         (a.b_resident ? w_bytes : 0) + (4 * kMaxStages + 10) * 8 + 2048 + 1024;
+  const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? w_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
+                         (4 * kMaxStages + 18) * 8 + 2048 + 1024;
   const int total_budget = 226 * 1024 - base_fixed;
-  a.kbps = (!a.halo && a.num_kb >= 2 && ctx->kbps2) ? 2 : 1;
+  // residual slabs ride the ring as single extra A blocks: one k-block per stage then
+  a.kbps = (!a.halo && a.num_kb >= 2 && ctx->kbps2 && io.res_mode != RES_PRE_ACT) ? 2 : 1;
   int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? 1 : a.kbps) * L.BN * 128);
   if (a.kbps == 2 && total_budget / stage_bytes < 3) {   // too few double stages to cover the TMA latency
     a.kbps = 1;
@@ -298,13 +324,12 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
   if (smem > 227 * 1024) return set_err(ctx, FRB_ERR_INVALID, "conv: shared-memory plan does not fit (%zu bytes)", smem);
   const int grid = std::min(a.total_tiles, ctx->num_sms);
-  if (ctx->use_bf16) {
-    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tma_kernel<true><<<grid, kTmaThreads, smem, stream>>>(a, tmA, L.tmB, tmO, tmR);
-  } else {
-    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tma_kernel<false><<<grid, kTmaThreads, smem, stream>>>(a, tmA, L.tmB, tmO, tmR);
-  }
+  const int act = io.res_mode == RES_POST_ACT_UPSAMPLE ? 0 : L.act_kind;
+  cudaError_t le;
+  if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  else if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  else le = conv_tma_launch_f16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  FRB_CUDA(ctx, le);
   ctx->launches++;
   return check_last(ctx, "conv_tma_kernel launch");
 }
@@ -416,6 +441,8 @@ int frb_destroy(frb_ctx* ctx) {
   ctx->nets.clear();
   if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
   for (cudaEvent_t e : ctx->lt_events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->d_ident[i]) cudaFree(ctx->d_ident[i]);
   if (ctx->trace_dev) cudaFree(ctx->trace_dev);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);

@@ -28,11 +28,12 @@ struct frb_ctx {
   int use_bf16 = 0;            // 0: fp16 activations/weights (default), 1: bf16
   int bn_cap = 256;            // largest conv tile N the planner may pick
   int force_gather = 0;        // debugging: never use the TMA A path
+  void* d_ident[2] = {nullptr, nullptr};   // 64 x 64 identity (fp16, bf16): B operand of the residual MMAs
   int kbps2 = 1;               // two 64-wide k-blocks per pipeline stage (0: one)
   int layer_times = 0;         // FRB_OPT_LAYER_TIMES: run_plan brackets every op with events (debug only)
   std::vector<cudaEvent_t> lt_events;      // lt_events[0] = before the first op, [i+1] = after op i
   std::vector<double> lt_info;             // 6 doubles per op: kind, M, N, K, flop, (ms filled by frb_debug_layer_times)
-  int trace_mode = 0;          // FRB_OPT_TRACE value: 1 timeline of CTA 0, 2 per-CTA stall counters
+  int trace_mode = 0;          // FRB_OPT_TRACE: per-CTA stall counters of the conv_tma roles
   long long* trace_dev = nullptr;  // FRB_OPT_TRACE: device buffer for conv_tma timeline records
   int halo_mode = 0;           // 1: stride-1 k x k convs read A from one halo tile per channel block (measured: not faster
                                //    than one box per tap, the small-N layers are bound by MMA operand reads, see profiles/)

@@ -54,8 +54,8 @@ enum frb_option {
   FRB_OPT_BN_CAP = 1,      /* largest conv tile N (multiple of 16, <= 256)                           */
   FRB_OPT_FORCE_GATHER = 2,/* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
   FRB_OPT_HALO = 3,        /* 0: one TMA box per filter tap instead of one halo tile per channel block    */
-  FRB_OPT_TRACE = 4,       /* 1: CTA 0 of every conv_tma launch records a (event, tile, clock) timeline;
-                              2: every CTA writes 16 stall-cycle counters at h_out[1 + 16 * cta] instead      */
+  FRB_OPT_TRACE = 4,       /* non-zero: every CTA of a conv_tma launch writes 16 stall-cycle counters of its
+                              three roles at h_out[1 + 16 * cta] (read with frb_debug_trace)                 */
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
   FRB_OPT_LAYER_TIMES = 6  /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
 };
@@ -67,7 +67,7 @@ int frb_destroy(frb_ctx* ctx);
 const char* frb_last_error(frb_ctx* ctx); /* valid until the next call on ctx */
 int frb_set_option(frb_ctx* ctx, int option, int value);
 long long frb_launch_count(frb_ctx* ctx); /* kernels launched through ctx so far */
-/* FRB_OPT_TRACE: copies the timeline of the LAST conv_tma launch: h_out[0] = record count, then (event, tile, clock) triples */
+/* FRB_OPT_TRACE: copies the stall counters of the LAST conv_tma launch (1 + 3 * max_records words, 16 per CTA from h_out[1]) */
 int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records);
 /* FRB_OPT_LAYER_TIMES: per-op rows (kind 0 conv / 1 dwconv / 2 maxpool / 3 avgpool / 4 l2norm, M, N, K, flop, ms) of the
  * LAST network forward; returns the row count (<= max_rows) or a negative frb_status. */
