@@ -1,0 +1,157 @@
+// Probe: how much does concurrent shared-memory / TMEM traffic slow tcgen05.mma down?  Every SM runs one CTA whose
+// thread 0 issues `iters` x 4 MMAs (M = 128, kind::f16) over rotating A / B buffers; meanwhile, by `mode` bits:
+//   1: a producer warp streams 16 KB TMA boxes into a 4-slot ring (what the conv kernel's A fills do)
+//   2: four warps stream 16-byte shared-memory stores over a 16 KB slab (the epilogue's staging writes)
+//   4: four warps loop tcgen05.ld 32x32b.x16 over the accumulator (the epilogue's TMEM reads)
+// Operands are either constant 1.0 or pseudo-random fp16 (bit toggling = tensor-core power).
+// Output: cycles per MMA (issue to completion of all), per N and mode, CTA 0.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o gpurun_out/umma_contention tools/umma_contention_probe.cu -lcuda
+#include <cstdio>
+#include <vector>
+#include "../facerec_b200/csrc/common.cuh"
+using namespace frb;
+
+constexpr int kThreads = 32 * 10;   // warp 0 MMA, 1-4 stores, 5-8 tmem loads, 9 TMA
+
+__global__ void __launch_bounds__(kThreads, 1)
+contention_kernel(const __grid_constant__ CUtensorMap tm, int N, int iters, int mode, int random_data, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sA = smem;                       // 4 x 16 KB
+  uint8_t* sB = sA + 4 * 16384;             // 2 x 32 KB
+  uint8_t* sT = sB + 2 * 32768;             // TMA ring: 4 x 16 KB
+  uint8_t* sS = sT + 4 * 16384;             // store slab: 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + 16384);   // [0] done, [1] scratch commit, [2..5] ring
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 8);
+  volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (4 * 16384 + 2 * 32768) / 4; i += blockDim.x) {
+    uint32_t v = 0x3c003c00u;                       // fp16 (1.0, 1.0)
+    if (random_data) {                              // two pseudo-random fp16 values in (-2, 2): realistic operand toggling
+      uint32_t h = (i + 1) * 2654435761u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      v = (h & 0x83FF83FFu) | 0x3C003C00u | ((h >> 7) & 0x04000400u) ^ 0u;
+      v &= 0xBFFFBFFFu;
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
+  if (threadIdx.x == 0) *stop = 0;
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, N, 0);
+      const uint64_t a = make_sw128_kmajor_desc(smem_u32(sA));
+      const uint64_t b = make_sw128_kmajor_desc(smem_u32(sB));
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint64_t ao = static_cast<uint64_t>((it & 3) * (16384 >> 4)), bo = static_cast<uint64_t>((it & 1) * (32768 >> 4));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(tmem, a + ao + k4 * 2, b + bo + k4 * 2, idesc, 1u);
+        tc_commit(&bars[1]);
+      }
+      tc_commit(&bars[0]);
+      mbar_wait(&bars[0], 0, nullptr, 0);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0) out[0] = t1 - t0;
+      *stop = 1;
+    }
+  } else if (warp <= 4) {
+    if (mode & 2) {
+      const uint4 v = make_uint4(1, 2, 3, 4);
+      int i = 0;
+      while (!*stop) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(sS + (((warp - 1) * 32 + lane) * 128 + ((j ^ (lane & 7)) << 4))) = v;
+        ++i;
+      }
+    }
+  } else if (warp <= 8) {
+    if (mode & 4) {
+      uint32_t acc = 0;
+      while (!*stop) {
+        uint32_t v[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld16(tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256 + c * 16, v);   // columns the MMAs do not write
+          tc_wait_ld();
+          acc += v[0];
+        }
+      }
+      if (acc == 0x12345678u) out[1] = acc;
+    }
+  } else {
+    if ((mode & 1) && lane == 0) {
+      uint32_t ph[4] = {0, 0, 0, 0};
+      for (int s = 0; s < 4; ++s) {
+        mbar_arrive_expect_tx(&bars[2 + s], 16384);
+        tma_load_2d(sT + s * 16384, &tm, &bars[2 + s], 0, (blockIdx.x * 4 + s) * 128);
+      }
+      int s = 0, row = 0;
+      while (!*stop) {
+        mbar_wait(&bars[2 + s], ph[s], nullptr, 0);
+        ph[s] ^= 1;
+        mbar_arrive_expect_tx(&bars[2 + s], 16384);
+        row = (row + 128) & 0xFFFF;
+        tma_load_2d(sT + s * 16384, &tm, &bars[2 + s], 0, row);
+        s = (s + 1) & 3;
+      }
+      for (int k = 0; k < 4; ++k) mbar_wait(&bars[2 + k], ph[k], nullptr, 0);   // drain before the CTA exits
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc_dyn(tmem, 512); }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 2;
+  EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+  const size_t rows = 1 << 17;   // 128 K rows x 128 B = 16 MB (L2-resident source)
+  void* src;
+  cudaMalloc(&src, rows * 128);
+  cudaMemset(src, 0, rows * 128);
+  CUtensorMap tm;
+  cuuint64_t gd[2] = {64, rows}, gs[1] = {128};
+  cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, src, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 3;
+  long long* d;
+  cudaMalloc(&d, 16);
+  const size_t smem = 4 * 16384 + 2 * 32768 + 4 * 16384 + 16384 + 256 + 1024;
+  cudaFuncSetAttribute(contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int iters = 200000;   // ~50 ms per launch: long enough for the power limiter to act
+  for (int grid : {1, 148})
+    for (int N : {64, 128, 256})
+      for (int mode : {0, 7})
+      for (int rnd : {0, 1}) {
+        contention_kernel<<<grid, kThreads, smem>>>(tm, N, iters, mode, rnd, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+        long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("grid %3d N %3d mode %d (tma %d sts %d tmem-ld %d) random data %d: %6.1f cycles per MMA\n", grid, N, mode, mode & 1, (mode >> 1) & 1,
+               (mode >> 2) & 1, rnd, static_cast<double>(h[0]) / (iters * 4.0));
+      }
+  return 0;
+}
