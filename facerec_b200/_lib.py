@@ -62,6 +62,17 @@ SIGNATURES = {
     "frb_linkage_complete": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "frb_knn_topk": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "frb_knn_vote": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "frb_format_f32_json": (C.c_longlong, [_vp, _i, _vp, C.c_longlong]),
+    "frb_sort_create": (_vp, [_i, _i, C.c_double]),
+    "frb_sort_destroy": (None, [_vp]),
+    "frb_sort_update": (_i, [_vp, _vp, _i, C.c_longlong, _vp]),
+    "frb_sort_has_valid_tracker": (_i, [_vp, C.c_longlong]),
+    "frb_sort_get_detection_bbox": (_i, [_vp, C.c_longlong, _vp]),
+    "frb_sort_kill_trackers": (None, [_vp]),
+    "frb_sort_nan_removed": (_i, [_vp]),
+    "frb_sort_pop_expired": (_i, [_vp, C.c_longlong, C.c_longlong]),
+    "frb_sort_expired_info": (_i, [_vp, _i, _vp, _vp]),
+    "frb_sort_expired_boxes": (_i, [_vp, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "libfacerec_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "conv_tma_stall.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
-           "linkage.cu", "api.cu"]
+           "linkage.cu", "sort.cu", "jsonfmt.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",

@@ -77,8 +77,23 @@ class B200RetinaFaceDetector:
             if arr.ndim != 4 or arr.shape[3] != 3 or arr.dtype != np.uint8:
                 raise ValueError("frames must be [B,H,W,3] uint8")
             dev = self._to_device(arr)
-        cand, keep, nkeep, count = self.detect_device(dev)
-        cand, keep, nkeep, count = cand.cpu().numpy(), keep.cpu().numpy(), nkeep.cpu().numpy(), count.cpu().numpy()
+        return self.detect_batch_collect(self.detect_batch_launch(dev))
+
+    def detect_batch_launch(self, frames_dev: torch.Tensor):
+        """Enqueue the whole detection pass for a GPU-resident batch plus the device-to-host copies of its results
+        (pinned buffers) and return a handle; nothing here waits for the GPU."""
+        outs = self.detect_device(frames_dev)
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+        for h, t in zip(host, outs):
+            h.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev, outs          # `outs` keeps the device tensors alive until the copies have run
+
+    def detect_batch_collect(self, handle) -> List[np.ndarray]:
+        host, ev, _ = handle
+        ev.synchronize()
+        cand, keep, nkeep, count = (h.numpy() for h in host)
         if (count > self.max_candidates).any():
             raise RuntimeError(f"more than max_candidates={self.max_candidates} priors passed the score threshold "
                                f"(max {int(count.max())}); raise max_candidates (<= 1024) or the threshold")

@@ -87,7 +87,31 @@ class B200FaceNet:
                   (rects[:, 4] > 0) & (rects[:, 1] + rects[:, 3] <= W_) & (rects[:, 2] + rects[:, 4] <= H))
             if not ok.all():
                 raise ValueError(f"crop rectangle outside its frame or empty: {rects[~ok][0].tolist()}")
-        return self.embed_device(frames_u8, torch.from_numpy(rects).to(self.device)).cpu().numpy()
+        return self.embed_collect(self.embed_boxes_launch(frames_u8, rects, checked=True))
+
+    def embed_boxes_launch(self, frames_u8: torch.Tensor, rects: np.ndarray, checked: bool = False):
+        """Enqueue crop + resize + InceptionResnetV1 for `rects` and the copy of the embeddings to pinned host memory;
+        returns a handle for embed_collect.  Nothing here waits for the GPU."""
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 5)
+        if not checked and len(rects):
+            B, H, W_, _ = frames_u8.shape
+            ok = ((rects[:, 0] >= 0) & (rects[:, 0] < B) & (rects[:, 1] >= 0) & (rects[:, 2] >= 0) & (rects[:, 3] > 0) &
+                  (rects[:, 4] > 0) & (rects[:, 1] + rects[:, 3] <= W_) & (rects[:, 2] + rects[:, 4] <= H))
+            if not ok.all():
+                raise ValueError(f"crop rectangle outside its frame or empty: {rects[~ok][0].tolist()}")
+        rp = torch.empty(rects.shape, dtype=torch.int32, pin_memory=True)
+        rp.numpy()[...] = rects
+        emb = self.embed_device(frames_u8, rp.to(self.device, non_blocking=True))
+        host = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+        host.copy_(emb, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev, (emb, rp)
+
+    def embed_collect(self, handle) -> np.ndarray:
+        host, ev, _ = handle
+        ev.synchronize()
+        return host.numpy()
 
     def embeddings(self, images: Sequence[np.ndarray]) -> np.ndarray:
         """images: list of HxWx3 uint8 crops of any size -> float32 [len, 512]."""

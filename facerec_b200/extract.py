@@ -85,6 +85,16 @@ class VideoSource:
             frame = self.cv2.resize(frame, (self.width, self.height))
         return self.cv2.cvtColor(frame, self.cv2.COLOR_BGR2RGB)
 
+    def read_into(self, dst: np.ndarray) -> bool:
+        """Same as read(), but the colour conversion writes straight into `dst` (a slot of a pinned batch buffer)."""
+        ok, frame = self.cap.read()
+        if not ok:
+            return False
+        if self.width != self.video_w or self.height != self.video_h:
+            frame = self.cv2.resize(frame, (self.width, self.height))
+        self.cv2.cvtColor(frame, self.cv2.COLOR_BGR2RGB, dst=dst)
+        return True
+
     def close(self):
         self.cap.release()
 
@@ -118,6 +128,28 @@ class SyntheticSource:
         pass
 
 
+class PreloadedSource:
+    """Frames of a synthetic clip generated up front (stands in for a decoder that keeps up): benchmarks only."""
+
+    def __init__(self, movie_id: int, n_frames: int, width: int, height: int, seed: int = 1234):
+        from . import synth
+        self.movie_id, self.n_frames, self.width, self.height = movie_id, n_frames, width, height
+        self.frames = [synth.frame(seed, i, height, width) for i in range(n_frames)]
+        self._pos = 0
+
+    def seek(self, index: int):
+        self._pos = index
+
+    def read(self) -> Optional[np.ndarray]:
+        if self._pos >= self.n_frames:
+            return None
+        self._pos += 1
+        return self.frames[self._pos - 1]
+
+    def close(self):
+        pass
+
+
 # --------------------------------------------------------------------------------------- writers
 def trajectory_record(trk, max_w: int, max_h: int) -> dict:
     """One trajectories.jsonl line (facerec/extract.py:55-80); `index`/`movie_id` are added by merge_shards.py."""
@@ -133,12 +165,32 @@ def dump_line(obj, file):
     file.write("\n")
 
 
+_FMT_BUF = None
+
+
+def format_f32_json(vec: np.ndarray) -> str:
+    """json.dumps(vec.tolist(), separators=(",", ":")) for a float32 vector, formatted in libfacerec_b200.so
+    (csrc/jsonfmt.cu): ~10 us instead of ~150 us per 512-float embedding."""
+    global _FMT_BUF
+    import ctypes as C
+    from . import _lib
+    v = np.ascontiguousarray(vec, dtype=np.float32).reshape(-1)
+    cap = 2 + 33 * len(v)
+    if _FMT_BUF is None or len(_FMT_BUF) < cap:
+        _FMT_BUF = C.create_string_buffer(max(cap, 2 + 33 * 512))
+    n = _lib.load_library().frb_format_f32_json(v.ctypes.data, len(v), _FMT_BUF, len(_FMT_BUF))
+    if n < 0:
+        raise RuntimeError("frb_format_f32_json failed")
+    return C.string_at(_FMT_BUF, n).decode("ascii")
+
+
 def feature_line(rec: dict, vec, keys) -> str:
     """One features.jsonl line (facerec/extract.py:186-195), byte-identical to
     json.dump({...,"embeddings": {k: vec for k in keys},...}, separators=(",", ":")): the 512-float vector is
-    serialised once and spliced in under every key instead of being encoded len(keys) times."""
+    serialised once and spliced in under every key instead of being encoded len(keys) times.  `vec` is a list of
+    Python floats or a float32 numpy vector (then the text comes from format_f32_json)."""
     d = lambda o: json.dumps(o, indent=None, separators=(",", ":"))
-    v = d(vec)
+    v = format_f32_json(vec) if isinstance(vec, np.ndarray) else d(vec)
     emb = ",".join(d(k) + ":" + v for k in keys)
     return ('{"frame":' + d(rec["frame"]) + ',"tag":' + d(rec["tag"]) + ',"embeddings":{' + emb + '},"box":' + d(rec["box"]) +
             ',"keypoints":' + d(rec["keypoints"]) + ',"w":' + d(rec["w"]) + ',"h":' + d(rec["h"]) + "}")
@@ -227,8 +279,8 @@ class Extractor:
             counts["boxes"] += n
             counts["frames"] += int(n > 0)
 
-        def flush(pending, batches):
-            """Embed every pending face from the GPU-resident batch it came from, then write the lines in order."""
+        def flush_sync(pending, batches):
+            """Embedders without the launch / collect split (test doubles): embed and write in one go."""
             for bid, frames_d in batches.items():
                 idx = [i for i, p in enumerate(pending) if p[0][0] == bid]
                 if not idx:
@@ -244,52 +296,118 @@ class Extractor:
                 features_file.write("\n")
             pending.clear()
 
+        def embed_launch(pending, batches):
+            """Enqueue the embeddings of every pending face from the GPU-resident batch it came from (no waiting)."""
+            handles = []
+            for bid, frames_d in batches.items():
+                idx = [i for i, p in enumerate(pending) if p[0][0] == bid]
+                if not idx:
+                    continue
+                rects = np.array([[pending[i][0][1], *pending[i][1]] for i in idx], np.int32)
+                if ((rects[:, 3] <= 0) | (rects[:, 4] <= 0)).any():
+                    raise ValueError("empty face crop (the reference would fail in cv2.resize here)")
+                handles.append((idx, self.embedder.embed_boxes_launch(frames_d, rects)))
+            return handles
+
+        def write_features(pending, handles):
+            """Wait for the launched embeddings, then write the feature lines in order."""
+            for idx, h in handles:
+                emb = self.embedder.embed_collect(h)
+                for i, e in zip(idx, emb):
+                    pending[i][2]["embeddings"] = e if e.dtype == np.float32 else e.tolist()
+            for _, _, rec in pending:
+                features_file.write(feature_line(rec, rec["embeddings"], self.emb_keys))
+                features_file.write("\n")
+            pending.clear()
+
         # Frame ingest (SURVEY 8 f4): a reader thread decodes the next batches into (pinned) host buffers while the
         # GPU works on the current one; cv2 releases the GIL while decoding.
         import queue
         import threading
         n_to_read = end_overlap - beg
-        batches_q: "queue.Queue" = queue.Queue(maxsize=2)
+        batches_q: "queue.Queue" = queue.Queue(maxsize=1)
         pin = device.type == "cuda"
+
+        # Ring of batch buffers the frames are decoded INTO (no np.stack, no pin_memory copy: both were a full extra
+        # pass over 400 MB per 64 x 1080p batch and capped the extractor at ~400 frames/s).  6 slots: one being filled,
+        # one queued, two in flight on the GPU, one being walked by the host, one still referenced by the
+        # min_trajectory-delayed frames of the batch before it.
+        ring = [torch.empty((self.batch, d_height, d_width, 3), dtype=torch.uint8, pin_memory=pin) for _ in range(6)]
+        into = getattr(src, "read_into", None)
 
         def reader():
             left = n_to_read
+            k = 0
             try:
                 while left > 0:
-                    frames = []
-                    while len(frames) < self.batch and len(frames) < left:
-                        fr = src.read()
-                        if fr is None:
-                            left = len(frames)
-                            break
-                        frames.append(fr)
-                    if not frames:
+                    t = ring[k % len(ring)]
+                    arr = t.numpy()
+                    n = 0
+                    while n < self.batch and n < left:
+                        if into is not None:
+                            if not into(arr[n]):
+                                left = n
+                                break
+                        else:
+                            fr = src.read()
+                            if fr is None:
+                                left = n
+                                break
+                            arr[n] = fr
+                        n += 1
+                    if n == 0:
                         break
-                    arr = np.stack(frames)
-                    t = torch.from_numpy(arr)
-                    batches_q.put((arr, t.pin_memory() if pin else t))
-                    left -= len(frames)
+                    batches_q.put((arr[:n], t[:n]))
+                    left -= n
+                    k += 1
             except BaseException as e:      # noqa: BLE001 - surface decode errors on the consumer side
                 batches_q.put(e)
                 return
             batches_q.put(None)
 
         threading.Thread(target=reader, daemon=True).start()
-        f = beg
-        batch_id = 0
-        while True:
+        from collections import deque
+        from time import perf_counter
+        tm = self.timing = {"wait_reader": 0.0, "launch": 0.0, "wait_detect": 0.0, "host_loop": 0.0, "wait_embed_write": 0.0}
+        staged_embedder = hasattr(self.embedder, "embed_boxes_launch")
+        staged_detector = hasattr(self.detector, "detect_batch_launch")
+        inflight = deque()            # batches whose detection (and scene statistics) are running on the GPU
+        state = {"next_frame": beg, "next_batch": 0, "done": False}
+
+        def launch_next():
+            """Take the next decoded batch, start its upload, detection and scene statistics; never waits for the GPU."""
+            if state["done"]:
+                return
+            t0 = perf_counter()
             item = batches_q.get()
+            t1 = perf_counter()
+            tm["wait_reader"] += t1 - t0
             if item is None:
-                break
+                state["done"] = True
+                return
             if isinstance(item, BaseException):
                 raise item
             frames_h, frames_t = item
-            frames = frames_h
             frames_d = frames_t.to(device, non_blocking=True)
-            dets = self.detector.detect_batch_raw(frames_d)
-            cuts = scene.update_batch(frames_d) if gpu_scene else None
+            det_h = self.detector.detect_batch_launch(frames_d) if staged_detector else None
+            scene_h = scene.stats_launch(frames_d) if gpu_scene else None
+            inflight.append((state["next_batch"], state["next_frame"], frames_h, frames_d, det_h, scene_h))
+            state["next_batch"] += 1
+            state["next_frame"] += len(frames_h)
+            tm["launch"] += perf_counter() - t1
+
+        # Two batches in flight: while the host walks batch k (SORT, scheduling, JSON) the GPU runs detection of
+        # batch k+1; embed(k) is enqueued before detect(k+2), so waiting for it never waits for a whole detection pass.
+        launch_next()
+        launch_next()
+        while inflight:
+            batch_id, f, frames_h, frames_d, det_h, scene_h = inflight.popleft()
+            t0 = perf_counter()
+            dets = self.detector.detect_batch_collect(det_h) if staged_detector else self.detector.detect_batch_raw(frames_d)
+            cuts = scene.update_collect(scene_h) if gpu_scene else None
+            t1 = perf_counter()
             pending = []
-            for b in range(len(frames)):
+            for b in range(len(frames_h)):
                 fi = f + b
                 cut = cuts[b] if gpu_scene else scene.update(frames_h[b])
                 faces = self.detector.format(dets[b])
@@ -309,18 +427,30 @@ class Extractor:
                     if fd["index"] % self.save_every == 0:
                         schedule(fd, pending)
             recent[batch_id] = frames_d
-            flush(pending, recent)
+            t2 = perf_counter()
+            if staged_embedder:
+                handles = embed_launch(pending, recent)
+                launch_next()
+                write_features(pending, handles)
+            else:
+                flush_sync(pending, recent)
+                launch_next()
+            t3 = perf_counter()
+            tm["wait_detect"] += t1 - t0
+            tm["host_loop"] += t2 - t1
+            tm["wait_embed_write"] += t3 - t2
             oldest = min([fd["slot"][0] for fd in buf], default=batch_id)
             for k in [k for k in recent if k < oldest]:
                 del recent[k]
-            f += len(frames)
-            batch_id += 1
 
         pending = []
         for fd in buf:
             if fd["index"] % self.save_every == 0:
                 schedule(fd, pending)
-        flush(pending, recent)
+        if staged_embedder:
+            write_features(pending, embed_launch(pending, recent))
+        else:
+            flush_sync(pending, recent)
         for trk in tracker.pop_expired(expiry_age=0):
             dump_line(trajectory_record(trk, d_width, d_height), trajectories_file)
             counts["traj"] += 1
@@ -373,7 +503,7 @@ def main(argv=None):
     from ._lib import Context
     from .detector import B200RetinaFaceDetector
     from .embedder import B200FaceNet
-    from .sort import Sort
+    from .sort import NativeSort as Sort   # csrc/sort.cu; the numpy restatement in sort.py stays as the cross-check
     ctx = Context(args.device)
     detector = B200RetinaFaceDetector(args.min_face_size, args.backbone, seed=args.weight_seed,
                                       threshold=args.face_threshold, ctx=ctx)

@@ -86,6 +86,11 @@ class B200SceneChangeDetector:
         self._torch = torch
 
     def update_batch(self, frames):
+        return self.update_collect(self.stats_launch(frames))
+
+    def stats_launch(self, frames):
+        """Enqueue the pixel statistics of a batch (and their copies to pinned host memory); batches must be launched
+        in clip order, the kernel reads the previous batch's last frame / CDF."""
         torch = self._torch
         from ._lib import ptr, current_stream
         B, H, W, _ = frames.shape
@@ -96,9 +101,23 @@ class B200SceneChangeDetector:
         self.ctx.check(self.ctx.lib.frb_scene_stats(self.ctx.handle, ptr(frames), B, H, W, int(self.crop), ptr(self.prev_frame),
                                                     ptr(self.prev_cdf), ptr(hist), ptr(cdf), ptr(sums), current_stream()),
                        "frb_scene_stats")
-        h = hist.cpu().numpy().astype(np.float64)
-        c = cdf.cpu().numpy()
-        s = sums.cpu().numpy()
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (hist, cdf, sums)]
+        for hbuf, t in zip(host, (hist, cdf, sums)):
+            hbuf.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.prev_frame = frames[B - 1].clone()
+        self.prev_cdf = cdf[B - 1].clone()
+        return host, ev, (hist, cdf, sums)
+
+    def update_collect(self, handle):
+        """The scalar recurrences and the threshold cascade over a launched batch: one bool per frame."""
+        host, ev, _ = handle
+        ev.synchronize()
+        h = host[0].numpy().astype(np.float64)
+        c = host[1].numpy()
+        s = host[2].numpy()
+        B = h.shape[0]
         n = h[0].sum()
         cuts = []
         for b in range(B):
@@ -115,6 +134,4 @@ class B200SceneChangeDetector:
                 if sdmafd_eq is not None and adfv_eq is not None:
                     cut = SceneChangeDetector.check(mafd, mafd_eq, sdmafd_eq, adfv_eq)
             cuts.append(bool(cut))
-        self.prev_frame = frames[B - 1].clone()
-        self.prev_cdf = cdf[B - 1].clone()
         return cuts

@@ -213,3 +213,76 @@ class Sort:
                     trk.history = trk.history[:len(trk) - trk.time_since_update]
                     out.append(trk)
         return out
+
+
+class _ExpiredTrack:
+    """What pop_expired hands to the trajectory writer: first_frame + history of (box, is_posterior)."""
+
+    def __init__(self, first_frame, boxes, detected):
+        self.first_frame = first_frame
+        self.history = [(boxes[i], bool(detected[i])) for i in range(len(boxes))]
+
+    def __len__(self):
+        return len(self.history)
+
+
+class NativeSort:
+    """Same interface as `Sort`, state and arithmetic in libfacerec_b200.so (csrc/sort.cu): the per-frame
+    host cost drops from ~1 ms of numpy calls to a few microseconds.  Ids, validity and integer boxes are identical to
+    `Sort`; float boxes agree to ~1e-12 (LAPACK / BLAS vs. plain loops in the 4x4 inverse and 8x8 products)."""
+
+    def __init__(self, max_age: int = 5, min_hits: int = 3, iou_threshold: float = 0.5):
+        import ctypes as C
+        from . import _lib
+        self._C = C
+        self.lib = _lib.load_library()
+        self.max_age, self.min_hits, self.iou_threshold = max_age, min_hits, iou_threshold
+        self.handle = C.c_void_p(self.lib.frb_sort_create(max_age, min_hits, float(iou_threshold)))
+        if not self.handle.value:
+            raise RuntimeError("frb_sort_create failed")
+        self._nan_seen = 0
+
+    def __del__(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.frb_sort_destroy(self.handle)
+            self.handle = self._C.c_void_p()
+
+    def update(self, detections: np.ndarray, frame: int):
+        det = np.ascontiguousarray(detections, dtype=np.float64).reshape(-1, 5)
+        ids = np.empty(len(det), np.int64)
+        rc = self.lib.frb_sort_update(self.handle, det.ctypes.data, len(det), int(frame), ids.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"frb_sort_update failed ({rc})")
+        nan = self.lib.frb_sort_nan_removed(self.handle)
+        for _ in range(nan - self._nan_seen):
+            print("WARNING: Removed tracker with NaN predictions.")
+        self._nan_seen = nan
+        return ids
+
+    def has_valid_tracker(self, detection_id) -> bool:
+        r = self.lib.frb_sort_has_valid_tracker(self.handle, int(detection_id))
+        assert r >= 0, "Tried to access non-existent tracker <" + str(detection_id) + ">"
+        return bool(r)
+
+    def get_detection_bbox(self, detection_id):
+        box = np.empty(4, np.float64)
+        rc = self.lib.frb_sort_get_detection_bbox(self.handle, int(detection_id), box.ctypes.data)
+        assert rc == 0, "Tried to access non-existent tracker!"
+        return box
+
+    def kill_trackers(self):
+        self.lib.frb_sort_kill_trackers(self.handle)
+
+    def pop_expired(self, expiry_age: int, current_frame: Optional[int] = None):
+        C = self._C
+        n = self.lib.frb_sort_pop_expired(self.handle, int(expiry_age),
+                                          int(current_frame) if current_frame is not None else 2 ** 63 - 1)
+        out = []
+        for i in range(n):
+            first, ln = C.c_longlong(), C.c_int()
+            self.lib.frb_sort_expired_info(self.handle, i, C.byref(first), C.byref(ln))
+            boxes = np.empty((ln.value, 4), np.float64)
+            det = np.empty(ln.value, np.uint8)
+            self.lib.frb_sort_expired_boxes(self.handle, i, boxes.ctypes.data, det.ctypes.data)
+            out.append(_ExpiredTrack(first.value, boxes, det))
+        return out

@@ -189,6 +189,30 @@ int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
 int frb_knn_vote(frb_ctx* ctx, const int32_t* d_idx, const int32_t* d_label_idx /*[M] in [0,n_classes)*/, int Q, int k,
                  int n_classes, float* d_proba /*[Q,n_classes]*/, void* stream);
 
+/* ---- host-side SORT tracker ---------------------------------------------------
+ * Replaces: class Sort / KalmanBoxTracker, facerec/sort.py:82-378, as driven by facerec/extract.py:312-327.
+ * No GPU work and no frb_ctx: plain host state.  Detections are rows x1,y1,x2,y2,score (float64, as the reference
+ * builds them at extract.py:319); ids are the running global detection ids of Sort.update (sort.py:251-253). */
+typedef struct frb_sort frb_sort;
+frb_sort* frb_sort_create(int max_age, int min_hits, double iou_threshold);           /* sort.py:204-222 */
+void frb_sort_destroy(frb_sort* s);
+int frb_sort_update(frb_sort* s, const double* h_dets /*[n,5]*/, int n, long long frame, long long* h_ids /*[n]*/);
+int frb_sort_has_valid_tracker(frb_sort* s, long long detection_id);                  /* 1 / 0, -1: unknown id; sort.py:297-308 */
+int frb_sort_get_detection_bbox(frb_sort* s, long long detection_id, double* h_box4); /* sort.py:321-331 */
+void frb_sort_kill_trackers(frb_sort* s);                                             /* sort.py:333-336 */
+int frb_sort_nan_removed(frb_sort* s);  /* trackers dropped for NaN predictions so far (the reference prints a warning each) */
+/* sort.py:338-378: forget trackers idle for >= expiry_age frames (current_frame = LLONG_MAX: all); returns how many
+ * VALID trajectories were popped; read them with the two calls below before the next pop. */
+int frb_sort_pop_expired(frb_sort* s, long long expiry_age, long long current_frame);
+int frb_sort_expired_info(frb_sort* s, int i, long long* first_frame, int* len);
+int frb_sort_expired_boxes(frb_sort* s, int i, double* h_boxes /*[len,4]*/, unsigned char* h_detected /*[len]*/);
+
+/* ---- features.jsonl writer helper ---------------------------------------------
+ * JSON text of a float32 vector, byte-identical to Python's json.dumps([float(x) for x in v], separators=(",",":"))
+ * (the "embeddings" value of a features line, facerec/extract.py:186-195).  Needs cap >= 2 + 33 * n; returns the
+ * text length (no terminator) or -1. */
+long long frb_format_f32_json(const float* h_v, int n, char* h_out, long long cap);
+
 #ifdef __cplusplus
 }
 #endif

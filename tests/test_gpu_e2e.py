@@ -72,7 +72,7 @@ def test_extract_cluster_classify_pipeline(ctx, tmp_path):
     from facerec_b200 import extract, cluster, classify_knn, formats
     from facerec_b200.detector import B200RetinaFaceDetector
     from facerec_b200.embedder import B200FaceNet
-    from facerec_b200.sort import Sort
+    from facerec_b200.sort import NativeSort as Sort
     det = B200RetinaFaceDetector(20, "mnet025", ctx=ctx)
     emb = B200FaceNet(ctx=ctx)
     out = str(tmp_path / "data")

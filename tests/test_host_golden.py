@@ -33,16 +33,16 @@ def test_bbox_float_to_int_matches_reference():
         assert tuple(r[1:]) == crop_rect([t[0], t[1], t[2] - t[0], t[3] - t[1]], 640, 360, 16)
 
 
-def _run_sort(script):
+def _run_sort(script, native=False):
     from facerec_b200 import sort as S
     S.KalmanBoxTracker.count = 0
-    mt = S.Sort(max_age=5, min_hits=3, iou_threshold=0.5)
+    mt = (S.NativeSort if native else S.Sort)(max_age=5, min_hits=3, iou_threshold=0.5)
     out = {"ids": [], "queries": [], "expired": []}
     buf = []
 
     def dump(trks):
         for t in trks:
-            out["expired"].append({"first_frame": t.first_frame, "initial_hits": t.initial_hits,
+            out["expired"].append({"first_frame": t.first_frame, "initial_hits": getattr(t, "initial_hits", None),
                                    "boxes": [[float(v) for v in b] for b, _ in t.history],
                                    "detected": [bool(d) for _, d in t.history]})
 
@@ -78,6 +78,25 @@ def test_sort_matches_reference_runs():
             assert g["box"] == r["box"]                      # bit-identical Kalman posterior
         for g, r in zip(got["expired"], ref["expired"]):
             assert g == r
+
+
+def test_native_sort_matches_reference_runs():
+    """csrc/sort.cu behind the C ABI: ids, validity and every integer box the extractor derives are identical to the
+    reference runs; float boxes agree to 1e-9 (plain loops vs. LAPACK / BLAS in the 4x4 inverse and 8x8 products)."""
+    from facerec_b200.pipeline import bbox_float_to_int
+    for run in _gold("sort_runs.json"):
+        got = _run_sort(run["script"], native=True)
+        ref = run["result"]
+        assert got["ids"] == ref["ids"]
+        assert len(got["queries"]) == len(ref["queries"]) and len(got["expired"]) == len(ref["expired"])
+        for g, r in zip(got["queries"], ref["queries"]):
+            assert (g["frame"], g["det"], g["valid"]) == (r["frame"], r["det"], r["valid"])
+            np.testing.assert_allclose(g["box"], r["box"], rtol=1e-9, atol=1e-9)
+            assert bbox_float_to_int(g["box"], 640, 360) == bbox_float_to_int(r["box"], 640, 360)
+        for g, r in zip(got["expired"], ref["expired"]):
+            assert g["first_frame"] == r["first_frame"] and g["detected"] == r["detected"]
+            np.testing.assert_allclose(np.array(g["boxes"]), np.array(r["boxes"]), rtol=1e-9, atol=1e-9)
+            assert [bbox_float_to_int(b, 640, 360) for b in g["boxes"]] == [bbox_float_to_int(b, 640, 360) for b in r["boxes"]]
 
 
 def test_scene_detector_matches_reference():
@@ -171,8 +190,8 @@ class _FakeEmbedder:
         return np.stack([self.mg.fake_embedding(frames[f, y:y + h, x:x + w].numpy()) for f, x, y, w, h in rects])
 
 
-@pytest.mark.parametrize("n_shards,shard_i,batch", [(1, 0, 64), (1, 0, 7), (2, 0, 5), (2, 1, 16)])
-def test_extractor_reproduces_reference_process_video(tmp_path, n_shards, shard_i, batch):
+@pytest.mark.parametrize("n_shards,shard_i,batch,native", [(1, 0, 64, False), (1, 0, 7, True), (2, 0, 5, False), (2, 1, 16, True)])
+def test_extractor_reproduces_reference_process_video(tmp_path, n_shards, shard_i, batch, native):
     """facerec/extract.py:199-369 was run verbatim (fake detector / embedder) by tools/make_golden.py on a lossless
     clip; the batched extractor must write byte-identical features / trajectories / scene_changes files."""
     from facerec_b200 import extract, sort as S
@@ -180,7 +199,7 @@ def test_extractor_reproduces_reference_process_video(tmp_path, n_shards, shard_
     clip = str(tmp_path / "100002-fixture.avi")
     mg.write_fixture_clip(clip, mg.fixture_clip_frames())
     S.KalmanBoxTracker.count = 0
-    ex = extract.Extractor(_FakeDetector(mg), _FakeEmbedder(mg), S.Sort(5, 3, 0.5), str(tmp_path / "out"), n_shards, shard_i,
+    ex = extract.Extractor(_FakeDetector(mg), _FakeEmbedder(mg), (S.NativeSort if native else S.Sort)(5, 3, 0.5), str(tmp_path / "out"), n_shards, shard_i,
                            save_every=5, min_trajectory=3, max_trajectory_age=5, save_images=False, batch=batch)
     with contextlib.redirect_stdout(io.StringIO()):
         ex.process_video(clip)
@@ -211,3 +230,21 @@ def test_feature_line_is_byte_identical_to_json_dump():
     json.dump({"frame": rec["frame"], "tag": rec["tag"], "embeddings": {k: vec for k in FACENET_KEYS}, "box": rec["box"],
                "keypoints": rec["keypoints"], "w": 640, "h": 360}, ref, indent=None, separators=(",", ":"))
     assert feature_line(rec, vec, FACENET_KEYS) == ref.getvalue()
+
+
+def test_native_float_json_is_byte_identical_to_json_dumps():
+    """csrc/jsonfmt.cu: the text of a float32 vector equals json.dumps(v.tolist()) over 30 decades of magnitude and the
+    repr layout boundaries (1e-4, 1e16, zeros, subnormals, float32 max)."""
+    from facerec_b200.extract import format_f32_json, feature_line, FACENET_KEYS
+    rng = np.random.RandomState(0)
+    v = np.concatenate([rng.standard_normal(2000).astype(np.float32) * np.float32(s)
+                        for s in (1, 1e-3, 1e-6, 1e-12, 1e5, 1e10, 1e18, 1e-30, 1e30)] +
+                       [np.array([0.0, -0.0, 1.0, -1.0, 0.5, 1e16, 9.999999e15, 1e-4, 9.9999e-5, 123456.0, 1e22, 3.4028235e38,
+                                  1.4e-45, 1e-5, 2.0 ** 24, 16777217.0, 0.1, 100.0, 1e15], np.float32)])
+    assert format_f32_json(v) == json.dumps(v.tolist(), separators=(",", ":"))
+    e = rng.standard_normal(512).astype(np.float32)
+    e /= np.linalg.norm(e)
+    rec = {"frame": 35, "tag": "100001:35:10_20_110_140", "box": [10, 20, 110, 140],
+           "keypoints": {"left_eye": (30, 50), "right_eye": (70, 51), "nose": (50, 80), "mouth_left": (35, 110), "mouth_right": (66, 111)},
+           "w": 640, "h": 360}
+    assert feature_line(rec, e, FACENET_KEYS) == feature_line(rec, e.tolist(), FACENET_KEYS)

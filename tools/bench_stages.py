@@ -29,7 +29,8 @@ def ev_time(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--extract-frames", type=int, default=480)
+    ap.add_argument("--extract-frames", type=int, default=960)
+    ap.add_argument("--extract-frames-1080p", type=int, default=768)
     a = ap.parse_args()
     ctx = _lib.Context(0)
     out = {}
@@ -51,24 +52,11 @@ def main():
     from facerec_b200 import extract
     from facerec_b200.detector import B200RetinaFaceDetector
     from facerec_b200.embedder import B200FaceNet
-    from facerec_b200.sort import Sort
+    from facerec_b200.sort import NativeSort as Sort
     emb = B200FaceNet(ctx=ctx)
-    class Preloaded:
-        """Frames generated before the clock starts (stands in for a decoder that keeps up)."""
-        def __init__(self, n, W_, H_):
-            self.movie_id, self.n_frames, self.width, self.height = 100001, n, W_, H_
-            self.frames = [synth.frame(1234, i, H_, W_) for i in range(n)]
-            self.pos = 0
-        def seek(self, i): self.pos = i
-        def read(self):
-            if self.pos >= self.n_frames: return None
-            self.pos += 1
-            return self.frames[self.pos - 1]
-        def close(self): pass
-
-    for backbone, (W_, H_), n in (("mnet025", (640, 360), a.extract_frames), ("r50", (1920, 1080), 384)):
+    for backbone, (W_, H_), n in (("mnet025", (640, 360), a.extract_frames), ("r50", (1920, 1080), a.extract_frames_1080p)):
         det = B200RetinaFaceDetector(20, backbone, ctx=ctx)
-        src = Preloaded(n, W_, H_)
+        src = extract.PreloadedSource(100001, n, W_, H_)
         with tempfile.TemporaryDirectory() as tmp:
             for rep in range(2):            # first pass warms plans / arena; the second is the measurement
                 src.seek(0)
@@ -77,7 +65,8 @@ def main():
                 with contextlib.redirect_stdout(io.StringIO()):
                     counts = ex.process_video(src)
                 dt = time.time() - t0
-        out[f"extract_{backbone}_{W_}x{H_}"] = {"n_frames": n, "seconds": dt, "frames_per_s": n / dt, **counts}
+        out[f"extract_{backbone}_{W_}x{H_}"] = {"n_frames": n, "seconds": dt, "frames_per_s": n / dt, **counts,
+                                                "main_thread_seconds": {k: round(v, 4) for k, v in ex.timing.items()}}
     print(json.dumps(out))
 
 
