@@ -335,6 +335,9 @@ class Extractor:
         ring = [torch.empty((self.batch, d_height, d_width, 3), dtype=torch.uint8, pin_memory=pin) for _ in range(6)]
         into = getattr(src, "read_into", None)
 
+        from concurrent.futures import ThreadPoolExecutor
+        copiers = ThreadPoolExecutor(max_workers=4)     # numpy releases the GIL while it copies a frame into its slot
+
         def reader():
             left = n_to_read
             k = 0
@@ -343,6 +346,7 @@ class Extractor:
                     t = ring[k % len(ring)]
                     arr = t.numpy()
                     n = 0
+                    copies = []
                     while n < self.batch and n < left:
                         if into is not None:
                             if not into(arr[n]):
@@ -353,8 +357,10 @@ class Extractor:
                             if fr is None:
                                 left = n
                                 break
-                            arr[n] = fr
+                            copies.append(copiers.submit(np.copyto, arr[n], fr))
                         n += 1
+                    for c in copies:
+                        c.result()
                     if n == 0:
                         break
                     batches_q.put((arr[:n], t[:n]))
