@@ -324,6 +324,8 @@ def run_b200(a):
     ms_total, ms_e2e = float(t[0]), float(t[1])
     if rank == 0:
         clocks = sampler.window(t0, t1) if sampler else {}
+        if sampler and not clocks.get("samples"):      # nvidia-smi delivered nothing inside the first region: use both
+            clocks = sampler.window(t0, t2)
         if sampler:
             sampler.stop()
         peak, peak_src = load_peaks()

@@ -260,8 +260,10 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       return rc;
   } else {
     pick_patch(io.B, Ho, Wo, L.sw, L.sh, a.bw, a.bh, a.bb);
-    // halo mode: stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide x 16 tall)
-    if (!L.special && ctx->halo_mode && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
+    // halo mode (FRB_OPT_HALO): stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide
+    // x 16 tall), including the s2d stem's 4 x 1 window conv.  Off by default: measured slower everywhere, even for
+    // column filters whose shifted descriptors stay swizzle-atom aligned (stem 3.09 vs 2.39 ms inside the forward).
+    if (ctx->halo_mode > 0 && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
       const double eff_patch = static_cast<double>(io.B) * Ho * Wo /
                                (128.0 * ((Wo + a.bw - 1) / a.bw) * ((Ho + a.bh - 1) / a.bh) * ((io.B + a.bb - 1) / a.bb));
       const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
@@ -282,7 +284,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       // overlapping windows: dim0 = 64 elements starting at s2d pixel w, dim1 steps one s2d pixel (16 elements)
       const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)io.H, (uint64_t)io.B};
       const uint64_t str[3] = {32, (uint64_t)io.W * 32, (uint64_t)io.H * io.W * 32};
-      const uint32_t box[4] = {64, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bb};
+      const uint32_t box[4] = {64, (uint32_t)(a.halo ? a.halo_w : a.bw), (uint32_t)(a.halo ? a.halo_h : a.bh), (uint32_t)a.bb};
       const uint32_t est[4] = {1, 1, 1, 1};
       if ((rc = encode_nd(ctx, &tmA, io.in, 4, dims, str, box, est)) != FRB_OK) return rc;
     } else if (a.halo) {

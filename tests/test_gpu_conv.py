@@ -50,6 +50,8 @@ CASES = [
     (1, 32, 64, 128, 128, 1, 7, (1, 1), (0, 3), 1, 0, False),    # halo mode with a 1x7 filter (14 x 16 halo)
     (1, 32, 48, 256, 256, 3, 3, (1, 1), (1, 1), 1, 0, False),    # halo mode: 4 channel blocks x 9 taps, BN = 256
     (3, 270, 480, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),    # ResNet layer1 conv2 at full 1080p/4 size
+    (2, 40, 44, 128, 96, 7, 1, (1, 1), (3, 0), 1, 0, False),     # column filter: aligned halo tiles by default, 2 channel blocks
+    (1, 50, 40, 64, 64, 4, 1, (1, 1), (2, 0), 2, 0, False),      # 4 x 1 window (the shape of the s2d stem), resident weights
 ]
 
 

@@ -11,7 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shape", action="append", default=[])
 ap.add_argument("--res", action="store_true")
 ap.add_argument("--bn-cap", type=int, default=256)
-ap.add_argument("--halo", action="store_true")
+ap.add_argument("--halo", type=int, default=0, help="FRB_OPT_HALO value")
 a = ap.parse_args()
 for shape in a.shape:
     B, H, W, Cin, Cout, k, s, p = (int(v) for v in shape.split(","))
@@ -21,15 +21,14 @@ for shape in a.shape:
     res = torch.randn(B, Ho, Wo, Cout, device="cuda").half() if a.res else None
     plain = _lib.Context(0)
     plain.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
-    if a.halo:
-        plain.set_option(_lib.FRB_OPT_HALO, 1)
-    _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=5)
+    plain.set_option(_lib.FRB_OPT_HALO, a.halo)
+    ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)       # clocks up
+    _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)
     plain.close()
     ctx = _lib.Context(0)
     ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
     ctx.set_option(_lib.FRB_OPT_TRACE, 2)
-    if a.halo:
-        ctx.set_option(_lib.FRB_OPT_HALO, 1)
+    ctx.set_option(_lib.FRB_OPT_HALO, a.halo)
     _, ms = ops.conv2d(ctx, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=1)
     buf = np.zeros(1 + 3 * 4000, np.int64)
     ctx.check(ctx.lib.frb_debug_trace(ctx.handle, buf.ctypes.data, 4000), "trace")

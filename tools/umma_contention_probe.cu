@@ -102,7 +102,9 @@ contention_kernel(const __grid_constant__ CUtensorMap tm, int N, int iters, int 
         tma_load_2d(sT + s * 16384, &tm, &bars[2 + s], 0, (blockIdx.x * 4 + s) * 128);
       }
       int s = 0, row = 0;
+      long long boxes = 0;
       while (!*stop) {
+        ++boxes;
         mbar_wait(&bars[2 + s], ph[s], nullptr, 0);
         ph[s] ^= 1;
         mbar_arrive_expect_tx(&bars[2 + s], 16384);
@@ -111,6 +113,7 @@ contention_kernel(const __grid_constant__ CUtensorMap tm, int N, int iters, int 
         s = (s + 1) & 3;
       }
       for (int k = 0; k < 4; ++k) mbar_wait(&bars[2 + k], ph[k], nullptr, 0);   // drain before the CTA exits
+      if (blockIdx.x == 0) out[1] = boxes;
     }
   }
   tc_fence_before();
@@ -143,15 +146,17 @@ int main() {
   const int iters = 200000;   // ~50 ms per launch: long enough for the power limiter to act
   for (int grid : {1, 148})
     for (int N : {64, 128, 256})
-      for (int mode : {0, 7})
-      for (int rnd : {0, 1}) {
+      for (int mode : {0, 1, 7})
+      for (int rnd : {1}) {
+        cudaMemset(d, 0, 16);
         contention_kernel<<<grid, kThreads, smem>>>(tm, N, iters, mode, rnd, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
-        long long h[2];
+        long long h[2] = {0, 0};
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("grid %3d N %3d mode %d (tma %d sts %d tmem-ld %d) random data %d: %6.1f cycles per MMA\n", grid, N, mode, mode & 1, (mode >> 1) & 1,
-               (mode >> 2) & 1, rnd, static_cast<double>(h[0]) / (iters * 4.0));
+        const double tma_bpc = (mode & 1) ? static_cast<double>(h[1]) * 16384.0 / static_cast<double>(h[0]) : 0.0;
+        printf("grid %3d N %3d mode %d (tma %d sts %d tmem-ld %d) random data %d: %6.1f cycles per MMA, TMA fill %5.1f B/clk\n", grid, N, mode, mode & 1, (mode >> 1) & 1,
+               (mode >> 2) & 1, rnd, static_cast<double>(h[0]) / (iters * 4.0), tma_bpc); if (0) printf("%d%d%d%d%d%f",grid, N, mode, mode & 1, rnd, static_cast<double>(h[0]) / (iters * 4.0));
       }
   return 0;
 }
