@@ -82,15 +82,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* w
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }
-// Pull one box into L2 only (no shared-memory destination, no barrier): a hint issued tiles ahead of the loads that use it
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* desc, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* desc, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* desc, uint64_t* bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -130,13 +121,6 @@ __device__ __forceinline__ void tma_store_wait() {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// 32 bytes through the read-only path without an L1 line (streamed once): one full sector per thread and request
-__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* v) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(p));
 }
 
 // ----------------------------------------------------------------- cp.async

@@ -23,10 +23,11 @@
 // the A descriptor of tap (r, s) at pixel (r, s) of that tile: 8-row groups are 8 consecutive pixels of a halo
 // row (bw = 8), the stride between groups is the halo row pitch.  The 128-byte swizzle is a function of the
 // shared-memory ADDRESS (tools/umma_shift_probe.cu: any 128-byte row offset and any group stride read back
-// exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.
+// exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.  Optional
+// (FRB_OPT_HALO) and off by default: it measures 5-9 % SLOWER than one box per tap on every layer tried.
 //
-// Warp roles (448 threads, 14 warps = at most 4 per scheduler so the epilogue may hold 128 registers without
-// spilling — with ~227 KB of shared memory there is no L1 left and a spill is an L2 round trip): warps 0-11 are
+// Warp roles (448 threads, 14 warps = at most 4 per scheduler, i.e. up to 128 registers per thread: with ~227 KB
+// of shared memory there is no L1 left and a spill is an L2 round trip): warps 0-11 are
 // three independent epilogue groups (one warp per TMEM lane quarter each), 12 the MMA issuer + TMEM allocator,
 // 13 the TMA producer.  Profiles that led here: profiles/r01_stall_counters_v6.txt (16 warps sharing every slab
 // behind two 512-thread barriers: 2 000 cycles per slab, the MMA issuer waiting for a TMEM buffer 78 % of the time).
@@ -44,7 +45,7 @@ constexpr int kSlab = 64;                  // epilogue / store granularity in ou
 constexpr int kSlabBytes = kBM * kSlab * 2;
 constexpr int kEpiGroups = kEpiWarps / 4;  // independent epilogue groups: one warp per TMEM lane quarter each
 constexpr int kGroupThreads = 128;
-constexpr int kOutBufs = kEpiGroups;       // one staging slab per group (doubles as its residual slab)
+constexpr int kOutBufs = kEpiGroups;       // one staging slab per group
 constexpr int kMaxAcc = 4;                 // TMEM accumulator buffers: 4 for BN <= 128, else 2
 constexpr int kResidentWeightBytes = 80 * 1024;
 constexpr int kIdentBytes = 64 * 128;      // identity B operand of the residual MMAs
