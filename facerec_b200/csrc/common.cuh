@@ -248,6 +248,20 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking look at a barrier phase (never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int* wd, int code) {
   if (mbar_try_wait_a(bar, parity)) return;
   const long long t0 = clock64();

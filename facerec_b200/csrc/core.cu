@@ -230,6 +230,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.Ho = Ho; a.Wo = Wo; a.M = static_cast<int>(M); a.B = io.B;
   a.watchdog = ctx->wd_dev;
   a.stall = ctx->trace_mode != 0 ? ctx->trace_dev : nullptr;
+  a.skip_loads = ctx->skip_loads;
   if (ctx->trace_dev) cudaMemsetAsync(ctx->trace_dev, 0, 8, stream);
 
   CUtensorMap tmA, tmO, tmR, tmI;
@@ -322,7 +323,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   }
   const int fixed = base_fixed + a.a_stages * a.halo_bytes;
   const int budget = 226 * 1024 - fixed;
-  a.stages = stage_bytes > 0 ? std::max(2, std::min(kMaxStages, budget / stage_bytes)) : 2;
+  a.stages = stage_bytes > 0 ? std::max(2, std::min(std::min(kMaxStages, ctx->max_stages), budget / stage_bytes)) : 2;
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
   if (smem > 227 * 1024) return set_err(ctx, FRB_ERR_INVALID, "conv: shared-memory plan does not fit (%zu bytes)", smem);
   const int grid = std::min(a.total_tiles, ctx->num_sms);
@@ -466,6 +467,8 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_HALO: ctx->halo_mode = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_KBPS2: ctx->kbps2 = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;
     case FRB_OPT_TRACE:
       ctx->trace_mode = value;
       if (value && ctx->trace_dev == nullptr) {

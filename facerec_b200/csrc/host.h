@@ -29,6 +29,8 @@ struct frb_ctx {
   int bn_cap = 256;            // largest conv tile N the planner may pick
   int force_gather = 0;        // debugging: never use the TMA A path
   void* d_ident[2] = {nullptr, nullptr};   // 64 x 64 identity (fp16, bf16): B operand of the residual MMAs
+  int skip_loads = 0;          // FRB_OPT_SKIP_LOADS: timing experiment, results are garbage
+  int max_stages = 64;         // FRB_OPT_MAX_STAGES: cap on the conv_tma stage ring (latency-sensitivity experiments)
   int kbps2 = 1;               // two 64-wide k-blocks per pipeline stage (0: one)
   int layer_times = 0;         // FRB_OPT_LAYER_TIMES: run_plan brackets every op with events (debug only)
   std::vector<cudaEvent_t> lt_events;      // lt_events[0] = before the first op, [i+1] = after op i

@@ -66,7 +66,6 @@ void predict(Tracker& t) {                    // facerec/sort.py:143-161
 // inverse of a 4x4 by LU with partial pivoting (what numpy.linalg.inv does through gesv)
 void inv4(const double S[4][4], double out[4][4]) {
   double a[4][4], b[4][4];
-  int piv[4];
   memcpy(a, S, sizeof(a));
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) b[i][j] = i == j ? 1.0 : 0.0;
@@ -74,7 +73,6 @@ void inv4(const double S[4][4], double out[4][4]) {
     int p = k;
     for (int i = k + 1; i < 4; ++i)
       if (std::fabs(a[i][k]) > std::fabs(a[p][k])) p = i;
-    piv[k] = p;
     if (p != k) {
       for (int j = 0; j < 4; ++j) { std::swap(a[k][j], a[p][j]); std::swap(b[k][j], b[p][j]); }
     }
@@ -93,7 +91,6 @@ void inv4(const double S[4][4], double out[4][4]) {
     }
   }
   memcpy(out, b, sizeof(b));
-  (void)piv;
 }
 
 void update(Tracker& t, const double* bbox) { // facerec/sort.py:125-141 + filterpy KalmanFilter.update
@@ -132,7 +129,8 @@ void update(Tracker& t, const double* bbox) { // facerec/sort.py:125-141 + filte
       for (int k = 0; k < 4; ++k) kr += K[i][k] * kR[k] * K[j][k];
       Pn[i][j] = s + kr;
     }
-  memcpy(t.P, Pn, sizeof(Pn));
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 8; ++j) t.P[i][j] = Pn[i][j];
   std::array<double, 4> b;
   t.state_box(b.data());
   t.boxes.back() = b;                          // the posterior replaces this frame's prediction

@@ -58,7 +58,9 @@ enum frb_option {
   FRB_OPT_TRACE = 4,       /* non-zero: every CTA of a conv_tma launch writes 16 stall-cycle counters of its
                               three roles at h_out[1 + 16 * cta] (read with frb_debug_trace)                 */
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
-  FRB_OPT_LAYER_TIMES = 6  /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
+  FRB_OPT_LAYER_TIMES = 6, /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
+  FRB_OPT_MAX_STAGES = 7,  /* cap on the conv_tma stage ring depth (>= 2; experiments)                          */
+  FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

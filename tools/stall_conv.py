@@ -12,6 +12,9 @@ ap.add_argument("--shape", action="append", default=[])
 ap.add_argument("--res", action="store_true")
 ap.add_argument("--bn-cap", type=int, default=256)
 ap.add_argument("--halo", type=int, default=0, help="FRB_OPT_HALO value")
+ap.add_argument("--max-stages", type=int, default=64)
+ap.add_argument("--kbps1", action="store_true")
+ap.add_argument("--skip-loads", action="store_true")
 a = ap.parse_args()
 for shape in a.shape:
     B, H, W, Cin, Cout, k, s, p = (int(v) for v in shape.split(","))
@@ -22,6 +25,9 @@ for shape in a.shape:
     plain = _lib.Context(0)
     plain.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
     plain.set_option(_lib.FRB_OPT_HALO, a.halo)
+    plain.set_option(_lib.FRB_OPT_MAX_STAGES, a.max_stages)
+    plain.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
+    plain.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
     ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)       # clocks up
     _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)
     plain.close()
@@ -29,6 +35,9 @@ for shape in a.shape:
     ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
     ctx.set_option(_lib.FRB_OPT_TRACE, 2)
     ctx.set_option(_lib.FRB_OPT_HALO, a.halo)
+    ctx.set_option(_lib.FRB_OPT_MAX_STAGES, a.max_stages)
+    ctx.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
+    ctx.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
     _, ms = ops.conv2d(ctx, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=1)
     buf = np.zeros(1 + 3 * 4000, np.int64)
     ctx.check(ctx.lib.frb_debug_trace(ctx.handle, buf.ctypes.data, 4000), "trace")
