@@ -15,4 +15,9 @@ schema, the 0.95 threshold, min-size filter and int() keypoints (facerec/detecto
 crop arithmetic (facerec/extract.py:38-53,157-164), SORT (facerec/sort.py), the distance calls
 (facerec/cluster.py:41, facerec/classify_knn.py:212,227: pinned here against scipy / scikit-learn,
 the very libraries the reference calls) and the file formats (facerec/utils/utils.py:90-120).
+One network piece IS pinned to a canonical implementation available here: the ResNet-50 body of the R50
+detector reproduces torchvision.models.resnet50's own layer2/3/4 activations from BN-folded weights
+(tests/test_oracle_cpu.py::test_oracle_r50_backbone_matches_torchvision); NMS is pinned to
+torchvision.ops.nms and the 160x160 resize to cv2.resize.  MobileNet0.25, FPN/SSH/heads and
+InceptionResnetV1 have no installed counterpart and stay unpinned.
 """

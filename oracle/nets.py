@@ -41,6 +41,26 @@ def _conv(x, P, name, stride=1, padding=0, act="none", groups=1):
     return _act(F.conv2d(x, w, b, stride=stride, padding=padding, groups=groups), act)
 
 
+def r50_features(P, x):
+    """torchvision-style ResNet-50 body: outputs of layer2, layer3, layer4 (C = 512 / 1024 / 2048 at
+    stride 8 / 16 / 32).  Pinned against torchvision.models.resnet50 itself in tests/test_oracle_cpu.py."""
+    y = _conv(x, P, "conv1", 2, 3, "relu")
+    y = F.max_pool2d(y, 3, 2, 1)
+    feats = []
+    for l, nb in enumerate(R50_BLOCKS, start=1):
+        for i in range(nb):
+            s = 2 if (i == 0 and l > 1) else 1
+            p = f"layer{l}.{i}"
+            o = _conv(y, P, p + ".conv1", 1, 0, "relu")
+            o = _conv(o, P, p + ".conv2", s, 1, "relu")   # torchvision v1.5: stride on the 3x3
+            o = _conv(o, P, p + ".conv3", 1, 0, "none")
+            idn = _conv(y, P, p + ".down", s, 0, "none") if i == 0 else y
+            y = F.relu(o + idn)
+        if l >= 2:
+            feats.append(y)
+    return feats
+
+
 def retina_forward(P, x, backbone: str):
     """x: [B,3,H,W] float32, BGR minus (104,117,123).  Returns loc [B,P,4], conf logits [B,P,2], landm [B,P,10]."""
     if backbone == "mnet025":
@@ -54,20 +74,7 @@ def retina_forward(P, x, backbone: str):
                 feats.append(y)
     elif backbone == "r50":
         neck = "relu"
-        y = _conv(x, P, "conv1", 2, 3, "relu")
-        y = F.max_pool2d(y, 3, 2, 1)
-        feats = []
-        for l, nb in enumerate(R50_BLOCKS, start=1):
-            for i in range(nb):
-                s = 2 if (i == 0 and l > 1) else 1
-                p = f"layer{l}.{i}"
-                o = _conv(y, P, p + ".conv1", 1, 0, "relu")
-                o = _conv(o, P, p + ".conv2", s, 1, "relu")   # torchvision v1.5: stride on the 3x3
-                o = _conv(o, P, p + ".conv3", 1, 0, "none")
-                idn = _conv(y, P, p + ".down", s, 0, "none") if i == 0 else y
-                y = F.relu(o + idn)
-            if l >= 2:
-                feats.append(y)
+        feats = r50_features(P, x)
     else:
         raise ValueError(backbone)
     o1 = _conv(feats[0], P, "fpn.out1", 1, 0, neck)

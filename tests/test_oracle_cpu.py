@@ -195,3 +195,51 @@ def test_row_sharded_pdist_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0][0]
+
+
+def test_oracle_r50_backbone_matches_torchvision():
+    """Pins the FLOP-heavy part of the detector oracle: the functional ResNet-50 body of oracle/nets.py, fed the
+    BN-folded weights of a torchvision.models.resnet50 with randomised BatchNorm statistics, reproduces torchvision's
+    own layer2 / layer3 / layer4 activations (the RetinaFace-R50 backbone named by north_star)."""
+    import torch
+    import torchvision
+    from facerec_b200.weights import fold_bn
+    from oracle import nets
+    torch.manual_seed(0)
+    m = torchvision.models.resnet50(weights=None).eval()
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+
+    W = {}
+
+    def put(name, conv, bn):
+        w, b = fold_bn(conv.weight.detach().numpy().transpose(0, 2, 3, 1), bn.weight.detach().numpy(), bn.bias.detach().numpy(),
+                       bn.running_mean.numpy(), bn.running_var.numpy(), bn.eps)
+        W[name + ".w"], W[name + ".b"] = w, b
+
+    put("conv1", m.conv1, m.bn1)
+    for l in range(1, 5):
+        for i, blk in enumerate(getattr(m, f"layer{l}")):
+            p = f"layer{l}.{i}"
+            put(p + ".conv1", blk.conv1, blk.bn1)
+            put(p + ".conv2", blk.conv2, blk.bn2)
+            put(p + ".conv3", blk.conv3, blk.bn3)
+            if blk.downsample is not None:
+                put(p + ".down", blk.downsample[0], blk.downsample[1])
+    x = torch.randn(2, 3, 96, 128, generator=g)
+    with torch.no_grad():
+        y = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+        y = m.layer1(y)
+        ref = []
+        for l in (m.layer2, m.layer3, m.layer4):
+            y = l(y)
+            ref.append(y)
+        got = nets.r50_features(nets.params_from_weights(W), x)
+    assert [tuple(t.shape) for t in got] == [(2, 512, 12, 16), (2, 1024, 6, 8), (2, 2048, 3, 4)]
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max())
