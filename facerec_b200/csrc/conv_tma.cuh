@@ -68,6 +68,7 @@ struct ConvTmaArgs {
   int halo_w, halo_h;    // halo tile = (bh + kh - 1) x (bw + kw - 1) pixels of 128 B
   int halo_bytes;        // bytes of one halo buffer (1024-aligned)
   int a_stages;          // halo buffers in the ring
+  int brow;              // halo mode, streamed weights: filter taps per B stage (1, or kw = a whole filter row under one wait)
   int act_kind;          // 0: per-channel slope (general), 1: ReLU everywhere, 2: linear everywhere
   const float* bias;     // [n_tiles*BN]
   const float* slope;    // [n_tiles*BN]
@@ -122,7 +123,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int b_stage_bytes = p.BN * 128;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * p.kbps * kAStageBytes);   // ring (or resident matrix)
-  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages * (p.halo ? 1 : p.kbps)) * b_stage_bytes;
+  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages * (p.halo ? p.brow : p.kbps)) * b_stage_bytes;
   uint8_t* smem_i = smem_o + kOutBufs * kSlabBytes;                                    // 64 x 64 identity (kRes = 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_i + (kRes == 1 ? kIdentBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
@@ -406,7 +407,93 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
       const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
-      if (p.halo) {
+      auto mma4 = [&](uint32_t a, uint32_t b, uint32_t acc0) {          // one 64-channel tap out of a halo tile
+        tc_mma_f16(d_tmem, pack_desc(a, hi_halo), pack_desc(b, hi1024), idesc, acc0);
+        tc_mma_f16(d_tmem, pack_desc(a + 2, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
+        tc_mma_f16(d_tmem, pack_desc(a + 4, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
+        tc_mma_f16(d_tmem, pack_desc(a + 6, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
+      };
+      const uint32_t row_a = static_cast<uint32_t>(p.halo_w) * 8u;             // next halo row (descriptor units of 16 B)
+      if (p.halo && p.b_resident) {
+        // Resident weights: nothing but the halo tile has to arrive, so ALL taps of a channel block go out under one
+        // barrier wait, back to back (an mbarrier wait costs the pipe ~140 cycles, tools/umma_issue_probe.cu; the
+        // per-tap path below pays elect + __syncwarp + bookkeeping between every four MMAs).
+        const uint32_t tap_b = static_cast<uint32_t>(p.cin_blocks) * b_step;   // next tap of the same channel block
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          sc.start();
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          sc.stop(st_full);
+          tc_fence_after();
+          const uint32_t a0 = a_lo0 + static_cast<uint32_t>(astage) * halo_step;          // pixel (0,0) of the halo tile
+          const uint32_t b0 = b_res + static_cast<uint32_t>(cb) * b_step;                  // block (tap 0, cb)
+          const uint32_t acc = cb != 0 ? 1u : 0u;
+          if (elect_one()) {
+            if (p.kh == 3 && p.kw == 3) {
+              mma4(a0, b0, acc);
+              mma4(a0 + 8, b0 + tap_b, 1u);
+              mma4(a0 + 16, b0 + 2 * tap_b, 1u);
+              mma4(a0 + row_a, b0 + 3 * tap_b, 1u);
+              mma4(a0 + row_a + 8, b0 + 4 * tap_b, 1u);
+              mma4(a0 + row_a + 16, b0 + 5 * tap_b, 1u);
+              mma4(a0 + 2 * row_a, b0 + 6 * tap_b, 1u);
+              mma4(a0 + 2 * row_a + 8, b0 + 7 * tap_b, 1u);
+              mma4(a0 + 2 * row_a + 16, b0 + 8 * tap_b, 1u);
+            } else {
+              uint32_t a_row = a0, b_tap = b0, acc_t = acc;
+              for (int tr = 0; tr < p.kh; ++tr, a_row += row_a) {
+                uint32_t a_tap = a_row;
+                for (int ts = 0; ts < p.kw; ++ts, a_tap += 8, b_tap += tap_b) {
+                  mma4(a_tap, b_tap, acc_t);
+                  acc_t = 1u;
+                }
+              }
+            }
+            tc_commit_a(aempty0 + astage * 8);
+            if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+          }
+          __syncwarp();
+          if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+        }
+      } else if (p.halo && p.brow > 1) {
+        // Streamed weights, one filter ROW (kw taps) per B stage: a wait per row instead of a wait per tap
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          sc.start();
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          sc.stop(st_full);
+          uint32_t a_row = a_lo0 + static_cast<uint32_t>(astage) * halo_step;
+          uint32_t acc = cb != 0 ? 1u : 0u;
+          for (int tr = 0; tr < p.kh; ++tr) {
+            sc.start();
+            mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+            sc.stop(st_full);
+            tc_fence_after();
+            if (elect_one()) {
+              if (p.kw == 3) {
+                mma4(a_row, b_ring, acc);
+                mma4(a_row + 8, b_ring + b_step, 1u);
+                mma4(a_row + 16, b_ring + 2 * b_step, 1u);
+              } else {
+                uint32_t acc_t = acc;
+                for (int ts = 0; ts < p.kw; ++ts) {
+                  mma4(a_row + static_cast<uint32_t>(ts) * 8u, b_ring + static_cast<uint32_t>(ts) * b_step, acc_t);
+                  acc_t = 1u;
+                }
+              }
+              tc_commit_a(empty0 + stage * 8);
+              if (tr == p.kh - 1) {
+                tc_commit_a(aempty0 + astage * 8);
+                if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+              }
+            }
+            __syncwarp();
+            acc = 1u;
+            a_row += row_a;
+            b_ring += static_cast<uint32_t>(p.brow) * b_step;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; b_ring = b_lo0; }
+          }
+          if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+        }
+      } else if (p.halo) {
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           sc.start();
           mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
@@ -549,7 +636,24 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           }
           __syncwarp();
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
-          if (!p.b_resident) {
+          if (!p.b_resident && p.brow > 1) {
+            int kcoord = hb * kBK;                                        // K coordinate of (tap 0, hb)
+            for (int tr = 0; tr < p.kh; ++tr) {
+              sc.start();
+              mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
+              sc.stop(st_empty);
+              if (elect_one()) {
+                mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(p.brow * b_stage_bytes));
+                for (int ts = 0; ts < p.brow; ++ts)
+                  tma_load_2d_a(b_dst + static_cast<uint32_t>(ts * b_stage_bytes), &tmB, full0 + stage * 8,
+                                kcoord + ts * p.cin_blocks * kBK, n_coord);
+              }
+              __syncwarp();
+              kcoord += p.brow * p.cin_blocks * kBK;
+              b_dst += static_cast<uint32_t>(p.brow * b_stage_bytes);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; b_dst = b_s0; }
+            }
+          } else if (!p.b_resident) {
             int kcoord = hb * kBK;                                        // K coordinate of (tap 0, hb)
             for (int tap = 0; tap < taps; ++tap) {
               sc.start();

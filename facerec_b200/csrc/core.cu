@@ -261,20 +261,31 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       return rc;
   } else {
     pick_patch(io.B, Ho, Wo, L.sw, L.sh, a.bw, a.bh, a.bb);
-    // halo mode (FRB_OPT_HALO): stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide
-    // x 16 tall), including the s2d stem's 4 x 1 window conv.  Off by default: measured slower everywhere, even for
-    // column filters whose shifted descriptors stay swizzle-atom aligned (stem 3.09 vs 2.39 ms inside the forward).
-    if (ctx->halo_mode > 0 && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
+    // halo mode: stride-1 k x k conv read from one halo tile per 64-channel block (patch fixed at 8 wide x 16 tall),
+    // including the s2d stem's 4 x 1 window conv.  What it buys is fewer barrier waits in the MMA issuer (each costs the
+    // tensor pipe ~140 cycles whatever the ring depth, tools/umma_issue_probe.cu) and k*k-fold less TMA traffic:
+    //  * resident weights: the halo tile is all that has to arrive, every tap of a channel block goes out under ONE
+    //    wait (3x3 64->64: 4 924 -> 2 637 cycles per tile, stem 2.59 -> 1.91 ms inside the forward) - default;
+    //  * streamed weights, a whole filter row of taps per B stage (fits for BN <= 128 with 3-wide filters): one wait
+    //    per row (3x3 128->128: 12 949 -> 7 974 cycles per tile) - default when the 8 x 16 patch wastes little;
+    //  * streamed weights, one tap per stage (BN > 128): a wash, on request only.
+    // FRB_OPT_HALO = 1 forces it wherever it is possible, -1 turns it off.
+    if (ctx->halo_mode >= 0 && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
       const double eff_patch = static_cast<double>(io.B) * Ho * Wo /
                                (128.0 * ((Wo + a.bw - 1) / a.bw) * ((Ho + a.bh - 1) / a.bh) * ((io.B + a.bb - 1) / a.bb));
       const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
-      if (eff_halo >= 0.85 * eff_patch) {
+      const int halo_bytes = ((8 + L.kw - 1) * (16 + L.kh - 1) * 128 + 1023) & ~1023;
+      const bool resident_w = L.n_tiles * L.kh * L.kw * ((L.Cin + kBK - 1) / kBK) * L.BN * 128 <= kResidentWeightBytes;
+      const bool row_fits = L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * halo_bytes <=
+                                            226 * 1024 - (kOutBufs * kSlabBytes + (4 * kMaxStages + 18) * 8 + 2048 + 1024);
+      const bool want = ctx->halo_mode > 0 || resident_w || (row_fits && eff_halo >= 0.9 * eff_patch);
+      if (want && eff_halo >= 0.85 * eff_patch) {
         a.halo = 1;
         a.bw = 8; a.bh = 16; a.bb = 1;
         a.kh = L.kh;
         a.halo_w = 8 + L.kw - 1;
         a.halo_h = 16 + L.kh - 1;
-        a.halo_bytes = (a.halo_w * a.halo_h * 128 + 1023) & ~1023;
+        a.halo_bytes = halo_bytes;
       }
     }
     a.tiles_w = (Wo + a.bw - 1) / a.bw;
@@ -310,7 +321,10 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   const int total_budget = 226 * 1024 - base_fixed;
   // residual slabs ride the ring as single extra A blocks: one k-block per stage then
   a.kbps = (!a.halo && a.num_kb >= 2 && ctx->kbps2 && io.res_mode != RES_PRE_ACT) ? 2 : 1;
-  int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? 1 : a.kbps) * L.BN * 128);
+  // halo mode with streamed weights: a whole filter row of taps per B stage when two such stages and two halo tiles fit
+  a.brow = 1;
+  if (a.halo && !a.b_resident && L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * a.halo_bytes <= total_budget) a.brow = L.kw;
+  int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? a.brow : a.kbps) * L.BN * 128);
   if (a.kbps == 2 && total_budget / stage_bytes < 3) {   // too few double stages to cover the TMA latency
     a.kbps = 1;
     stage_bytes /= 2;
@@ -318,7 +332,8 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (a.halo) {
     // TMA latency is hidden by bytes in flight: with resident weights the whole budget goes to halo buffers,
     // otherwise the halo ring gets about a third and the weight ring the rest
-    const int for_a = a.b_resident ? total_budget : std::max(2 * a.halo_bytes, total_budget / 3);
+    const int for_a = a.b_resident ? total_budget
+                                   : std::max(2 * a.halo_bytes, std::min(total_budget / 3, total_budget - 2 * a.brow * L.BN * 128));
     a.a_stages = std::max(2, std::min(kMaxStages, for_a / a.halo_bytes));
   }
   const int fixed = base_fixed + a.a_stages * a.halo_bytes;
@@ -464,7 +479,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       ctx->bn_cap = value;
       return FRB_OK;
     case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
-    case FRB_OPT_HALO: ctx->halo_mode = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_HALO: ctx->halo_mode = value > 0 ? 1 : (value < 0 ? -1 : 0); return FRB_OK;
     case FRB_OPT_KBPS2: ctx->kbps2 = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;

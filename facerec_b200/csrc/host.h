@@ -37,8 +37,7 @@ struct frb_ctx {
   std::vector<double> lt_info;             // 6 doubles per op: kind, M, N, K, flop, (ms filled by frb_debug_layer_times)
   int trace_mode = 0;          // FRB_OPT_TRACE: per-CTA stall counters of the conv_tma roles
   long long* trace_dev = nullptr;  // FRB_OPT_TRACE: device buffer for conv_tma timeline records
-  int halo_mode = 0;           // 1: stride-1 k x k convs read A from one halo tile per channel block (measured: not faster
-                               //    than one box per tap, the small-N layers are bound by MMA operand reads, see profiles/)
+  int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
   int* wd_dev = nullptr;

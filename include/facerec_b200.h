@@ -53,8 +53,9 @@ enum frb_option {
   FRB_OPT_BF16 = 0,        /* 1: bf16 activations/weights instead of fp16 (set before frb_load_model) */
   FRB_OPT_BN_CAP = 1,      /* largest conv tile N (multiple of 16, <= 256)                           */
   FRB_OPT_FORCE_GATHER = 2,/* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
-  FRB_OPT_HALO = 3,        /* 1: stride-1 k x k convs read one halo tile per channel block instead of one TMA
-                              box per filter tap (default 0: measured slower)                              */
+  FRB_OPT_HALO = 3,        /* stride-1 k x k convs reading one halo tile per channel block instead of one TMA box
+                              per filter tap: 0 (default) where it pays (resident weights, or a filter row of
+                              streamed weights per stage), 1 wherever possible, -1 never                          */
   FRB_OPT_TRACE = 4,       /* non-zero: every CTA of a conv_tma launch writes 16 stall-cycle counters of its
                               three roles at h_out[1 + 16 * cta] (read with frb_debug_trace)                 */
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
