@@ -325,7 +325,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.brow = 1;
   if (a.halo && !a.b_resident && L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * a.halo_bytes <= total_budget) a.brow = L.kw;
   int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? a.brow : a.kbps) * L.BN * 128);
-  if (a.kbps == 2 && total_budget / stage_bytes < 3) {   // too few double stages to cover the TMA latency
+  if (a.kbps == 2 && total_budget / stage_bytes < ctx->kbps2_min_stages) {   // too few double stages to cover the TMA latency
     a.kbps = 1;
     stage_bytes /= 2;
   }
@@ -480,7 +480,10 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       return FRB_OK;
     case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_HALO: ctx->halo_mode = value > 0 ? 1 : (value < 0 ? -1 : 0); return FRB_OK;
-    case FRB_OPT_KBPS2: ctx->kbps2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_KBPS2:
+      ctx->kbps2 = value ? 1 : 0;
+      if (value >= 2) ctx->kbps2_min_stages = value;
+      return FRB_OK;
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;

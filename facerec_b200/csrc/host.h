@@ -31,6 +31,7 @@ struct frb_ctx {
   void* d_ident[2] = {nullptr, nullptr};   // 64 x 64 identity (fp16, bf16): B operand of the residual MMAs
   int skip_loads = 0;          // FRB_OPT_SKIP_LOADS: timing experiment, results are garbage
   int max_stages = 64;         // FRB_OPT_MAX_STAGES: cap on the conv_tma stage ring (latency-sensitivity experiments)
+  int kbps2_min_stages = 3;    // FRB_OPT_KBPS2 value >= 2 sets it: fewest double stages that must fit for two k-blocks per stage
   int kbps2 = 1;               // two 64-wide k-blocks per pipeline stage (0: one)
   int layer_times = 0;         // FRB_OPT_LAYER_TIMES: run_plan brackets every op with events (debug only)
   std::vector<cudaEvent_t> lt_events;      // lt_events[0] = before the first op, [i+1] = after op i
