@@ -17,10 +17,16 @@ ap.add_argument("--kbps1", action="store_true")
 ap.add_argument("--skip-loads", action="store_true")
 a = ap.parse_args()
 for shape in a.shape:
-    B, H, W, Cin, Cout, k, s, p = (int(v) for v in shape.split(","))
+    f = [int(v) for v in shape.split(",")]
+    if len(f) == 10:                      # B,H,W,Cin,Cout,kh,kw,stride,ph,pw
+        B, H, W, Cin, Cout, kh, kw, s, ph, pw = f
+    else:
+        B, H, W, Cin, Cout, k, s, p = f
+        kh = kw = k
+        ph = pw = p
     x = torch.randn(B, H, W, Cin, device="cuda").half()
-    w = (np.random.RandomState(0).standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
-    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    w = (np.random.RandomState(0).standard_normal((Cout, kh, kw, Cin)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+    Ho, Wo = (H + 2 * ph - kh) // s + 1, (W + 2 * pw - kw) // s + 1
     res = torch.randn(B, Ho, Wo, Cout, device="cuda").half() if a.res else None
     plain = _lib.Context(0)
     plain.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
@@ -28,8 +34,8 @@ for shape in a.shape:
     plain.set_option(_lib.FRB_OPT_MAX_STAGES, a.max_stages)
     plain.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
     plain.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
-    ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)       # clocks up
-    _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=20)
+    ops.conv2d(plain, x, w, None, (s, s), (ph, pw), 1, 0.0, res, 1 if a.res else 0, iters=20)       # clocks up
+    _, ms0 = ops.conv2d(plain, x, w, None, (s, s), (ph, pw), 1, 0.0, res, 1 if a.res else 0, iters=20)
     plain.close()
     ctx = _lib.Context(0)
     ctx.set_option(_lib.FRB_OPT_BN_CAP, a.bn_cap)
@@ -38,13 +44,13 @@ for shape in a.shape:
     ctx.set_option(_lib.FRB_OPT_MAX_STAGES, a.max_stages)
     ctx.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
     ctx.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
-    _, ms = ops.conv2d(ctx, x, w, None, (s, s), (p, p), 1, 0.0, res, 1 if a.res else 0, iters=1)
+    _, ms = ops.conv2d(ctx, x, w, None, (s, s), (ph, pw), 1, 0.0, res, 1 if a.res else 0, iters=1)
     buf = np.zeros(1 + 3 * 4000, np.int64)
     ctx.check(ctx.lib.frb_debug_trace(ctx.handle, buf.ctypes.data, 4000), "trace")
     c = buf[1:1 + 148 * 16].reshape(148, 16).astype(np.float64)
     c = c[c[:, 0] > 0]
     m = c.mean(0)
-    fl = 2.0 * B * Ho * Wo * Cout * k * k * Cin
+    fl = 2.0 * B * Ho * Wo * Cout * kh * kw * Cin
     print(f"== {shape}{' +res' if a.res else ''}: {ms0:.3f} ms plain ({fl / ms0 / 1e9:.0f} TFLOP/s), {ms:.3f} ms counted; "
           f"{m[5]:.1f} tiles per CTA, {m[0] / max(m[5], 1):.0f} cycles per tile")
     print(f"   epilogue t0 : accumulator wait {m[1] / m[0] * 100:5.1f}%  residual wait {m[2] / m[0] * 100:5.1f}%  "
