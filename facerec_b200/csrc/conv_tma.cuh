@@ -142,6 +142,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
   const int nslab = (p.BN + kSlab - 1) / kSlab;
   const int nacc = p.BN <= 128 ? kMaxAcc : 2;          // accumulator buffers in TMEM (nacc * BN <= 512 columns)
+  const int nacc_shift = p.BN <= 128 ? 2 : 1;          // log2(nacc): the per-tile bookkeeping of the single-warp roles avoids divisions
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(nacc * p.BN)) tmem_cols <<= 1;
 
@@ -246,8 +247,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       prefetch(cur);
     }
     for (int q = grp; q < my_slabs; q += kEpiGroups) {
-      const int buf = cur.tile_iter % nacc;
-      const uint32_t tphase = static_cast<uint32_t>(cur.tile_iter / nacc) & 1u;
+      const int buf = cur.tile_iter & (nacc - 1);                       // nacc is 2 or 4
+      const uint32_t tphase = static_cast<uint32_t>(cur.tile_iter >> nacc_shift) & 1u;
       const int ncols = cur.ncols;
 
       const typename E::T* up_row = nullptr;
@@ -398,9 +399,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     if (p.b_resident || kRes == 1) mbar_wait(bres_bar, 0, p.watchdog, 250);
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
-      const int buf = tile_iter % nacc;
-      const uint32_t tphase = static_cast<uint32_t>(tile_iter / nacc) & 1u;
-      const int n_tile = tile % p.n_tiles;
+      const int buf = tile_iter & (nacc - 1);
+      const uint32_t tphase = static_cast<uint32_t>(tile_iter >> nacc_shift) & 1u;
+      const int n_tile = tile - fastdiv(tile, p.fd_n) * p.n_tiles;
       sc.start();
       mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf);
       sc.stop(st_tempty);
