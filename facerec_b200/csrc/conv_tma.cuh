@@ -26,10 +26,10 @@
 // exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.  Optional
 // (FRB_OPT_HALO) and off by default: it measures 5-9 % SLOWER than one box per tap on every layer tried.
 //
-// Warp roles (448 threads, 14 warps = at most 4 per scheduler, i.e. up to 128 registers per thread: with ~227 KB
+// Warp roles (480 threads, 15 warps = at most 4 per scheduler, i.e. up to 128 registers per thread: with ~227 KB
 // of shared memory there is no L1 left and a spill is an L2 round trip): warps 0-11 are
-// three independent epilogue groups (one warp per TMEM lane quarter each), 12 the MMA issuer + TMEM allocator,
-// 13 the TMA producer.  Profiles that led here: profiles/r01_stall_counters_v6.txt (16 warps sharing every slab
+// three independent epilogue groups (one warp per TMEM lane quarter each), 12 and 14 two MMA issuers taking tiles
+// alternately (12 also allocates TMEM), 13 the TMA producer.  Profiles that led here: profiles/r01_stall_counters_v6.txt (16 warps sharing every slab
 // behind two 512-thread barriers: 2 000 cycles per slab, the MMA issuer waiting for a TMEM buffer 78 % of the time).
 // Persistent: one CTA per SM walks tiles round-robin (n fastest, so CTAs running at the same time
 // share the A patch through L2).
@@ -40,7 +40,7 @@ namespace frb {
 
 constexpr int kEpiWarps = 12;             // 14 warps in all: at most 4 per scheduler (measured: 16 + 2 warps is 2-3 % slower end to end)
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kTmaThreads = kEpiThreads + 64;
+constexpr int kTmaThreads = kEpiThreads + 96;   // + MMA issuer A, TMA producer, MMA issuer B
 constexpr int kSlab = 64;                  // epilogue / store granularity in output channels
 constexpr int kSlabBytes = kBM * kSlab * 2;
 constexpr int kEpiGroups = kEpiWarps / 4;  // independent epilogue groups: one warp per TMEM lane quarter each
@@ -77,6 +77,7 @@ struct ConvTmaArgs {
   int B;                 // images (patch tiling bounds check of the residual rows)
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
+  int dual_issue;        // 1: two MMA issuer warps take tiles alternately where the rings allow it (FRB_OPT_DUAL_ISSUE)
   int skip_loads;        // debug (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers, MMAs read stale tiles
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
 };
@@ -133,16 +134,23 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   uint64_t* bres_bar = bars + 2 * kMaxStages + 16;    // [1] resident weights + identity have landed
   uint64_t* afull_bar = bars + 2 * kMaxStages + 17;   // [kMaxStages] halo ring
   uint64_t* aempty_bar = bars + 3 * kMaxStages + 17;  // [kMaxStages]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 17);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 18);   // [kEpiGroups][kSlab]
+  uint64_t* turn_bar = bars + 4 * kMaxStages + 17;    // [2] issuer w has finished issuing a tile (dual issue hand-over)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 19);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 20);   // [kEpiGroups][kSlab]
   float* s_slope = s_bias + kEpiGroups * kSlab;                           // [kEpiGroups][kSlab]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
+  constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1, kMmaWarp2 = kEpiWarps + 2;
   const int nslab = (p.BN + kSlab - 1) / kSlab;
   const int nacc = p.BN <= 128 ? kMaxAcc : 2;          // accumulator buffers in TMEM (nacc * BN <= 512 columns)
   const int nacc_shift = p.BN <= 128 ? 2 : 1;          // log2(nacc): the per-tile bookkeeping of the single-warp roles avoids divisions
+  // Two MMA issuer warps take the CTA's tiles alternately when two consecutive tiles fit in one pass over each ring
+  // (see the issuer role).  Ring slots a tile consumes:
+  const int tile_stages = p.halo ? (p.b_resident ? 0 : p.cin_blocks * (p.brow > 1 ? p.kh : p.kh * p.kw))
+                                 : (p.num_kb + p.kbps - 1) / p.kbps + (kRes == 1 ? nslab : 0);
+  const int tile_astages = p.halo ? p.cin_blocks : 0;
+  const bool dual = p.dual_issue == 1 && 2 * tile_stages <= p.stages && (!p.halo || 2 * tile_astages <= p.a_stages);
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(nacc * p.BN)) tmem_cols <<= 1;
 
@@ -166,6 +174,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         mbar_init(&tempty_bar[b], 4 * nslab);          // every warp of the nslab groups that read the buffer
       }
       mbar_init(bres_bar, 1);
+      mbar_init(&turn_bar[0], 1);
+      mbar_init(&turn_bar[1], 1);
       for (int s = 0; s < kMaxStages; ++s) {
         mbar_init(&afull_bar[s], 1);
         mbar_init(&aempty_bar[s], 1);
@@ -270,6 +280,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       if (gtid < kSlab) g_bias[gtid] = next_bs;
       else if (kAct == 0) g_slope[gtid - kSlab] = next_bs;
 
+      if (kStall && leader && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + 3 + grp] = q * 10 + 1;
       sc.start();
       mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
       sc.stop(st_tfull);
@@ -361,6 +372,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         prefetch(cur);
       }
       fence_proxy_async_smem();
+      if (kStall && leader && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + 3 + grp] = q * 10 + 5;
       sc.start();
       named_bar_sync(1 + grp, kGroupThreads);  // barrier B
       sc.stop(st_bar);
@@ -375,7 +387,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       o[0] = clock64() - st_begin; o[1] = st_tfull; o[2] = st_res; o[3] = st_slab; o[4] = st_bar; o[5] = my_tiles;
     }
     if (leader) tma_store_wait<0>();           // stores must land before the CTA (and its smem) goes away
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kMmaWarp || warp == kMmaWarp2) {
     // ============================================================== MMA issuer
     // Everything here is warp-uniform and incremental: descriptor LOW words (start address >> 4) advance by
     // constant steps, high words are constants, barriers are 32-bit shared addresses, and only the tcgen05
@@ -392,20 +404,50 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     int stage = 0, astage = 0;
     uint32_t phase = 0, aphase = 0;
     uint32_t a_ring = a_lo0, b_ring = b_lo0;          // descriptor low words of the current ring slots
-    int tile_iter = 0;
-    StallClock<kStall> sc{kStall && p.stall != nullptr, 0};
+    // Two issuer warps take the CTA's tiles alternately (A the even tile_iters, B the odd ones): the barrier waits and
+    // the per-tile bookkeeping of one (650-850 cycles per tile, as long as 16 N=64 MMAs) overlap with the other's MMAs.
+    // They use different TMEM buffers, their own commits, and ring positions that each warp advances past the other's
+    // tile (a tile always consumes the same number of ring slots).  The MMAs themselves still go out in tile order —
+    // a warp waits for the other's "tile issued" arrival right before its first MMA — because every other barrier in
+    // here tells phases apart by parity only and relies on tiles completing in order (an epilogue group that ran
+    // ahead of a lagging issuer would take the previous phase of a TMEM buffer for its own).
+    const int iw = warp == kMmaWarp ? 0 : 1;
+    const int b_slots = p.halo ? p.brow : p.kbps;     // k-blocks (taps) of weights per ring stage
+    auto skip_tile = [&]() {                           // move the ring positions past one tile issued by the other warp
+      stage += tile_stages;
+      while (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+      a_ring = a_lo0 + static_cast<uint32_t>(stage * p.kbps) * a_step;
+      b_ring = b_lo0 + static_cast<uint32_t>(stage * b_slots) * b_step;
+      astage += tile_astages;
+      while (p.halo && astage >= p.a_stages) { astage -= p.a_stages; aphase ^= 1; }
+    };
+    // mbarrier waits tell phases apart by parity only: a waiter must never be two phases ahead of a barrier.  With two
+    // issuers that holds as long as two consecutive tiles fit in one pass over each ring; longer tiles keep one issuer
+    // (their per-tile overheads are amortised over many MMAs anyway).
+    const int solo = p.dual_issue == 2 ? 1 : 0;      // debug: which warp issues when there is only one issuer
+    const int nw = dual ? 2 : 1;
+    if (iw == 1 && dual) skip_tile();
+    const uint32_t turn_other = smem_u32(&turn_bar[iw ^ 1]);
+    int tile_iter = dual ? iw : 0;
+    StallClock<kStall> sc{kStall && p.stall != nullptr && iw == 0, 0};
     long long st_tempty = 0, st_full = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
     if (p.b_resident || kRes == 1) mbar_wait(bres_bar, 0, p.watchdog, 250);
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = dual ? blockIdx.x + iw * gridDim.x : (iw == solo ? static_cast<int>(blockIdx.x) : p.total_tiles); tile < p.total_tiles;
+         tile += nw * gridDim.x, tile_iter += nw) {
       const int buf = tile_iter & (nacc - 1);
       const uint32_t tphase = static_cast<uint32_t>(tile_iter >> nacc_shift) & 1u;
       const int n_tile = tile - fastdiv(tile, p.fd_n) * p.n_tiles;
+      if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 1;
       sc.start();
-      mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf);
+      mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf + 1000 * iw);
       sc.stop(st_tempty);
       tc_fence_after();
+      if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 2;
+      auto my_turn = [&]() {                 // dual issue: the other warp has issued the tile before this one
+        if (dual && tile_iter > 0) mbar_wait_a(turn_other, static_cast<uint32_t>((tile_iter - 1) >> 1) & 1u, p.watchdog, 260 + 1000 * iw);
+      };
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
       const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
       auto mma4 = [&](uint32_t a, uint32_t b, uint32_t acc0) {          // one 64-channel tap out of a halo tile
@@ -422,8 +464,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         const uint32_t tap_b = static_cast<uint32_t>(p.cin_blocks) * b_step;   // next tap of the same channel block
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           sc.start();
-          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage + 1000 * iw);
           sc.stop(st_full);
+          if (cb == 0) my_turn();
           tc_fence_after();
           const uint32_t a0 = a_lo0 + static_cast<uint32_t>(astage) * halo_step;          // pixel (0,0) of the halo tile
           const uint32_t b0 = b_res + static_cast<uint32_t>(cb) * b_step;                  // block (tap 0, cb)
@@ -459,14 +502,15 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         // Streamed weights, one filter ROW (kw taps) per B stage: a wait per row instead of a wait per tap
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           sc.start();
-          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage + 1000 * iw);
           sc.stop(st_full);
           uint32_t a_row = a_lo0 + static_cast<uint32_t>(astage) * halo_step;
           uint32_t acc = cb != 0 ? 1u : 0u;
           for (int tr = 0; tr < p.kh; ++tr) {
             sc.start();
-            mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+            mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
             sc.stop(st_full);
+            if (cb == 0 && tr == 0) my_turn();
             tc_fence_after();
             if (elect_one()) {
               if (p.kw == 3) {
@@ -497,7 +541,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       } else if (p.halo) {
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           sc.start();
-          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage);
+          mbar_wait_a(afull0 + astage * 8, aphase, p.watchdog, 220 + astage + 1000 * iw);
           sc.stop(st_full);
           tc_fence_after();
           uint32_t a_tap = a_lo0 + static_cast<uint32_t>(astage) * halo_step;          // pixel (0,0) of the halo tile
@@ -507,10 +551,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
             for (int ts = 0; ts < p.kw; ++ts) {
               if (!p.b_resident) {
                 sc.start();
-                mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+                mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
                 sc.stop(st_full);
                 tc_fence_after();
                 b_tap = b_ring;
+              }
+              if (cb == 0 && tr == 0 && ts == 0) {
+                my_turn();
+                tc_fence_after();
               }
               const bool last_tap = tr == p.kh - 1 && ts == p.kw - 1;
               if (elect_one()) {
@@ -542,10 +590,13 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         uint32_t b_cur = b_res;
         for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kbps) {
           const bool two = p.kbps == 2 && kb0 + 1 < p.num_kb;            // this stage carries two k-blocks
+          if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 3 + 10000 * stage + 100000 * phase;
           sc.start();
-          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
           sc.stop(st_full);
+          if (kb0 == 0) my_turn();
           tc_fence_after();
+          if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 4;
           if (!p.b_resident) b_cur = b_ring;
           if (elect_one()) {
             tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, kb0 != 0 ? 1u : 0u);
@@ -575,7 +626,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           const uint32_t idesc_r = make_idesc_f16(kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
           const uint32_t d_r = d_tmem + static_cast<uint32_t>(rs * kSlab);
           sc.start();
-          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
           sc.stop(st_full);
           tc_fence_after();
           if (elect_one()) {
@@ -592,7 +643,13 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
         }
       }
+      if (dual) {
+        if (elect_one()) mbar_arrive(&turn_bar[iw]);     // everything of this tile has been issued: the other warp's turn
+        __syncwarp();
+        skip_tile();
+      }
     }
+    if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = 99999;
     if (kStall && sc.on && lane == 0) {
       long long* o = p.stall + 1 + blockIdx.x * 16;
       o[6] = clock64() - st_begin; o[7] = st_tempty; o[8] = st_full;
@@ -624,6 +681,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
       const int n_coord = n_tile * p.BN;
+      if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + 2] = tile_iter;
       if (p.halo) {
         const int taps = p.kh * p.kw;
         for (int hb = 0; hb < p.cin_blocks; ++hb) {
@@ -720,6 +778,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         }
       }
     }
+    if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + 2] = 99999;
     if (kStall && sc.on && lane == 0) {
       long long* o = p.stall + 1 + blockIdx.x * 16;
       o[9] = clock64() - st_begin; o[10] = st_empty; o[11] = st_rempty;

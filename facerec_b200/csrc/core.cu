@@ -23,8 +23,10 @@ int set_err(frb_ctx* ctx, int code, const char* fmt, ...) {
 
 static void append_watchdog(frb_ctx* ctx) {
   if (ctx != nullptr && ctx->wd_host != nullptr && ctx->wd_host[0] != 0) {
-    char buf[128];
-    snprintf(buf, sizeof(buf), " [pipeline watchdog: wait code %d in block %d]", ctx->wd_host[0], ctx->wd_host[1]);
+    char buf[384];
+    const int* pr = ctx->wd_host + 16 + 8 * (ctx->wd_host[1] >= 0 && ctx->wd_host[1] < 148 ? ctx->wd_host[1] : 0);
+    snprintf(buf, sizeof(buf), " [pipeline watchdog: wait code %d in block %d; its progress (stall-counter build only): issuer A %d, "
+             "issuer B %d, producer %d, epilogue groups %d %d %d]", ctx->wd_host[0], ctx->wd_host[1], pr[0], pr[1], pr[2], pr[3], pr[4], pr[5]);
     ctx->err += buf;
     ctx->wd_host[0] = 0;
   }
@@ -231,6 +233,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.watchdog = ctx->wd_dev;
   a.stall = ctx->trace_mode != 0 ? ctx->trace_dev : nullptr;
   a.skip_loads = ctx->skip_loads;
+  a.dual_issue = ctx->dual_issue;
   if (ctx->trace_dev) cudaMemsetAsync(ctx->trace_dev, 0, 8, stream);
 
   CUtensorMap tmA, tmO, tmR, tmI;
@@ -277,7 +280,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       const int halo_bytes = ((8 + L.kw - 1) * (16 + L.kh - 1) * 128 + 1023) & ~1023;
       const bool resident_w = L.n_tiles * L.kh * L.kw * ((L.Cin + kBK - 1) / kBK) * L.BN * 128 <= kResidentWeightBytes;
       const bool row_fits = L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * halo_bytes <=
-                                            226 * 1024 - (kOutBufs * kSlabBytes + (4 * kMaxStages + 18) * 8 + 2048 + 1024);
+                                            226 * 1024 - (kOutBufs * kSlabBytes + (4 * kMaxStages + 20) * 8 + 2048 + 1024);
       const bool want = ctx->halo_mode > 0 || resident_w || (row_fits && eff_halo >= 0.9 * eff_patch);
       if (want && eff_halo >= 0.85 * eff_patch) {
         a.halo = 1;
@@ -317,7 +320,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   const int w_bytes = L.n_tiles * a.num_kb * L.BN * 128;
   a.b_resident = w_bytes <= kResidentWeightBytes ? 1 : 0;
   const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? w_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
-                         (4 * kMaxStages + 18) * 8 + 2048 + 1024;
+                         (4 * kMaxStages + 20) * 8 + 2048 + 1024;
   const int total_budget = 226 * 1024 - base_fixed;
   // residual slabs ride the ring as single extra A blocks: one k-block per stage then
   a.kbps = (!a.halo && a.num_kb >= 2 && ctx->kbps2 && io.res_mode != RES_PRE_ACT) ? 2 : 1;
@@ -436,8 +439,8 @@ int frb_init(int device, frb_ctx** out) {
   frb_ctx* ctx = new frb_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
-  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->wd_host), 64, cudaHostAllocMapped) == cudaSuccess) {
-    memset(ctx->wd_host, 0, 64);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->wd_host), 64 + 148 * 32, cudaHostAllocMapped) == cudaSuccess) {
+    memset(ctx->wd_host, 0, 64 + 148 * 32);
     if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->wd_dev), ctx->wd_host, 0) != cudaSuccess)
       ctx->wd_dev = nullptr;
   }
@@ -485,6 +488,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       if (value >= 2) ctx->kbps2_min_stages = value;
       return FRB_OK;
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_DUAL_ISSUE: ctx->dual_issue = value; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;
     case FRB_OPT_TRACE:

@@ -61,6 +61,7 @@ enum frb_option {
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
   FRB_OPT_LAYER_TIMES = 6, /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
   FRB_OPT_MAX_STAGES = 7,  /* cap on the conv_tma stage ring depth (>= 2; experiments)                          */
+  FRB_OPT_DUAL_ISSUE = 9,  /* 0: a single MMA issuer warp per CTA (default 1: two, alternating tiles, where safe)   */
   FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 

@@ -21,6 +21,8 @@ def main():
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     H, Wd = 1080, 1920
     ctx = _lib.Context(0)
+    if os.environ.get("FRB_DUAL"):
+        ctx.set_option(_lib.FRB_OPT_DUAL_ISSUE, int(os.environ["FRB_DUAL"]))
     if os.environ.get("FRB_KBPS2"):
         ctx.set_option(_lib.FRB_OPT_KBPS2, int(os.environ["FRB_KBPS2"]))
     if os.environ.get("FRB_HALO"):
