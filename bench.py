@@ -357,9 +357,9 @@ def run_b200(a):
         }
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            fps, faces, dt = cpu_reference_fps(frames_h[:a.ref_frames], first, a.backbone, a.save_every, threads)
+            fps, faces, dt = cpu_reference_fps(frames_h[:a.cpu_baseline_frames], first, a.backbone, a.save_every, threads)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                                    "sample": f"first {a.ref_frames} frame(s) of the same batch ({dt:.1f} s of CPU work), fp32 "
+                                    "sample": f"first {a.cpu_baseline_frames} frame(s) of the same batch ({dt:.1f} s of CPU work), fp32 "
                                               f"PyTorch oracle, batch 1 per frame/face; {faces} faces embedded"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -380,6 +380,8 @@ def main():
     ap.add_argument("--clip-seed", type=int, default=1234)
     ap.add_argument("--ref-frames", type=int, default=5,
                     help="frames per step of the CPU arm / cpu_baseline sample (5 = one save_every period: 5 detects, 1 embed pass)")
+    ap.add_argument("--cpu-baseline-frames", type=int, default=25,
+                    help="frames of the batch the cpu_baseline leg runs through the oracle (25 = five save_every periods, ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -425,17 +425,17 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     // issuers that holds as long as two consecutive tiles fit in one pass over each ring; longer tiles keep one issuer
     // (their per-tile overheads are amortised over many MMAs anyway).
     const int solo = p.dual_issue == 2 ? 1 : 0;      // debug: which warp issues when there is only one issuer
-    const int nw = dual ? 2 : 1;
     if (iw == 1 && dual) skip_tile();
     const uint32_t turn_other = smem_u32(&turn_bar[iw ^ 1]);
     int tile_iter = dual ? iw : 0;
+    const int tstep = dual ? 2 : 1;
     StallClock<kStall> sc{kStall && p.stall != nullptr && iw == 0, 0};
     long long st_tempty = 0, st_full = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
     if (p.b_resident || kRes == 1) mbar_wait(bres_bar, 0, p.watchdog, 250);
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
-    for (int tile = dual ? blockIdx.x + iw * gridDim.x : (iw == solo ? static_cast<int>(blockIdx.x) : p.total_tiles); tile < p.total_tiles;
-         tile += nw * gridDim.x, tile_iter += nw) {
+    for (int tile = dual ? blockIdx.x + iw * gridDim.x : (iw == solo ? static_cast<int>(blockIdx.x) : p.total_tiles);
+         tile < p.total_tiles; tile += tstep * gridDim.x, tile_iter += tstep) {
       const int buf = tile_iter & (nacc - 1);
       const uint32_t tphase = static_cast<uint32_t>(tile_iter >> nacc_shift) & 1u;
       const int n_tile = tile - fastdiv(tile, p.fd_n) * p.n_tiles;
@@ -587,59 +587,61 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
         }
       } else {
+        // One walk over the tile's ring stages: n_k weight stages (one or two k-blocks each), then for kRes = 1 the
+        // residual slabs (accumulator columns [rs * 64, rs * 64 + ncols) += residual slab x identity).
+        // (Splitting the stages of a tile between the two issuers was tried: 2-4 % on the long tiles, but the order in
+        // which the k-blocks reach the accumulator then depends on timing and results stop being reproducible.)
+        const int n_k = (p.num_kb + p.kbps - 1) / p.kbps;
         uint32_t b_cur = b_res;
-        for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kbps) {
-          const bool two = p.kbps == 2 && kb0 + 1 < p.num_kb;            // this stage carries two k-blocks
-          if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 3 + 10000 * stage + 100000 * phase;
-          sc.start();
-          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
-          sc.stop(st_full);
-          if (kb0 == 0) my_turn();
-          tc_fence_after();
-          if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 4;
-          if (!p.b_resident) b_cur = b_ring;
-          if (elect_one()) {
-            tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, kb0 != 0 ? 1u : 0u);
-            tc_mma_f16(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
-            tc_mma_f16(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
-            tc_mma_f16(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
-            if (two) {
-              const uint32_t a2 = a_ring + a_step, b2 = b_cur + b_step;
-              tc_mma_f16(d_tmem, pack_desc(a2, hi1024), pack_desc(b2, hi1024), idesc, 1u);
-              tc_mma_f16(d_tmem, pack_desc(a2 + 2, hi1024), pack_desc(b2 + 2, hi1024), idesc, 1u);
-              tc_mma_f16(d_tmem, pack_desc(a2 + 4, hi1024), pack_desc(b2 + 4, hi1024), idesc, 1u);
-              tc_mma_f16(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
+        int kb0 = 0;
+        for (int j = 0; j < tile_stages; ++j) {
+          {
+            if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 3 + 10000 * stage + 100000 * phase;
+            sc.start();
+            mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
+            sc.stop(st_full);
+            if (j == 0) my_turn();
+            tc_fence_after();
+            const bool last_mine = j + 1 >= tile_stages;
+            if (j < n_k) {
+              const bool two = p.kbps == 2 && kb0 + 1 < p.num_kb;          // this stage carries two k-blocks
+              if (!p.b_resident) b_cur = b_ring;
+              if (elect_one()) {
+                tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, j != 0 ? 1u : 0u);
+                tc_mma_f16(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
+                tc_mma_f16(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
+                tc_mma_f16(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
+                if (two) {
+                  const uint32_t a2 = a_ring + a_step, b2 = b_cur + b_step;
+                  tc_mma_f16(d_tmem, pack_desc(a2, hi1024), pack_desc(b2, hi1024), idesc, 1u);
+                  tc_mma_f16(d_tmem, pack_desc(a2 + 2, hi1024), pack_desc(b2 + 2, hi1024), idesc, 1u);
+                  tc_mma_f16(d_tmem, pack_desc(a2 + 4, hi1024), pack_desc(b2 + 4, hi1024), idesc, 1u);
+                  tc_mma_f16(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
+                }
+                tc_commit_a(empty0 + stage * 8);
+                if (last_mine) tc_commit_a(tfull0 + buf * 8);
+              }
+            } else {
+              const int rs = j - n_k;
+              const uint32_t idesc_r = make_idesc_f16(kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
+              const uint32_t d_r = d_tmem + static_cast<uint32_t>(rs * kSlab);
+              if (elect_one()) {
+                tc_mma_f16(d_r, pack_desc(a_ring, hi1024), pack_desc(ident_lo, hi1024), idesc_r, 1u);
+                tc_mma_f16(d_r, pack_desc(a_ring + 2, hi1024), pack_desc(ident_lo + 2, hi1024), idesc_r, 1u);
+                tc_mma_f16(d_r, pack_desc(a_ring + 4, hi1024), pack_desc(ident_lo + 4, hi1024), idesc_r, 1u);
+                tc_mma_f16(d_r, pack_desc(a_ring + 6, hi1024), pack_desc(ident_lo + 6, hi1024), idesc_r, 1u);
+                tc_commit_a(empty0 + stage * 8);
+                if (last_mine) tc_commit_a(tfull0 + buf * 8);
+              }
             }
-            tc_commit_a(empty0 + stage * 8);
-            if (kRes != 1 && kb0 + p.kbps >= p.num_kb) tc_commit_a(tfull0 + buf * 8);
+            __syncwarp();
           }
-          __syncwarp();
-          b_cur += static_cast<uint32_t>(p.kbps) * b_step;
+          if (j < n_k) {
+            kb0 += p.kbps;
+            b_cur += static_cast<uint32_t>(p.kbps) * b_step;
+          }
           a_ring += static_cast<uint32_t>(p.kbps) * a_step;
           b_ring += static_cast<uint32_t>(p.kbps) * b_step;
-          if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
-        }
-      }
-      if constexpr (kRes == 1) {
-        // residual slabs: accumulator columns [rs * 64, rs * 64 + ncols) += residual slab (A, from the ring) x identity
-        for (int rs = 0; rs < nslab; ++rs) {
-          const uint32_t idesc_r = make_idesc_f16(kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
-          const uint32_t d_r = d_tmem + static_cast<uint32_t>(rs * kSlab);
-          sc.start();
-          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage + 1000 * iw);
-          sc.stop(st_full);
-          tc_fence_after();
-          if (elect_one()) {
-            tc_mma_f16(d_r, pack_desc(a_ring, hi1024), pack_desc(ident_lo, hi1024), idesc_r, 1u);
-            tc_mma_f16(d_r, pack_desc(a_ring + 2, hi1024), pack_desc(ident_lo + 2, hi1024), idesc_r, 1u);
-            tc_mma_f16(d_r, pack_desc(a_ring + 4, hi1024), pack_desc(ident_lo + 4, hi1024), idesc_r, 1u);
-            tc_mma_f16(d_r, pack_desc(a_ring + 6, hi1024), pack_desc(ident_lo + 6, hi1024), idesc_r, 1u);
-            tc_commit_a(empty0 + stage * 8);
-            if (rs == nslab - 1) tc_commit_a(tfull0 + buf * 8);
-          }
-          __syncwarp();
-          a_ring += a_step;
-          b_ring += b_step;
           if (++stage == p.stages) { stage = 0; phase ^= 1; a_ring = a_lo0; b_ring = b_lo0; }
         }
       }

@@ -65,3 +65,31 @@ def test_irv1_forward_matches_oracle(ctx):
     assert cos.min().item() >= 0.999, cos
     # distinct faces stay distinct (the test is not vacuous)
     assert (ref @ ref.T - torch.eye(len(boxes))).max().item() < 0.9999
+
+
+def test_forwards_are_bit_reproducible(ctx):
+    """The same input gives the same bits every time, with one and with two MMA issuer warps: no output depends on the
+    timing of the pipeline roles (a stage-split between the issuers was dropped for breaking exactly this)."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(3)
+    fr = torch.from_numpy(_frames(rng, 3, 270, 480)).cuda()
+    mid = weights.MODEL_IDS["retina_r50"]
+    ops.load_model(ctx, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+    x16 = ops.preprocess_u8(ctx, fr, True, ops.input_layout(mid))
+    runs = [[t.clone() for t in ops.retina_forward(ctx, mid, x16, 270, 480)] for _ in range(3)]
+    for r in runs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], r))
+    solo = _lib.Context(0)
+    try:
+        solo.set_option(_lib.FRB_OPT_DUAL_ISSUE, 0)
+        ops.load_model(solo, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+        one = ops.retina_forward(solo, mid, x16, 270, 480)
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], one))
+    finally:
+        solo.close()
+    ops.load_model(ctx, weights.MODEL_IDS["irv1"], weights.write_blob(weights.synth_weights("irv1", 0)))
+    faces = torch.zeros(24, 160, 160, 8)
+    faces[..., :3] = torch.randn(24, 160, 160, 3, generator=torch.Generator().manual_seed(1)) * 0.5
+    f16 = faces.half().cuda()
+    e = [ops.irv1_forward(ctx, f16).clone() for _ in range(3)]
+    assert torch.equal(e[0], e[1]) and torch.equal(e[0], e[2])
