@@ -96,4 +96,5 @@ if __name__ == "__main__":
     ap.add_argument("--frames", type=int, default=48)
     ap.add_argument("--stride", type=int, default=7)
     a = ap.parse_args()
-    print(json.dumps(run(a.backbone, a.height, a.width, a.frames, stride=a.stride)))
+    out = run(a.backbone, a.height, a.width, a.frames, stride=a.stride)
+    print(json.dumps({k: (v.item() if hasattr(v, "item") else v) for k, v in out.items()}))
