@@ -78,6 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* w
   }
 }
 
+// ---------------------------------------------------------------------- programmatic dependent launch
+// wait: returns once every kernel this one depends on has completed and its writes are visible (at once when the
+// launch carried no programmatic dependency).  launch_dependents: the next kernel of the stream may start launching.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");

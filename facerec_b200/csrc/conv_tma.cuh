@@ -78,6 +78,7 @@ struct ConvTmaArgs {
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
   int dual_issue;        // 1: two MMA issuer warps take tiles alternately where the rings allow it (FRB_OPT_DUAL_ISSUE)
+  int pdl;               // 1: launched with programmatic stream serialization (FRB_OPT_PDL)
   int skip_loads;        // debug (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers, MMAs read stale tiles
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
 };
@@ -190,6 +191,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
+  // global memory and may run under the tail of the previous kernel of the stream.  The roles that touch global
+  // memory (TMA producer, epilogue) wait for that kernel below; the producer fetches the constant operands first.
+  if (p.pdl) griddep_launch_dependents();
 
   // tile -> coordinates of its first pixel
   auto decode = [&](int tile, int& n_tile, int& c1, int& c2, int& c3) {
@@ -232,6 +237,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     StallClock<kStall> sc{kStall && p.stall != nullptr && threadIdx.x == 0, 0};
     long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
+    griddep_wait();                            // the upsampled residual is read, the output written, from here
 
     struct Slab { int tile_iter, s, n0, ncols, c1, c2, c3; };
     auto slab_at = [&](int ti, int s2) {
@@ -677,6 +683,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
             tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
       if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
     }
+    griddep_wait();                      // weights and identity are constants; activations are the previous kernel's
     const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
     const uint32_t halo_tx = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {

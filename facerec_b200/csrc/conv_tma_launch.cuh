@@ -11,8 +11,17 @@ static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, c
   auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kernel<<<grid, kTmaThreads, smem, st>>>(a, tmA, tmB, tmO, tmR, tmI);
-  return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTmaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = a.pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a, tmA, tmB, tmO, tmR, tmI);
 }
 
 // res: ConvRes of the launch; act: 0 per-channel slope, 1 ReLU, 2 linear (an upsampled residual always takes 0)

@@ -234,6 +234,15 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.stall = ctx->trace_mode != 0 ? ctx->trace_dev : nullptr;
   a.skip_loads = ctx->skip_loads;
   a.dual_issue = ctx->dual_issue;
+  {
+    // Programmatic dependent launch pays where launches are short: InceptionResnetV1's 105 launches of 15-35 us gain
+    // 2.6 us each, the 0.3-1.5 ms launches of RetinaFace-R50 at 1080p lose ~5 us each, with either trigger placement
+    // (profiles/r01_pdl_ab.txt).  Estimated duration: the larger of the tensor time and the HBM time of the launch.
+    const double flop = 2.0 * static_cast<double>(M) * L.Cout * L.kh * L.kw * L.Cin;
+    const double bytes = 2.0 * static_cast<double>(M) * (L.Cout + static_cast<double>(L.Cin) / (L.sh * L.sw));
+    const double est_us = std::max(flop / 6.0e8, bytes / 5.0e6);
+    a.pdl = !ctx->layer_times && (ctx->pdl == 2 || (ctx->pdl == 1 && est_us < 100.0));
+  }
   if (ctx->trace_dev) cudaMemsetAsync(ctx->trace_dev, 0, 8, stream);
 
   CUtensorMap tmA, tmO, tmR, tmI;
@@ -489,6 +498,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       return FRB_OK;
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_DUAL_ISSUE: ctx->dual_issue = value; return FRB_OK;
+    case FRB_OPT_PDL: ctx->pdl = value; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;
     case FRB_OPT_TRACE:

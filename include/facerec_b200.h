@@ -62,6 +62,8 @@ enum frb_option {
   FRB_OPT_LAYER_TIMES = 6, /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
   FRB_OPT_MAX_STAGES = 7,  /* cap on the conv_tma stage ring depth (>= 2; experiments)                          */
   FRB_OPT_DUAL_ISSUE = 9,  /* 0: a single MMA issuer warp per CTA (default 1: two, alternating tiles, where safe)   */
+  FRB_OPT_PDL = 10,        /* programmatic dependent launch of the conv kernels (set-up under the previous kernel's   */
+                           /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
   FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 

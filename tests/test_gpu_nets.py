@@ -93,3 +93,33 @@ def test_forwards_are_bit_reproducible(ctx):
     f16 = faces.half().cuda()
     e = [ops.irv1_forward(ctx, f16).clone() for _ in range(3)]
     assert torch.equal(e[0], e[1]) and torch.equal(e[0], e[2])
+
+
+@pytest.mark.parametrize("pdl", [0, 2])
+def test_dependent_launch_policy_does_not_change_results(ctx, pdl):
+    """FRB_OPT_PDL only moves a kernel's set-up under the previous kernel's tail: plain stream order (0), the default
+    (short launches only) and 'always' (2) give the same bits, back to back, for both networks."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(5)
+    fr = torch.from_numpy(_frames(rng, 2, 270, 480)).cuda()
+    mid = weights.MODEL_IDS["retina_r50"]
+    irv1 = weights.MODEL_IDS["irv1"]
+    faces = torch.zeros(40, 160, 160, 8)
+    faces[..., :3] = torch.randn(40, 160, 160, 3, generator=torch.Generator().manual_seed(2)) * 0.5
+    f16 = faces.half().cuda()
+    outs = []
+    for c, opt in ((ctx, None), (_lib.Context(0), pdl)):
+        try:
+            if opt is not None:
+                c.set_option(_lib.FRB_OPT_PDL, opt)
+            ops.load_model(c, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+            ops.load_model(c, irv1, weights.write_blob(weights.synth_weights("irv1", 0)))
+            x16 = ops.preprocess_u8(c, fr, True, ops.input_layout(mid))
+            res = []
+            for _ in range(3):                      # back to back: set-up of launch k+1 overlaps the tail of launch k
+                res = [t.clone() for t in ops.retina_forward(c, mid, x16, 270, 480)] + [ops.irv1_forward(c, f16).clone()]
+            outs.append(res)
+        finally:
+            if opt is not None:
+                c.close()
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
