@@ -48,6 +48,10 @@ constexpr int kGroupThreads = 128;
 constexpr int kOutBufs = kEpiGroups;       // one staging slab per group
 constexpr int kMaxAcc = 4;                 // TMEM accumulator buffers: 4 for BN <= 128, else 2
 constexpr int kResidentWeightBytes = 80 * 1024;
+// One N tile's weights resident per CTA (b_resident = 2).  The 32 KB slices of layer2's conv3 + skip take those launches
+// from 0.97 to 0.75 ms (HBM-bound at 6.4 TB/s); the 64 KB slice of layer3's conv3 measured neutral: it costs ring depth
+// and with it the second MMA issuer (profiles/r01_pdl_ab.txt).
+constexpr int kResidentSliceBytes = 48 * 1024;
 constexpr int kIdentBytes = 64 * 128;      // identity B operand of the residual MMAs
 
 struct ConvTmaArgs {
@@ -62,7 +66,8 @@ struct ConvTmaArgs {
   int a_bytes;           // bytes one A box delivers (= patch pixels * 128)
   int stages;
   int kbps;              // 64-wide k-blocks per pipeline stage (2 halves the barrier round trips per unit of K)
-  int b_resident;        // whole weight matrix stays in shared memory (n_tiles * num_kb blocks of BN x 64)
+  int b_resident;        // 1: whole weight matrix stays in shared memory (n_tiles * num_kb blocks of BN x 64); 2: only the
+                         // N tile of this CTA (the grid is a multiple of n_tiles, so a CTA never sees another one)
   int halo;              // 1: stride-1 k x k conv fed from ONE halo tile per 64-channel block (see below)
   int kh;                // filter rows (halo mode walks taps itself)
   int halo_w, halo_h;    // halo tile = (bh + kh - 1) x (bw + kw - 1) pixels of 128 B
@@ -125,7 +130,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int b_stage_bytes = p.BN * 128;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * p.kbps * kAStageBytes);   // ring (or resident matrix)
-  uint8_t* smem_o = smem_b + (p.b_resident ? p.n_tiles * p.num_kb : p.stages * (p.halo ? p.brow : p.kbps)) * b_stage_bytes;
+  const int res_nts = p.b_resident == 2 ? 1 : p.n_tiles;                                // resident N tiles and the first of them
+  const int res_nt0 = p.b_resident == 2 ? static_cast<int>(blockIdx.x) % p.n_tiles : 0;
+  uint8_t* smem_o = smem_b + (p.b_resident ? res_nts * p.num_kb : p.stages * (p.halo ? p.brow : p.kbps)) * b_stage_bytes;
   uint8_t* smem_i = smem_o + kOutBufs * kSlabBytes;                                    // 64 x 64 identity (kRes = 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_i + (kRes == 1 ? kIdentBytes : 0));
   uint64_t* full_bar = bars;                          // [kMaxStages]
@@ -455,7 +462,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         if (dual && tile_iter > 0) mbar_wait_a(turn_other, static_cast<uint32_t>((tile_iter - 1) >> 1) & 1u, p.watchdog, 260 + 1000 * iw);
       };
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
-      const uint32_t b_res = b_lo0 + static_cast<uint32_t>(n_tile * p.num_kb) * b_step;   // resident weights of this N tile
+      const uint32_t b_res = b_lo0 + static_cast<uint32_t>((n_tile - res_nt0) * p.num_kb) * b_step;   // resident weights of this N tile
       auto mma4 = [&](uint32_t a, uint32_t b, uint32_t acc0) {          // one 64-channel tap out of a halo tile
         tc_mma_f16(d_tmem, pack_desc(a, hi_halo), pack_desc(b, hi1024), idesc, acc0);
         tc_mma_f16(d_tmem, pack_desc(a + 2, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
@@ -675,12 +682,12 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     long long st_empty = 0, st_rempty = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
     if ((p.b_resident || kRes == 1) && lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? p.n_tiles * p.num_kb * b_stage_bytes : 0) +
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? res_nts * p.num_kb * b_stage_bytes : 0) +
                                                             (kRes == 1 ? kIdentBytes : 0)));
       if (p.b_resident)
-        for (int nt = 0; nt < p.n_tiles; ++nt)
+        for (int nt = 0; nt < res_nts; ++nt)
           for (int kb = 0; kb < p.num_kb; ++kb)
-            tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, nt * p.BN);
+            tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, (res_nt0 + nt) * p.BN);
       if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
     }
     griddep_wait();                      // weights and identity are constants; activations are the previous kernel's

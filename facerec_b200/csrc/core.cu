@@ -328,7 +328,15 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   // small weight matrices (the bandwidth-bound early layers) stay resident in shared memory for the whole kernel
   const int w_bytes = L.n_tiles * a.num_kb * L.BN * 128;
   a.b_resident = w_bytes <= kResidentWeightBytes ? 1 : 0;
-  const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? w_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
+  // ... or just the N tile a CTA works on: with a grid that is a multiple of n_tiles, tile = blockIdx + k * grid keeps
+  // tile % n_tiles fixed per CTA, and the weight slice is fetched once instead of once per tile (the 1x1 expansions of
+  // layer2/3 move 1/3 fewer bytes through L2)
+  const int slice_bytes = a.num_kb * L.BN * 128;
+  if (!a.b_resident && !a.halo && ctx->weight_slice && L.n_tiles > 1 && slice_bytes <= kResidentSliceBytes &&
+      a.total_tiles >= 4 * ctx->num_sms && L.n_tiles <= ctx->num_sms / 4)
+    a.b_resident = 2;
+  const int res_bytes = a.b_resident == 2 ? slice_bytes : w_bytes;
+  const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? res_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
                          (4 * kMaxStages + 20) * 8 + 2048 + 1024;
   const int total_budget = 226 * 1024 - base_fixed;
   // residual slabs ride the ring as single extra A blocks: one k-block per stage then
@@ -353,7 +361,8 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   a.stages = stage_bytes > 0 ? std::max(2, std::min(std::min(kMaxStages, ctx->max_stages), budget / stage_bytes)) : 2;
   const size_t smem = static_cast<size_t>(a.stages) * stage_bytes + fixed;
   if (smem > 227 * 1024) return set_err(ctx, FRB_ERR_INVALID, "conv: shared-memory plan does not fit (%zu bytes)", smem);
-  const int grid = std::min(a.total_tiles, ctx->num_sms);
+  int grid = std::min(a.total_tiles, ctx->num_sms);
+  if (a.b_resident == 2) grid = grid / L.n_tiles * L.n_tiles;
   const int act = io.res_mode == RES_POST_ACT_UPSAMPLE ? 0 : L.act_kind;
   cudaError_t le;
   if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
@@ -499,6 +508,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_DUAL_ISSUE: ctx->dual_issue = value; return FRB_OK;
     case FRB_OPT_PDL: ctx->pdl = value; return FRB_OK;
+    case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;
     case FRB_OPT_TRACE:

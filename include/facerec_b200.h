@@ -64,6 +64,8 @@ enum frb_option {
   FRB_OPT_DUAL_ISSUE = 9,  /* 0: a single MMA issuer warp per CTA (default 1: two, alternating tiles, where safe)   */
   FRB_OPT_PDL = 10,        /* programmatic dependent launch of the conv kernels (set-up under the previous kernel's   */
                            /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
+  FRB_OPT_WEIGHT_SLICE = 11,/* 0: stream the weights of every tile (default 1: a CTA keeps its N tile's weights in    */
+                           /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
   FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 

@@ -52,7 +52,11 @@ CASES = [
     (3, 270, 480, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),    # ResNet layer1 conv2 at full 1080p/4 size
     (2, 40, 44, 128, 96, 7, 1, (1, 1), (3, 0), 1, 0, False),     # column filter: aligned halo tiles by default, 2 channel blocks
     (1, 50, 40, 64, 64, 4, 1, (1, 1), (2, 0), 2, 0, False),      # 4 x 1 window (the shape of the s2d stem), resident weights
+    (4, 68, 120, 128, 512, 1, 1, (1, 1), (0, 0), 1, 1, False),   # ResNet conv3 + skip with a resident weight slice per CTA
+    (4, 68, 120, 128, 576, 1, 1, (1, 1), (0, 0), 2, 0, False),   # no skip: two k-blocks per stage, three 192-wide N tiles, 147 CTAs
+    (4, 68, 120, 128, 576, 1, 1, (1, 1), (0, 0), 1, 1, False),   # nine 64-wide N tiles: grid of 144 CTAs
 ]
+SLICE_CASES = CASES[-3:]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
@@ -99,6 +103,26 @@ def test_conv2d_halo_mode_matches_torch(case):
         ref = _ref(x16, w, b, stride, pad, act, 0.1, res16, res_mode)
         err = (out.float().cpu() - ref).abs()
         assert bool((err <= 2e-3 * ref.abs() + 2e-3).all()), err.max().item()
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("case", SLICE_CASES, ids=lambda c: f"{c[4]}r{c[10]}")
+def test_conv2d_weight_slice_is_bit_identical_to_streaming(ctx, case):
+    """FRB_OPT_WEIGHT_SLICE changes where a tile's weights come from, not the order its k-blocks are accumulated in."""
+    from facerec_b200 import ops, _lib
+    B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32 = case
+    g = torch.Generator().manual_seed(7 + Cout)
+    x16 = torch.randn(B, H, W, Cin, generator=g).half().cuda()
+    w = (torch.randn(Cout, kh, kw, Cin, generator=g) / np.sqrt(Cin)).numpy().astype(np.float32)
+    res16 = torch.randn(B, H, W, Cout, generator=g).half().cuda() if res_mode == 1 else None
+    sliced, _ = ops.conv2d(ctx, x16, w, None, stride, pad, act, 0.1, res16, res_mode)
+    c = _lib.Context(0)
+    try:
+        c.set_option(_lib.FRB_OPT_WEIGHT_SLICE, 0)
+        streamed, _ = ops.conv2d(c, x16, w, None, stride, pad, act, 0.1, res16, res_mode)
+        torch.cuda.synchronize()
+        assert torch.equal(sliced, streamed)
     finally:
         c.close()
 

@@ -25,6 +25,8 @@ def main():
         ctx.set_option(_lib.FRB_OPT_DUAL_ISSUE, int(os.environ["FRB_DUAL"]))
     if os.environ.get("FRB_KBPS2"):
         ctx.set_option(_lib.FRB_OPT_KBPS2, int(os.environ["FRB_KBPS2"]))
+    if os.environ.get("FRB_SLICE"):
+        ctx.set_option(_lib.FRB_OPT_WEIGHT_SLICE, int(os.environ["FRB_SLICE"]))
     if os.environ.get("FRB_PDL"):
         ctx.set_option(_lib.FRB_OPT_PDL, int(os.environ["FRB_PDL"]))
     if os.environ.get("FRB_HALO"):

@@ -16,6 +16,7 @@ ap.add_argument("--max-stages", type=int, default=64)
 ap.add_argument("--kbps1", action="store_true")
 ap.add_argument("--skip-loads", action="store_true")
 ap.add_argument("--no-plain", action="store_true", help="skip the uninstrumented timing run")
+ap.add_argument("--slice", type=int, default=1, help="FRB_OPT_WEIGHT_SLICE")
 ap.add_argument("--issue", type=int, default=1, help="FRB_OPT_DUAL_ISSUE: 0 warp A only, 1 both, 2 warp B only")
 a = ap.parse_args()
 for shape in a.shape:
@@ -37,6 +38,7 @@ for shape in a.shape:
     plain.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
     plain.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
     plain.set_option(_lib.FRB_OPT_DUAL_ISSUE, a.issue)
+    plain.set_option(_lib.FRB_OPT_WEIGHT_SLICE, a.slice)
     ms0 = 1.0
     if not a.no_plain:
         ops.conv2d(plain, x, w, None, (s, s), (ph, pw), 1, 0.0, res, 1 if a.res else 0, iters=20)       # clocks up
@@ -50,6 +52,7 @@ for shape in a.shape:
     ctx.set_option(_lib.FRB_OPT_KBPS2, 0 if a.kbps1 else 1)
     ctx.set_option(_lib.FRB_OPT_SKIP_LOADS, int(a.skip_loads))
     ctx.set_option(_lib.FRB_OPT_DUAL_ISSUE, a.issue)
+    ctx.set_option(_lib.FRB_OPT_WEIGHT_SLICE, a.slice)
     _, ms = ops.conv2d(ctx, x, w, None, (s, s), (ph, pw), 1, 0.0, res, 1 if a.res else 0, iters=1)
     buf = np.zeros(1 + 3 * 4000, np.int64)
     ctx.check(ctx.lib.frb_debug_trace(ctx.handle, buf.ctypes.data, 4000), "trace")
