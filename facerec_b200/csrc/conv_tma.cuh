@@ -83,6 +83,7 @@ struct ConvTmaArgs {
   int res_ld, rH, rW, Ho, Wo, M;
   int* watchdog;
   int dual_issue;        // 1: two MMA issuer warps take tiles alternately where the rings allow it (FRB_OPT_DUAL_ISSUE)
+  int mpair;             // 1: halo mode, a tile is two 8-wide patches side by side under one halo tile and one weight stream
   int pdl;               // 1: launched with programmatic stream serialization (FRB_OPT_PDL)
   int skip_loads;        // debug (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers, MMAs read stale tiles
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
@@ -158,7 +159,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const int tile_stages = p.halo ? (p.b_resident ? 0 : p.cin_blocks * (p.brow > 1 ? p.kh : p.kh * p.kw))
                                  : (p.num_kb + p.kbps - 1) / p.kbps + (kRes == 1 ? nslab : 0);
   const int tile_astages = p.halo ? p.cin_blocks : 0;
-  const bool dual = p.dual_issue == 1 && 2 * tile_stages <= p.stages && (!p.halo || 2 * tile_astages <= p.a_stages);
+  const bool dual = p.dual_issue == 1 && !p.mpair && 2 * tile_stages <= p.stages && (!p.halo || 2 * tile_astages <= p.a_stages);
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(nacc * p.BN)) tmem_cols <<= 1;
 
@@ -239,7 +240,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     uint8_t* const orow = smem_o + grp * kSlabBytes + static_cast<uint32_t>(row) * 128u;
     float* const g_bias = s_bias + grp * kSlab;
     float* const g_slope = s_slope + grp * kSlab;
-    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    // (a paired tile is two accumulators = two "tiles" of this role: the same slabs, the second 8 pixels to the right)
+    const int my_tiles = ((p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x))
+                         << (p.mpair ? 1 : 0);
     const int my_slabs = my_tiles * nslab;
     StallClock<kStall> sc{kStall && p.stall != nullptr && threadIdx.x == 0, 0};
     long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
@@ -250,7 +253,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     auto slab_at = [&](int ti, int s2) {
       Slab sl;
       int nt;
-      decode(blockIdx.x + ti * gridDim.x, nt, sl.c1, sl.c2, sl.c3);
+      decode(blockIdx.x + (p.mpair ? ti >> 1 : ti) * gridDim.x, nt, sl.c1, sl.c2, sl.c3);
+      if (p.mpair) sl.c1 += (ti & 1) * 8;
       sl.tile_iter = ti;
       sl.s = s2;
       sl.n0 = nt * p.BN + s2 * kSlab;
@@ -449,12 +453,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
     for (int tile = dual ? blockIdx.x + iw * gridDim.x : (iw == solo ? static_cast<int>(blockIdx.x) : p.total_tiles);
          tile < p.total_tiles; tile += tstep * gridDim.x, tile_iter += tstep) {
-      const int buf = tile_iter & (nacc - 1);
-      const uint32_t tphase = static_cast<uint32_t>(tile_iter >> nacc_shift) & 1u;
+      const int acc_iter = p.mpair ? 2 * tile_iter : tile_iter;          // a paired tile fills two accumulator buffers
+      const int buf = acc_iter & (nacc - 1);
+      const uint32_t tphase = static_cast<uint32_t>(acc_iter >> nacc_shift) & 1u;
       const int n_tile = tile - fastdiv(tile, p.fd_n) * p.n_tiles;
       if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 1;
       sc.start();
       mbar_wait_a(tempty0 + buf * 8, tphase ^ 1, p.watchdog, 200 + buf + 1000 * iw);
+      if (p.mpair) mbar_wait_a(tempty0 + (buf + 1) * 8, tphase ^ 1, p.watchdog, 201 + buf + 1000 * iw);
       sc.stop(st_tempty);
       tc_fence_after();
       if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + iw] = tile_iter * 10 + 2;
@@ -468,6 +474,17 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         tc_mma_f16(d_tmem, pack_desc(a + 2, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
         tc_mma_f16(d_tmem, pack_desc(a + 4, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
         tc_mma_f16(d_tmem, pack_desc(a + 6, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
+        if (p.mpair) {                                                   // the patch 8 pixels (8 x 128 B) to the right
+          const uint32_t d2 = d_tmem + static_cast<uint32_t>(p.BN);
+          tc_mma_f16(d2, pack_desc(a + 64, hi_halo), pack_desc(b, hi1024), idesc, acc0);
+          tc_mma_f16(d2, pack_desc(a + 66, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
+          tc_mma_f16(d2, pack_desc(a + 68, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
+          tc_mma_f16(d2, pack_desc(a + 70, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
+        }
+      };
+      auto commit_tile = [&]() {                                         // accumulator(s) complete -> epilogue
+        tc_commit_a(tfull0 + buf * 8);
+        if (p.mpair) tc_commit_a(tfull0 + (buf + 1) * 8);
       };
       const uint32_t row_a = static_cast<uint32_t>(p.halo_w) * 8u;             // next halo row (descriptor units of 16 B)
       if (p.halo && p.b_resident) {
@@ -506,7 +523,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               }
             }
             tc_commit_a(aempty0 + astage * 8);
-            if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+            if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
           }
           __syncwarp();
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
@@ -540,7 +557,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               tc_commit_a(empty0 + stage * 8);
               if (tr == p.kh - 1) {
                 tc_commit_a(aempty0 + astage * 8);
-                if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+                if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
               }
             }
             __syncwarp();
@@ -575,14 +592,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               }
               const bool last_tap = tr == p.kh - 1 && ts == p.kw - 1;
               if (elect_one()) {
-                tc_mma_f16(d_tmem, pack_desc(a_tap, hi_halo), pack_desc(b_tap, hi1024), idesc, acc);
-                tc_mma_f16(d_tmem, pack_desc(a_tap + 2, hi_halo), pack_desc(b_tap + 2, hi1024), idesc, 1u);
-                tc_mma_f16(d_tmem, pack_desc(a_tap + 4, hi_halo), pack_desc(b_tap + 4, hi1024), idesc, 1u);
-                tc_mma_f16(d_tmem, pack_desc(a_tap + 6, hi_halo), pack_desc(b_tap + 6, hi1024), idesc, 1u);
+                mma4(a_tap, b_tap, acc);
                 if (!p.b_resident) tc_commit_a(empty0 + stage * 8);
                 if (last_tap) {
                   tc_commit_a(aempty0 + astage * 8);
-                  if (kRes != 1 && cb == p.cin_blocks - 1) tc_commit_a(tfull0 + buf * 8);
+                  if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
                 }
               }
               __syncwarp();

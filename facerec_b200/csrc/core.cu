@@ -291,7 +291,22 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
       const bool row_fits = L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * halo_bytes <=
                                             226 * 1024 - (kOutBufs * kSlabBytes + (4 * kMaxStages + 20) * 8 + 2048 + 1024);
       const bool want = ctx->halo_mode > 0 || resident_w || (row_fits && eff_halo >= 0.9 * eff_patch);
-      if (want && eff_halo >= 0.85 * eff_patch) {
+      // streamed weights, TWO 8 x 16 patches side by side per tile (one (16 + kw - 1)-wide halo tile, two accumulators):
+      // every weight stage (one tap) feeds two M = 128 MMAs, i.e. half the weight bytes through L2 per output pixel and
+      // twice the MMAs per barrier wait.  Pays for N tiles of 192 / 256 (FPN merge1 1.98 -> 1.85 ms, SSH1 3x3 1.73 ->
+      // 1.59 ms); with N = 128 it replaces the row-per-stage path (12 MMAs per wait) by 8 per wait and loses 8 %
+      // (profiles/r01_pdl_ab.txt).
+      const double eff_pair = static_cast<double>(Ho) * Wo / (256.0 * ((Wo + 15) / 16) * ((Ho + 15) / 16));
+      const bool pair = !resident_w && (ctx->mpair == 2 || (ctx->mpair == 1 && L.BN >= 192)) && eff_pair >= 0.85 * eff_patch;
+      if (pair) {
+        a.halo = 1;
+        a.mpair = 1;
+        a.bw = 16; a.bh = 16; a.bb = 1;
+        a.kh = L.kh;
+        a.halo_w = 16 + L.kw - 1;
+        a.halo_h = 16 + L.kh - 1;
+        a.halo_bytes = (a.halo_w * a.halo_h * 128 + 1023) & ~1023;
+      } else if (want && eff_halo >= 0.85 * eff_patch) {
         a.halo = 1;
         a.bw = 8; a.bh = 16; a.bb = 1;
         a.kh = L.kh;
@@ -314,7 +329,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     } else if (a.halo) {
       if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.halo_w, a.halo_h, 1, 1, 1)) != FRB_OK) return rc;
     } else if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
-    if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
+    if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.mpair ? 8 : a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
     tmR = tmO;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_patch(ctx, &tmR, io.res, L.Cout, Wo, Ho, io.B, io.res_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK)
@@ -508,6 +523,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_LAYER_TIMES: ctx->layer_times = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_DUAL_ISSUE: ctx->dual_issue = value; return FRB_OK;
     case FRB_OPT_PDL: ctx->pdl = value; return FRB_OK;
+    case FRB_OPT_MPAIR: ctx->mpair = value; return FRB_OK;
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;

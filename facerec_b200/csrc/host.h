@@ -30,6 +30,7 @@ struct frb_ctx {
   int force_gather = 0;        // debugging: never use the TMA A path
   void* d_ident[2] = {nullptr, nullptr};   // 64 x 64 identity (fp16, bf16): B operand of the residual MMAs
   int dual_issue = 1;          // FRB_OPT_DUAL_ISSUE
+  int mpair = 1;               // FRB_OPT_MPAIR: 0 never, 1 for N tiles of 192 and more, 2 wherever possible
   int weight_slice = 1;        // FRB_OPT_WEIGHT_SLICE
   int pdl = 1;                 // FRB_OPT_PDL: 0 never, 1 short launches, 2 always
   int skip_loads = 0;          // FRB_OPT_SKIP_LOADS: timing experiment, results are garbage

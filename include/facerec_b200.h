@@ -66,6 +66,8 @@ enum frb_option {
                            /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
   FRB_OPT_WEIGHT_SLICE = 11,/* 0: stream the weights of every tile (default 1: a CTA keeps its N tile's weights in    */
                            /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
+  FRB_OPT_MPAIR = 12,      /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
+                           /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
   FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 

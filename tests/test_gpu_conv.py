@@ -84,14 +84,17 @@ def test_conv2d_matches_torch(ctx, case):
     assert bool((err <= tol).all()), f"max err {err.max().item():.4g} at ref {ref.flatten()[err.argmax()].item():.4g}"
 
 
+@pytest.mark.parametrize("pair", [0, 2], ids=["single", "paired"])
 @pytest.mark.parametrize("case", [c for c in CASES if c[5] * c[6] > 1 and c[7] == (1, 1) and c[3] % 64 == 0],
                          ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}")
-def test_conv2d_halo_mode_matches_torch(case):
-    """FRB_OPT_HALO: stride-1 k x k convs fed from one halo tile per channel block (shifted UMMA descriptors)."""
+def test_conv2d_halo_mode_matches_torch(case, pair):
+    """FRB_OPT_HALO: stride-1 k x k convs fed from one halo tile per channel block (shifted UMMA descriptors);
+    FRB_OPT_MPAIR: two patches per halo tile and weight stage where the weights are streamed."""
     from facerec_b200 import ops, _lib
     c = _lib.Context(0)
     try:
         c.set_option(_lib.FRB_OPT_HALO, 1)
+        c.set_option(_lib.FRB_OPT_MPAIR, pair)
         B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32 = case
         g = torch.Generator().manual_seed(99 + Cin + Cout)
         x16 = torch.randn(B, H, W, Cin, generator=g).half().cuda()

@@ -27,6 +27,10 @@ def main():
         ctx.set_option(_lib.FRB_OPT_KBPS2, int(os.environ["FRB_KBPS2"]))
     if os.environ.get("FRB_SLICE"):
         ctx.set_option(_lib.FRB_OPT_WEIGHT_SLICE, int(os.environ["FRB_SLICE"]))
+    if os.environ.get("FRB_BN_CAP"):
+        ctx.set_option(_lib.FRB_OPT_BN_CAP, int(os.environ["FRB_BN_CAP"]))
+    if os.environ.get("FRB_MPAIR"):
+        ctx.set_option(_lib.FRB_OPT_MPAIR, int(os.environ["FRB_MPAIR"]))
     if os.environ.get("FRB_PDL"):
         ctx.set_option(_lib.FRB_OPT_PDL, int(os.environ["FRB_PDL"]))
     if os.environ.get("FRB_HALO"):
