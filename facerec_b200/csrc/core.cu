@@ -283,8 +283,14 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     //  * streamed weights, one tap per stage (BN > 128): a wash, on request only.
     // FRB_OPT_HALO = 1 forces it wherever it is possible, -1 turns it off.
     if (ctx->halo_mode >= 0 && io.res_mode != RES_PRE_ACT && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1 && (L.Cin % kBK) == 0) {
-      const double eff_patch = static_cast<double>(io.B) * Ho * Wo /
-                               (128.0 * ((Wo + a.bw - 1) / a.bw) * ((Ho + a.bh - 1) / a.bh) * ((io.B + a.bb - 1) / a.bb));
+      // The per-tap path adds taps-major, the halo paths channel-block-major: which one a layer takes must not depend
+      // on the batch size, or a frame's bits would depend on its batch.  The patch efficiency the halo tiles are
+      // compared with is therefore the one of a reference batch of 64 images.
+      constexpr int kRefBatch = 64;
+      int rw, rh, rb;
+      pick_patch(kRefBatch, Ho, Wo, L.sw, L.sh, rw, rh, rb);
+      const double eff_patch = static_cast<double>(kRefBatch) * Ho * Wo /
+                               (128.0 * ((Wo + rw - 1) / rw) * ((Ho + rh - 1) / rh) * ((kRefBatch + rb - 1) / rb));
       const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
       const int halo_bytes = ((8 + L.kw - 1) * (16 + L.kh - 1) * 128 + 1023) & ~1023;
       const bool resident_w = L.n_tiles * L.kh * L.kw * ((L.Cin + kBK - 1) / kBK) * L.BN * 128 <= kResidentWeightBytes;
