@@ -61,14 +61,14 @@ enum frb_option {
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
   FRB_OPT_LAYER_TIMES = 6, /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
   FRB_OPT_MAX_STAGES = 7,  /* cap on the conv_tma stage ring depth (>= 2; experiments)                          */
+  FRB_OPT_SKIP_LOADS = 8,  /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
   FRB_OPT_DUAL_ISSUE = 9,  /* 0: a single MMA issuer warp per CTA (default 1: two, alternating tiles, where safe)   */
   FRB_OPT_PDL = 10,        /* programmatic dependent launch of the conv kernels (set-up under the previous kernel's   */
                            /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
   FRB_OPT_WEIGHT_SLICE = 11,/* 0: stream the weights of every tile (default 1: a CTA keeps its N tile's weights in    */
                            /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
-  FRB_OPT_MPAIR = 12,      /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
+  FRB_OPT_MPAIR = 12       /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
                            /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
-  FRB_OPT_SKIP_LOADS = 8   /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
