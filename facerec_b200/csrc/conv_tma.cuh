@@ -23,8 +23,18 @@
 // the A descriptor of tap (r, s) at pixel (r, s) of that tile: 8-row groups are 8 consecutive pixels of a halo
 // row (bw = 8), the stride between groups is the halo row pitch.  The 128-byte swizzle is a function of the
 // shared-memory ADDRESS (tools/umma_shift_probe.cu: any 128-byte row offset and any group stride read back
-// exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold.  Optional
-// (FRB_OPT_HALO) and off by default: it measures 5-9 % SLOWER than one box per tap on every layer tried.
+// exactly what TMA wrote), so shifted windows need no copy.  A traffic through L2 drops k*k-fold, and the issuer
+// waits once per channel block (resident weights: all taps under one wait) or once per filter row (streamed weights,
+// kw taps per B stage) instead of once per tap.  Default where it pays (conv_launch_tma), FRB_OPT_HALO overrides.
+// Paired tiles (FRB_OPT_MPAIR, streamed weights with N tiles >= 192): a tile is TWO 8 x 16 patches side by side under
+// one (16+kw-1)-wide halo tile; every weight stage feeds two M = 128 MMAs into two accumulator buffers, which the
+// epilogue treats as two ordinary tiles.  Half the weight bytes through L2 per pixel, twice the MMAs per wait.
+//
+// Weight slice (FRB_OPT_WEIGHT_SLICE): when the grid is a multiple of the number of N tiles, tile % n_tiles is the
+// same for every tile of a CTA, and a slice of up to 48 KB is loaded once like the small matrices above.
+//
+// Programmatic dependent launch (FRB_OPT_PDL, short launches only): barrier init, TMEM allocation, descriptor
+// prefetch and the resident-weight loads run before griddepcontrol.wait, i.e. under the previous kernel's tail.
 //
 // Warp roles (480 threads, 15 warps = at most 4 per scheduler, i.e. up to 128 registers per thread: with ~227 KB
 // of shared memory there is no L1 left and a spill is an L2 round trip): warps 0-11 are
