@@ -126,6 +126,11 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, name), name
     assert lib.frb_version() == 100
     assert lib.frb_num_priors(1080, 1920) == 85200
+    # every enumerator of the header has the same value in the ctypes mirror, and the other way round
+    enums = {k: int(v) for k, v in re.findall(r"\b(FRB_[A-Z0-9_]+)\s*=\s*(-?\d+)", header)}
+    mirror = {k: v for k, v in vars(_lib).items() if k.startswith("FRB_") and isinstance(v, int)}
+    assert enums and {k: enums.get(k) for k in mirror} == mirror, set(enums.items()) ^ set(mirror.items())
+    assert {k for k in enums if k.startswith("FRB_OPT_")} == {k for k in mirror if k.startswith("FRB_OPT_")}
 
 
 def test_product_fails_loudly_without_gpu():
