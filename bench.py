@@ -350,8 +350,8 @@ def run_b200(a):
                          "frac": fwd_tflops / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum over the 71 launches of one forward (64 x 1080p,
                          # R50), ncu metrics pass of tools/forward_once.py: profiles/r01_ncu_conv_tma_v5.md
-                         "traffic": 157.0e9 if (a.backbone, B, H, W) == ("r50", 64, 1080, 1920) else None,
-                         "traffic_unit": "bytes per forward (94.5 GB read + 62.5 GB write; algorithmic minimum 2.60 GB/frame x 64 = 166 GB)",
+                         "traffic": 157.5e9 if (a.backbone, B, H, W) == ("r50", 64, 1080, 1920) else None,
+                         "traffic_unit": "bytes per forward, ncu dram__bytes of the 71 launches (94.9 GB read + 62.6 GB written, profiles/r01_fwd_launches_v15.csv; algorithmic minimum 2.60 GB/frame x 64 = 166 GB)",
                          "kernel": f"conv_tma_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
