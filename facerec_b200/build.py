@@ -17,12 +17,16 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfacerec_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "conv_tma_stall.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
+SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
            "linkage.cu", "sort.cu", "jsonfmt.cu", "api.cu"]
+# FRB_DEBUG_BUILD=1: the tuning experiments of include/facerec_b200_debug.h (stall-accounting kernel variants, skipped loads)
+DEBUG_BUILD = os.environ.get("FRB_DEBUG_BUILD", "0") not in ("", "0")
+if DEBUG_BUILD:
+    SOURCES.insert(3, "conv_tma_stall.cu")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
-]
+] + (["-DFRB_DEBUG_BUILD"] if DEBUG_BUILD else [])
 
 
 def _nvcc() -> str:
@@ -47,6 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "facerec_b200.h"))
+    deps.append(os.path.join(ROOT, "include", "facerec_b200_debug.h"))
     stamp = os.path.join(OBJ_DIR, "stamp")
     dig = _digest(deps)
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:

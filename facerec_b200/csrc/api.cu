@@ -12,6 +12,18 @@ using namespace frb;
     if (!(cond)) return set_err((ctx), FRB_ERR_INVALID, "%s", (msg)); \
   } while (0)
 
+// Every entry point runs on the context's device whatever the caller's current device is (two contexts on two GPUs in
+// one process are legal); the work itself goes to the caller's stream, which must belong to that device.  A context is
+// meant to be driven from ONE stream at a time: the per-network activation arena and the scratch buffers are shared by
+// all calls on the context.
+#define FRB_ENTER(ctx)                                                        \
+  do {                                                                        \
+    if ((ctx) == nullptr) return FRB_ERR_INVALID;                             \
+    int _cur = -1;                                                            \
+    if (cudaGetDevice(&_cur) != cudaSuccess || _cur != (ctx)->device)         \
+      FRB_CUDA((ctx), cudaSetDevice((ctx)->device));                          \
+  } while (0)
+
 static Net* find_net(frb_ctx* ctx, int model_id) {
   auto it = ctx->nets.find(model_id);
   return it == ctx->nets.end() ? nullptr : it->second;
@@ -20,7 +32,7 @@ static Net* find_net(frb_ctx* ctx, int model_id) {
 extern "C" {
 
 int frb_load_model(frb_ctx* ctx, int model_id, const void* h_blob, size_t bytes) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, h_blob != nullptr && bytes > 0, "frb_load_model: empty blob");
   FRB_NEED(ctx, model_id >= FRB_RETINA_MNET025 && model_id <= FRB_IRV1, "frb_load_model: unknown model id");
   Net* net = build_net(ctx, model_id, h_blob, bytes);
@@ -49,7 +61,7 @@ size_t frb_input_elems(int layout, int B, int H, int W) {
 
 int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int layout,
                       void* d_out16, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_frames && d_out16 && B > 0 && H > 0 && W > 0, "frb_preprocess_u8: bad arguments");
   if (layout == FRB_LAYOUT_S2D16)
     return launch_preprocess_s2d(ctx, d_frames, B, H, W, src_is_rgb, d_out16, static_cast<cudaStream_t>(stream));
@@ -59,7 +71,7 @@ int frb_preprocess_u8(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W
 
 int frb_retina_forward(frb_ctx* ctx, int model_id, const void* d_in16, int B, int H, int W, float* d_loc, float* d_conf,
                        float* d_landm, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, model_id == FRB_RETINA_MNET025 || model_id == FRB_RETINA_R50, "frb_retina_forward: not a RetinaFace model id");
   FRB_NEED(ctx, d_in16 && d_loc && d_conf && d_landm, "frb_retina_forward: null pointer");
   Net* net = find_net(ctx, model_id);
@@ -70,7 +82,7 @@ int frb_retina_forward(frb_ctx* ctx, int model_id, const void* d_in16, int B, in
 int frb_prior_decode_filter(frb_ctx* ctx, const float* d_loc, const float* d_conf, const float* d_landm, int B, int H,
                             int W, float score_thr, int max_cand, float* d_cand, int32_t* d_count, int32_t* d_prior_idx,
                             void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_loc && d_conf && d_landm && d_cand && d_count && d_prior_idx, "frb_prior_decode_filter: null pointer");
   FRB_NEED(ctx, H > 0 && W > 0, "frb_prior_decode_filter: bad frame size");
   return launch_prior_decode_filter(ctx, d_loc, d_conf, d_landm, B, H, W, score_thr, max_cand, d_cand, d_count,
@@ -79,7 +91,7 @@ int frb_prior_decode_filter(frb_ctx* ctx, const float* d_loc, const float* d_con
 
 int frb_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
             float iou_thr, int legacy_plus_one, int32_t* d_keep, int32_t* d_nkeep, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_cand && d_count && d_prior_idx && d_keep && d_nkeep, "frb_nms: null pointer");
   return launch_nms(ctx, d_cand, d_count, d_prior_idx, B, max_cand, iou_thr, legacy_plus_one, d_keep, d_nkeep,
                     static_cast<cudaStream_t>(stream));
@@ -87,7 +99,7 @@ int frb_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int
 
 int frb_gather_kept(frb_ctx* ctx, const float* d_cand, const int32_t* d_keep, const int32_t* d_nkeep, int B, int max_cand,
                     int max_out, float* d_out, int32_t* d_nout, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_cand && d_keep && d_nkeep && d_out && d_nout, "frb_gather_kept: null pointer");
   return launch_gather_kept(ctx, d_cand, d_keep, d_nkeep, B, max_cand, max_out, d_out, d_nout,
                             static_cast<cudaStream_t>(stream));
@@ -95,14 +107,14 @@ int frb_gather_kept(frb_ctx* ctx, const float* d_cand, const int32_t* d_keep, co
 
 int frb_crop_resize_std(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, const int32_t* d_boxes, int F,
                         void* d_out16, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_frames_rgb && (F == 0 || (d_boxes && d_out16)), "frb_crop_resize_std: null pointer");
   FRB_NEED(ctx, B > 0 && H > 0 && W > 0 && F >= 0, "frb_crop_resize_std: bad shape");
   return launch_crop_resize(ctx, d_frames_rgb, B, H, W, d_boxes, F, 8, d_out16, static_cast<cudaStream_t>(stream));
 }
 
 int frb_irv1_forward(frb_ctx* ctx, const void* d_in16, int F, float* d_emb, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_in16 && d_emb, "frb_irv1_forward: null pointer");
   Net* net = find_net(ctx, FRB_IRV1);
   if (net == nullptr) return set_err(ctx, FRB_ERR_STATE, "frb_irv1_forward: InceptionResnetV1 not loaded");
@@ -111,7 +123,7 @@ int frb_irv1_forward(frb_ctx* ctx, const void* d_in16, int F, float* d_emb, void
 
 int frb_scene_stats(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int W, int crop, const uint8_t* d_prev_frame,
                     const double* d_prev_cdf, uint32_t* d_hist, double* d_cdf, double* d_sums, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_frames_rgb && d_hist && d_cdf && d_sums, "frb_scene_stats: null pointer");
   FRB_NEED(ctx, (d_prev_frame == nullptr) == (d_prev_cdf == nullptr), "frb_scene_stats: prev frame and prev cdf go together");
   return run_scene_stats(ctx, d_frames_rgb, B, H, W, crop, d_prev_frame, d_prev_cdf, d_hist, d_cdf, d_sums,
@@ -119,33 +131,33 @@ int frb_scene_stats(frb_ctx* ctx, const uint8_t* d_frames_rgb, int B, int H, int
 }
 
 int frb_segment_mean(frb_ctx* ctx, const float* d_X, const int32_t* d_offsets, int S, int D, float* d_out, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, S == 0 || (d_X && d_offsets && d_out), "frb_segment_mean: null pointer");
   return run_segment_mean(ctx, d_X, d_offsets, S, D, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int frb_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_X && d_out, "frb_pdist: null pointer");
   return run_pdist(ctx, d_X, N, D, row0, rows, layout, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int frb_linkage_complete(frb_ctx* ctx, float* d_D, int N, int32_t* d_merge_pairs, float* d_merge_dist, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, d_D && d_merge_pairs && d_merge_dist, "frb_linkage_complete: null pointer");
   return run_linkage_complete(ctx, d_D, N, d_merge_pairs, d_merge_dist, static_cast<cudaStream_t>(stream));
 }
 
 int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k, int32_t* d_idx,
                  float* d_dist, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, Q == 0 || (d_Q && d_DB && d_idx && d_dist), "frb_knn_topk: null pointer");
   return run_knn_topk(ctx, d_Q, Q, d_DB, M, D, k, d_idx, d_dist, static_cast<cudaStream_t>(stream));
 }
 
 int frb_knn_vote(frb_ctx* ctx, const int32_t* d_idx, const int32_t* d_label_idx, int Q, int k, int n_classes,
                  float* d_proba, void* stream) {
-  if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_ENTER(ctx);
   FRB_NEED(ctx, Q == 0 || (d_idx && d_label_idx && d_proba), "frb_knn_vote: null pointer");
   return run_knn_vote(ctx, d_idx, d_label_idx, Q, k, n_classes, d_proba, static_cast<cudaStream_t>(stream));
 }

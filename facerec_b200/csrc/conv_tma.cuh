@@ -95,7 +95,7 @@ struct ConvTmaArgs {
   int dual_issue;        // 1: two MMA issuer warps take tiles alternately where the rings allow it (FRB_OPT_DUAL_ISSUE)
   int mpair;             // 1: halo mode, a tile is two 8-wide patches side by side under one halo tile and one weight stream
   int pdl;               // 1: launched with programmatic stream serialization (FRB_OPT_PDL)
-  int skip_loads;        // debug (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers, MMAs read stale tiles
+  int skip_loads;        // debug build, stall variants only (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
 };
 
@@ -777,13 +777,13 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           sc.start();
           mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
           sc.stop(st_empty);
-          if (p.skip_loads) {
+          if (kStall && p.skip_loads) {
             if (elect_one()) mbar_arrive(&full_bar[stage]);
           } else if (elect_one()) {
             mbar_expect_tx_a(full0 + stage * 8, tx_bytes * static_cast<uint32_t>(nk));
           }
           for (int j = 0; j < nk; ++j) {
-            if (!p.skip_loads && elect_one()) {
+            if (!(kStall && p.skip_loads) && elect_one()) {
               if (!p.b_resident) tma_load_2d_a(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, full0 + stage * 8, kcoord, n_coord);
               if (p.patch) tma_load_4d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, cb * kBK, aw + tap_s, ah + tap_r, c3);
               else tma_load_2d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, kcoord, c1);

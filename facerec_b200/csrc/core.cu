@@ -386,8 +386,11 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (a.b_resident == 2) grid = grid / L.n_tiles * L.n_tiles;
   const int act = io.res_mode == RES_POST_ACT_UPSAMPLE ? 0 : L.act_kind;
   cudaError_t le;
+#ifdef FRB_DEBUG_BUILD
   if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
-  else if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  else
+#endif
+  if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
   else le = conv_tma_launch_f16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
   FRB_CUDA(ctx, le);
   ctx->launches++;
@@ -520,7 +523,6 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
       if (value < 16 || value > 256 || value % 16) return set_err(ctx, FRB_ERR_INVALID, "bn_cap must be 16..256 step 16");
       ctx->bn_cap = value;
       return FRB_OK;
-    case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_HALO: ctx->halo_mode = value > 0 ? 1 : (value < 0 ? -1 : 0); return FRB_OK;
     case FRB_OPT_KBPS2:
       ctx->kbps2 = value ? 1 : 0;
@@ -531,6 +533,14 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_PDL: ctx->pdl = value; return FRB_OK;
     case FRB_OPT_MPAIR: ctx->mpair = value; return FRB_OK;
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
+#ifndef FRB_DEBUG_BUILD
+    case FRB_OPT_FORCE_GATHER:
+    case FRB_OPT_SKIP_LOADS:
+    case FRB_OPT_MAX_STAGES:
+    case FRB_OPT_TRACE:
+      return set_err(ctx, FRB_ERR_STATE, "option %d is a tuning experiment of the debug build (include/facerec_b200_debug.h)", option);
+#else
+    case FRB_OPT_FORCE_GATHER: ctx->force_gather = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_SKIP_LOADS: ctx->skip_loads = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_MAX_STAGES: ctx->max_stages = value < 2 ? 2 : value; return FRB_OK;
     case FRB_OPT_TRACE:
@@ -542,6 +552,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
         ctx->trace_dev = nullptr;
       }
       return FRB_OK;
+#endif
   }
   return set_err(ctx, FRB_ERR_INVALID, "unknown option %d", option);
 }
@@ -549,7 +560,8 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
 long long frb_launch_count(frb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records) {
-  if (ctx == nullptr || h_out == nullptr || ctx->trace_dev == nullptr) return FRB_ERR_INVALID;
+  if (ctx == nullptr || h_out == nullptr) return FRB_ERR_INVALID;
+  if (ctx->trace_dev == nullptr) return set_err(ctx, FRB_ERR_STATE, "frb_debug_trace: FRB_OPT_TRACE is off (debug build only)");
   if (cudaDeviceSynchronize() != cudaSuccess) return FRB_ERR_CUDA;
   const int n = std::min(max_records, 4000);
   if (cudaMemcpy(h_out, ctx->trace_dev, (1 + 3 * static_cast<size_t>(n)) * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -575,6 +587,7 @@ int frb_conv2d(frb_ctx* ctx, const void* d_in16, int B, int H, int W, int Cin, c
                int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int act, float slope, const void* d_res16,
                int res_mode, int rH, int rW, void* d_out, int out_fp32, int iters, float* h_ms, void* stream) {
   if (ctx == nullptr) return FRB_ERR_INVALID;
+  FRB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ConvLayer L;
   L.Cin = Cin; L.Cout = Cout; L.kh = kh; L.kw = kw; L.sh = sh; L.sw = sw; L.ph = ph; L.pw = pw;

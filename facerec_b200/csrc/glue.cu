@@ -456,33 +456,53 @@ int launch_prior_decode_filter(frb_ctx* ctx, const float* d_loc, const float* d_
 }
 
 // ------------------------------------------------------------------------------------------ K7
-// One CTA per frame: bitonic sort of (score desc, prior index asc) in shared memory, IoU
-// suppression bitmask (n x n/32 words), then a single-warp sequential scan.  n <= 1024.
+// One CTA per frame: bitonic sort of (score desc, prior index asc) in shared memory, IoU suppression bitmask
+// (n x n/32 words) over the kNmsMax best candidates, then a single-warp sequential scan.  Up to kNmsCand candidates
+// per frame are sorted; when more than kNmsMax pass the threshold only the kNmsMax highest-scoring ones enter the
+// suppression step (the published RetinaFace pipeline trims to its top 5 000 before NMS for the same reason), so a
+// crowded frame degrades to its best candidates instead of failing.  Non-finite boxes (exp overflow of a box
+// regression in a 16-bit net) are never kept and never suppress anything.
 constexpr int kNmsMax = 1024;
+constexpr int kNmsCand = 8192;
 
 __device__ __forceinline__ bool nms_before(float sa, int pa, float sb, int pb) {
   return sa > sb || (sa == sb && pa < pb);
 }
 
+// shared-memory plan for a frame with np2 sorted slots and nn = min(n, kNmsMax) suppression candidates:
+//   [ s_idx np2 ][ region B ]   region B = { s_score np2, s_prior np2 } while sorting,
+//                                           { s_box nn2, s_area nn2, s_mask nn2 * nn2 / 32 } afterwards
+static size_t nms_smem_bytes(int max_cand) {
+  int np2 = 32;
+  while (np2 < max_cand) np2 <<= 1;
+  const int nn2 = std::min(np2, kNmsMax);
+  const size_t sort_b = static_cast<size_t>(np2) * 8;
+  const size_t mask_b = static_cast<size_t>(nn2) * 20 + static_cast<size_t>(nn2) * (nn2 / 32) * 4;
+  return static_cast<size_t>(np2) * 4 + std::max(sort_b, mask_b);
+}
+
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand, const int32_t* __restrict__ count,
                                                   const int32_t* __restrict__ prior_idx, int max_cand, float iou_thr,
                                                   int plus_one, int32_t* __restrict__ keep, int32_t* __restrict__ nkeep) {
-  extern __shared__ uint8_t nms_smem[];
+  extern __shared__ __align__(16) uint8_t nms_smem[];
   const int b = blockIdx.x;
-  const int n = min(count[b], max_cand);
+  const int n_all = min(count[b], max_cand);
   int np2 = 32;
-  while (np2 < n) np2 <<= 1;
-  float* s_score = reinterpret_cast<float*>(nms_smem);                 // [np2]
+  while (np2 < n_all) np2 <<= 1;
+  const int n = min(n_all, kNmsMax);                                   // candidates that enter the suppression step
+  const int nn2 = min(np2, kNmsMax);
+  int* s_idx = reinterpret_cast<int*>(nms_smem);                       // [np2]
+  uint8_t* region_b = nms_smem + static_cast<size_t>(np2) * 4;
+  float* s_score = reinterpret_cast<float*>(region_b);                 // [np2]   (sorting)
   int* s_prior = reinterpret_cast<int*>(s_score + np2);                // [np2]
-  int* s_idx = s_prior + np2;                                          // [np2]
-  float4* s_box = reinterpret_cast<float4*>(s_idx + np2);              // [np2]
-  float* s_area = reinterpret_cast<float*>(s_box + np2);               // [np2]
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_area + np2);        // [np2 * np2/32]
+  float4* s_box = reinterpret_cast<float4*>(region_b);                 // [nn2]   (after sorting; overlays the keys)
+  float* s_area = reinterpret_cast<float*>(s_box + nn2);               // [nn2]   NaN = non-finite box, never kept
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_area + nn2);        // [nn2 * nn2/32]
   const float* cb = cand + static_cast<size_t>(b) * max_cand * 15;
   const int32_t* pb = prior_idx + static_cast<size_t>(b) * max_cand;
 
   for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-    if (i < n) { s_score[i] = cb[i * 15 + 4]; s_prior[i] = pb[i]; s_idx[i] = i; }
+    if (i < n_all) { s_score[i] = cb[i * 15 + 4]; s_prior[i] = pb[i]; s_idx[i] = i; }
     else { s_score[i] = -INFINITY; s_prior[i] = 0x7fffffff; s_idx[i] = -1; }
   }
   __syncthreads();
@@ -503,12 +523,14 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand
       __syncthreads();
     }
   }
+  // the sort keys are dead from here: boxes, areas and the mask take their place
   const float po = plus_one ? 1.f : 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float* c = cb + s_idx[i] * 15;
     const float4 bx = make_float4(c[0], c[1], c[2], c[3]);
+    const bool finite = isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w);
     s_box[i] = bx;
-    s_area[i] = fmul(fadd(fsub(bx.z, bx.x), po), fadd(fsub(bx.w, bx.y), po));
+    s_area[i] = finite ? fmul(fadd(fsub(bx.z, bx.x), po), fadd(fsub(bx.w, bx.y), po)) : __int_as_float(0x7fc00000);
   }
   __syncthreads();
   const int words = (n + 31) >> 5;
@@ -526,7 +548,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand
       const float ih = fmaxf(0.f, fadd(fsub(fminf(a.w, q.w), fmaxf(a.y, q.y)), po));
       const float inter = fmul(iw, ih);
       const float ovr = __fdiv_rn(inter, fsub(fadd(aa, s_area[j]), inter));
-      if (ovr > iou_thr) bits |= 1u << jj;
+      if (ovr > iou_thr) bits |= 1u << jj;     // false for NaN: a non-finite box suppresses nothing
     }
     s_mask[i * words + w] = bits;
   }
@@ -538,6 +560,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand
     for (int i = 0; i < n; ++i) {
       const uint32_t rw = __shfl_sync(0xffffffffu, removed, i >> 5);
       if ((rw >> (i & 31)) & 1u) continue;
+      if (isnan(s_area[i])) continue;
       if (threadIdx.x == 0) keep[static_cast<size_t>(b) * max_cand + nk] = s_idx[i];
       ++nk;
       if (static_cast<int>(threadIdx.x) < words) removed |= s_mask[i * words + threadIdx.x];
@@ -548,16 +571,14 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ cand
 
 int launch_nms(frb_ctx* ctx, const float* d_cand, const int32_t* d_count, const int32_t* d_prior_idx, int B, int max_cand,
                float iou_thr, int legacy_plus_one, int32_t* d_keep, int32_t* d_nkeep, cudaStream_t st) {
-  if (max_cand <= 0 || max_cand > kNmsMax)
-    return set_err(ctx, FRB_ERR_INVALID, "nms: max_cand must be in 1..%d", kNmsMax);
+  if (max_cand <= 0 || max_cand > kNmsCand)
+    return set_err(ctx, FRB_ERR_INVALID, "nms: max_cand must be in 1..%d", kNmsCand);
   if (B <= 0) return FRB_OK;
-  int np2 = 32;
-  while (np2 < max_cand) np2 <<= 1;
-  const size_t smem = static_cast<size_t>(np2) * (4 + 4 + 4 + 16 + 4) + static_cast<size_t>(np2) * (np2 / 32) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FRB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  const size_t smem = nms_smem_bytes(max_cand);
+  if (!ctx->attr_nms) {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(nms_smem_bytes(kNmsCand))));
+    ctx->attr_nms = true;
   }
   nms_kernel<<<B, 256, smem, st>>>(d_cand, d_count, d_prior_idx, max_cand, iou_thr, legacy_plus_one, d_keep, d_nkeep);
   ctx->launches++;

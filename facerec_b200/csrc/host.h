@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/facerec_b200.h"
+#include "../../include/facerec_b200_debug.h"
 
 namespace frb {
 
@@ -49,6 +50,8 @@ struct frb_ctx {
   frb::EncodeTiledFn encode_tiled = nullptr;
   std::map<int, frb::Net*> nets;
   long long launches = 0;      // kernels launched through this context (bench bookkeeping)
+  bool attr_nms = false;       // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: tracked per context
+  bool attr_dist = false;
   void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };

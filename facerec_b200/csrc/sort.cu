@@ -165,6 +165,7 @@ std::vector<int> assign_max(const std::vector<double>& w, int n, int m) {
           if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
           if (minv[j] < delta) { delta = minv[j]; j1 = j; }
         }
+      if (!(delta < INF)) return std::vector<int>();   // non-finite weights: no augmenting path can be ranked (caller reports it)
       for (int j = 0; j <= C; ++j)
         if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
         else minv[j] -= delta;
@@ -211,6 +212,10 @@ void frb_sort_destroy(frb_sort* s) { delete s; }
 
 int frb_sort_update(frb_sort* s, const double* dets, int n, long long frame, long long* out_ids) {
   if (s == nullptr || n < 0 || (n > 0 && (dets == nullptr || out_ids == nullptr))) return FRB_ERR_INVALID;
+  // A non-finite detection would put NaN into the IoU matrix; the reference's linear_sum_assignment raises ValueError on
+  // that input (facerec/sort.py:31 via scipy).  Refuse it before any tracker state is touched.
+  for (int i = 0; i < 5 * n; ++i)
+    if (!std::isfinite(dets[i])) return FRB_ERR_INVALID;
   // predictions of the live trackers; NaN ones are dropped for good (facerec/sort.py:228-242)
   std::vector<std::shared_ptr<Tracker>> live;
   std::vector<std::array<double, 4>> pred;
@@ -239,10 +244,12 @@ int frb_sort_update(frb_sort* s, const double* dets, int n, long long frame, lon
         const double inter = iw * ih;
         double v = inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter);
         if (v < s->iou_threshold) v = -1.0;
-        iou[static_cast<size_t>(i) * m + j] = v;      // NaN compares false above and stays, as in numpy
+        if (std::isnan(v)) return FRB_ERR_INVALID;     // 0 / 0 of two degenerate boxes: scipy raises on the same matrix
+        iou[static_cast<size_t>(i) * m + j] = v;
       }
     }
     std::vector<int> r2c = assign_max(iou, n, m);
+    if (r2c.empty()) return FRB_ERR_INVALID;
     for (int i = 0; i < n; ++i)
       if (r2c[i] >= 0 && iou[static_cast<size_t>(i) * m + r2c[i]] >= s->iou_threshold) match[i] = r2c[i];
   }

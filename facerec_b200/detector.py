@@ -17,6 +17,7 @@ cores, PriorBox decode + score filter + compaction, per-frame NMS.  The host onl
 """
 from __future__ import annotations
 
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -30,14 +31,19 @@ KEYPOINT_NAMES = ("left_eye", "right_eye", "nose", "mouth_left", "mouth_right")
 
 class B200RetinaFaceDetector:
     def __init__(self, min_face_size: int = 0, backbone: str = "mnet025", weights: Optional[Dict[str, np.ndarray]] = None,
-                 seed: int = 0, threshold: float = 0.95, nms_threshold: float = 0.4, max_candidates: int = 1024,
-                 ctx: Optional[Context] = None, device: int = 0):
+                 seed: int = 0, threshold: float = 0.95, nms_threshold: float = 0.4, max_candidates: int = 5000,
+                 keep_top_k: int = 750, ctx: Optional[Context] = None, device: int = 0):
+        """max_candidates / keep_top_k are the published RetinaFace pipeline's pre-NMS top_k (5000) and post-NMS
+        keep_top_k (750): a frame with more candidates degrades to its highest-scoring ones (with a warning) instead of
+        failing.  Up to 8192 candidates per frame are supported; the 1024 best enter the NMS suppression step."""
         if backbone not in ("mnet025", "r50"):
             raise ValueError("backbone must be 'mnet025' or 'r50'")
         self.min_size = min_face_size
         self.threshold = float(threshold)
         self.nms_threshold = float(nms_threshold)
         self.max_candidates = int(max_candidates)
+        self.keep_top_k = int(keep_top_k)
+        self._host_pool: Dict[tuple, list] = {}     # pinned result buffers, reused across batches (no allocation per batch)
         self.ctx = ctx if ctx is not None else default_context(device)
         self.device = torch.device("cuda", self.ctx.device)
         self.model_name = "retina_" + backbone
@@ -79,30 +85,49 @@ class B200RetinaFaceDetector:
             dev = self._to_device(arr)
         return self.detect_batch_collect(self.detect_batch_launch(dev))
 
+    def _host_buffers(self, B: int):
+        key = (B, self.keep_top_k)
+        pool = self._host_pool.setdefault(key, [])
+        if pool:
+            return pool.pop()
+        return (torch.empty((B, self.keep_top_k, 15), dtype=torch.float32, pin_memory=True),
+                torch.empty((2, B), dtype=torch.int32, pin_memory=True))
+
     def detect_batch_launch(self, frames_dev: torch.Tensor):
-        """Enqueue the whole detection pass for a GPU-resident batch plus the device-to-host copies of its results
-        (pinned buffers) and return a handle; nothing here waits for the GPU."""
-        outs = self.detect_device(frames_dev)
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
-        for h, t in zip(host, outs):
-            h.copy_(t, non_blocking=True)
+        """Enqueue the whole detection pass for a GPU-resident batch plus the device-to-host copy of the kept detections
+        (dense [B, keep_top_k, 15] rows via frb_gather_kept, into pooled pinned buffers) and return a handle; nothing
+        here waits for the GPU."""
+        cand, keep, nkeep, count = self.detect_device(frames_dev)
+        dets, nout = ops.gather_kept(self.ctx, cand, keep, nkeep, self.keep_top_k)
+        hd, hn = self._host_buffers(frames_dev.shape[0])
+        hd.copy_(dets, non_blocking=True)
+        hn[0].copy_(nout, non_blocking=True)
+        hn[1].copy_(count, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return host, ev, outs          # `outs` keeps the device tensors alive until the copies have run
+        return (hd, hn), ev, (dets, nout, count)   # the device tensors stay alive until the copies have run
 
     def detect_batch_collect(self, handle) -> List[np.ndarray]:
-        host, ev, _ = handle
+        (hd, hn), ev, _ = handle
         ev.synchronize()
-        cand, keep, nkeep, count = (h.numpy() for h in host)
+        n, count = hn[0].numpy(), hn[1].numpy()
         if (count > self.max_candidates).any():
-            raise RuntimeError(f"more than max_candidates={self.max_candidates} priors passed the score threshold "
-                               f"(max {int(count.max())}); raise max_candidates (<= 1024) or the threshold")
-        return [cand[b, keep[b, :nkeep[b]]] for b in range(len(nkeep))]
+            warnings.warn(f"{int((count > self.max_candidates).sum())} frame(s) had more than max_candidates="
+                          f"{self.max_candidates} priors above the score threshold (max {int(count.max())}): the overflow "
+                          "was dropped before NMS", RuntimeWarning, stacklevel=2)
+        if (n > self.keep_top_k).any():
+            warnings.warn(f"a frame kept {int(n.max())} faces after NMS; only the keep_top_k={self.keep_top_k} highest-scoring "
+                          "are returned", RuntimeWarning, stacklevel=2)
+        out = [hd[b, :min(int(n[b]), self.keep_top_k)].numpy().copy() for b in range(len(n))]
+        self._host_pool.setdefault((len(n), self.keep_top_k), []).append((hd, hn))
+        return out
 
     def format(self, dets: np.ndarray) -> List[dict]:
         out = []
         for d in dets:
             x1, y1, x2, y2 = float(d[0]), float(d[1]), float(d[2]), float(d[3])
+            if not np.isfinite(d[:15]).all():     # never produced by frb_nms; guards hand-made rows (NaN < min_size is False)
+                continue
             if min(x2 - x1, y2 - y1) < self.min_size:
                 continue
             kp = {n: (int(d[5 + 2 * t]), int(d[6 + 2 * t])) for t, n in enumerate(KEYPOINT_NAMES)}

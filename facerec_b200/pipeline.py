@@ -12,6 +12,7 @@ extractor (facerec_b200/extract.py) additionally applies the SORT validity gate 
 """
 from __future__ import annotations
 
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -67,7 +68,7 @@ class BatchResult:
 
 class FacePipeline:
     def __init__(self, backbone: str = "r50", min_face_size: int = 20, save_every: int = 5, seed: int = 0,
-                 ctx: Optional[Context] = None, device: int = 0, max_faces_per_frame: int = 128,
+                 ctx: Optional[Context] = None, device: int = 0, max_faces_per_frame: int = 750,
                  det_weights=None, emb_weights=None):
         self.ctx = ctx if ctx is not None else default_context(device)
         self.device = torch.device("cuda", self.ctx.device)
@@ -98,10 +99,11 @@ class FacePipeline:
         torch.cuda.current_stream().synchronize()
         n, c = pn[0].numpy(), pn[1].numpy()
         if (c > self.detector.max_candidates).any() or (n > self.max_out).any():
-            raise RuntimeError(f"detection overflow: {int(c.max())} candidates / {int(n.max())} faces in one frame")
+            warnings.warn(f"detection overflow: {int(c.max())} candidates / {int(n.max())} faces in one frame; kept the "
+                          f"{self.detector.max_candidates} / {self.max_out} highest-scoring", RuntimeWarning, stacklevel=2)
         out = []
         for b in range(B):
-            d = pd[b, :n[b]].numpy()
+            d = pd[b, :min(int(n[b]), self.max_out)].numpy()
             if self.min_size > 0 and len(d):
                 d = d[np.minimum(d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]) >= self.min_size]
             out.append(d.copy())

@@ -52,16 +52,11 @@ enum frb_pdist_layout {
 enum frb_option {
   FRB_OPT_BF16 = 0,        /* 1: bf16 activations/weights instead of fp16 (set before frb_load_model) */
   FRB_OPT_BN_CAP = 1,      /* largest conv tile N (multiple of 16, <= 256)                           */
-  FRB_OPT_FORCE_GATHER = 2,/* 1: never feed the conv A operand by TMA (A/B testing of the two paths)  */
   FRB_OPT_HALO = 3,        /* stride-1 k x k convs reading one halo tile per channel block instead of one TMA box
                               per filter tap: 0 (default) where it pays (resident weights, or a filter row of
                               streamed weights per stage), 1 wherever possible, -1 never                          */
-  FRB_OPT_TRACE = 4,       /* non-zero: every CTA of a conv_tma launch writes 16 stall-cycle counters of its
-                              three roles at h_out[1 + 16 * cta] (read with frb_debug_trace)                 */
   FRB_OPT_KBPS2 = 5,       /* 0: one 64-wide k-block per pipeline stage instead of two                     */
   FRB_OPT_LAYER_TIMES = 6, /* 1: network forwards bracket every op with events, read by frb_debug_layer_times */
-  FRB_OPT_MAX_STAGES = 7,  /* cap on the conv_tma stage ring depth (>= 2; experiments)                          */
-  FRB_OPT_SKIP_LOADS = 8,  /* 1: TIMING EXPERIMENT ONLY - the A/B tiles of the per-tap path are never loaded (wrong results) */
   FRB_OPT_DUAL_ISSUE = 9,  /* 0: a single MMA issuer warp per CTA (default 1: two, alternating tiles, where safe)   */
   FRB_OPT_PDL = 10,        /* programmatic dependent launch of the conv kernels (set-up under the previous kernel's   */
                            /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
@@ -69,6 +64,8 @@ enum frb_option {
                            /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
   FRB_OPT_MPAIR = 12       /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
                            /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
+  /* values 2, 4, 7, 8 are timing / tracing experiments that only a debug build of the library honours:
+     include/facerec_b200_debug.h */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -78,8 +75,6 @@ int frb_destroy(frb_ctx* ctx);
 const char* frb_last_error(frb_ctx* ctx); /* valid until the next call on ctx */
 int frb_set_option(frb_ctx* ctx, int option, int value);
 long long frb_launch_count(frb_ctx* ctx); /* kernels launched through ctx so far */
-/* FRB_OPT_TRACE: copies the stall counters of the LAST conv_tma launch (1 + 3 * max_records words, 16 per CTA from h_out[1]) */
-int frb_debug_trace(frb_ctx* ctx, long long* h_out, int max_records);
 /* FRB_OPT_LAYER_TIMES: per-op rows (kind 0 conv / 1 dwconv / 2 maxpool / 3 avgpool / 4 l2norm, M, N, K, flop, ms) of the
  * LAST network forward; returns the row count (<= max_rows) or a negative frb_status. */
 int frb_debug_layer_times(frb_ctx* ctx, double* h_rows, int max_rows);

@@ -17,14 +17,20 @@ def _report():
     return m
 
 
-@pytest.mark.parametrize("backbone,H,W,n", [("mnet025", 360, 640, 24), ("r50", 1080, 1920, 3)])
-def test_detect_embed_parity_vs_oracle(ctx, backbone, H, W, n):
-    s = _report().run(backbone, H, W, n)
-    print(s)
+@pytest.mark.parametrize("backbone,H,W,n,stride", [("mnet025", 360, 640, 48, 7), ("r50", 1080, 1920, 8, 11)])
+def test_detect_embed_parity_vs_oracle(ctx, backbone, H, W, n, stride):
+    """north_star: identical kept-face sets with box IoU >= 0.99, embedding cosine >= 0.999.  Kept sets must be identical
+    on every frame except where a discrete decision (score 0.95, min size, NMS IoU 0.4) sits inside the declared
+    rounding bands of tools/parity_report.py; the full-size runs (240 frames at 360p, a whole 64-frame 1080p batch) are
+    committed under profiles/r02_parity_*.json."""
+    s = _report().run(backbone, H, W, n, stride=stride)
+    print({k: v for k, v in s.items() if k != "unexplained"}, s["unexplained"][:5])
     assert s["oracle_faces"] >= n                       # the calibrated heads do fire: the test is not vacuous
+    assert s["frac_identical_outside_band"] >= 0.95, s  # identical kept-face sets outside the declared bands
     assert s["face_match_rate"] >= 0.95, s              # >= 95 % of oracle faces reproduced with IoU >= 0.99
     assert abs(s["gpu_faces"] - s["oracle_faces"]) <= max(1, 0.05 * s["oracle_faces"]), s
-    assert s["cos_n"] > 0 and s["cos_min"] >= 0.999, s
+    assert s["cos_n_same_rect"] > 0 and s["cos_min_same_rect"] >= 0.999, s
+    assert s["cos_n_all"] >= s["cos_n_same_rect"] and s["cos_min_all"] >= 0.999, s   # unconditional: GPU crop vs oracle crop
     assert s["max_landmark_err_px"] < 1.0, s
 
 

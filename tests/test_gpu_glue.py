@@ -75,6 +75,37 @@ def test_nms_empty_and_overflow(ctx):
     assert count[1] == loc.shape[1] and 1 <= nkeep[1] <= 32
 
 
+def test_nms_crowded_frame_keeps_top_candidates_and_drops_nonfinite(ctx):
+    """More than 1024 priors above the threshold (a crowd, or a miscalibrated class head): the 1024 highest-scoring
+    candidates go through NMS (the published pipeline trims to its top 5000 the same way) and nothing raises; a
+    non-finite box (exp overflow of a 16-bit regression) is never kept and suppresses nothing."""
+    from facerec_b200 import ops
+    from oracle import postproc
+    rng = np.random.RandomState(11)
+    H, W = 360, 640
+    loc, conf, landm = _raw(rng, 2, H, W, 0.30)            # ~2 800 hot priors per frame
+    loc[1, :, 2] = np.where(rng.rand(loc.shape[1]) < 0.05, 600.0, loc[1, :, 2])   # exp(120) = inf -> x2 = -inf + inf
+    tl, tc, tm = (torch.from_numpy(a).cuda() for a in (loc, conf, landm))
+    cand, count, pidx = ops.prior_decode_filter(ctx, tl, tc, tm, H, W, 0.95, 5000)
+    keep, nkeep = ops.nms(ctx, cand, count, pidx, 0.4, True)
+    cand, count, pidx, keep, nkeep = (t.cpu().numpy() for t in (cand, count, pidx, keep, nkeep))
+    pri = postproc.priorbox(H, W)
+    for b in range(2):
+        scores = postproc.face_scores(conf[b])
+        sel = np.nonzero(scores > np.float32(0.95))[0]
+        assert 1024 < len(sel) == count[b] <= 5000
+        order = np.lexsort((sel, -scores[sel]))[:1024]        # the 1024 best: score descending, lower prior first
+        top = sel[order]
+        with np.errstate(over="ignore", invalid="ignore"):
+            boxes, _ = postproc.decode(loc[b][top], landm[b][top], pri[top], H, W)
+        finite = np.isfinite(boxes).all(1)
+        assert finite.all() == (b == 0)
+        k = postproc.nms(boxes[finite], scores[top][finite], top[finite], 0.4, True)
+        got = pidx[b, keep[b, :nkeep[b]]]
+        assert np.array_equal(got, top[finite][k])
+        assert np.isfinite(cand[b, keep[b, :nkeep[b]]]).all()
+
+
 def test_crop_resize_standardize_matches_cv2_semantics(ctx):
     from facerec_b200 import ops
     from oracle import crop

@@ -248,3 +248,15 @@ def test_native_float_json_is_byte_identical_to_json_dumps():
            "keypoints": {"left_eye": (30, 50), "right_eye": (70, 51), "nose": (50, 80), "mouth_left": (35, 110), "mouth_right": (66, 111)},
            "w": 640, "h": 360}
     assert feature_line(rec, e, FACENET_KEYS) == feature_line(rec, e.tolist(), FACENET_KEYS)
+
+
+def test_native_sort_rejects_non_finite_detections_like_scipy():
+    """A NaN box used to spin forever inside the C++ assignment (round-1 advisor finding); the reference raises
+    ValueError from scipy's linear_sum_assignment on the same input (facerec/sort.py:31)."""
+    from facerec_b200 import sort as S
+    for cls in (S.NativeSort, S.Sort):
+        S.KalmanBoxTracker.count = 0
+        mt = cls(5, 3, 0.5)
+        mt.update(np.array([[10, 10, 50, 50, 0.95]], float), frame=0)
+        with pytest.raises(ValueError):
+            mt.update(np.array([[np.nan, 10, 50, 50, 0.95]], float), frame=1)

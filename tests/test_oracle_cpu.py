@@ -114,12 +114,16 @@ def test_oracle_networks_shapes():
 
 
 def test_library_exports_every_header_symbol():
-    """The C-ABI library loads (no GPU needed) and exports exactly what include/facerec_b200.h declares."""
+    """The C-ABI library loads (no GPU needed) and exports exactly what include/facerec_b200.h (+ the debug-only additions
+    of include/facerec_b200_debug.h) declares."""
     import ctypes
     from facerec_b200 import _lib, build
     path = build.build()
     lib = ctypes.CDLL(path)
     header = open(os.path.join(ROOT, "include", "facerec_b200.h")).read()
+    header += open(os.path.join(ROOT, "include", "facerec_b200_debug.h")).read()
+    # the timing experiments are not part of the public header
+    assert "SKIP_LOADS" not in open(os.path.join(ROOT, "include", "facerec_b200.h")).read()
     declared = set(re.findall(r"\b(frb_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
