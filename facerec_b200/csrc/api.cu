@@ -155,6 +155,8 @@ int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   return run_knn_topk(ctx, d_Q, Q, d_DB, M, D, k, d_idx, d_dist, static_cast<cudaStream_t>(stream));
 }
 
+int frb_knn_redo_count(frb_ctx* ctx) { return ctx ? ctx->knn_redo_last : -1; }
+
 int frb_knn_vote(frb_ctx* ctx, const int32_t* d_idx, const int32_t* d_label_idx, int Q, int k, int n_classes,
                  float* d_proba, void* stream) {
   FRB_ENTER(ctx);

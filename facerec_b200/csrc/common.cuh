@@ -301,6 +301,72 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* d
       : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (thread-block cluster of 2, cta_group::2)
+// Two CTAs on the two SMs of a TPC run ONE tcgen05.mma of M = 256: each CTA holds its own 128 rows of A and of the
+// accumulator and HALF of the B tile (N/2 rows); the leader CTA (cluster rank 0) issues the instruction, the tensor cores
+// of both SMs read both halves of B.  Per SM that halves the B bytes pulled through L2 for the same MMA work.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on a barrier that may live in the peer CTA (shared::cluster address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// D[tmem, 256 x N over the pair] (+)= A * B, issued by one thread of the leader CTA; descriptors are CTA-local offsets
+// that mean the same location in both CTAs.
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier that may live in the peer CTA (the leader's)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* desc, uint32_t bar_cluster, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* desc, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 //   [4,6) c_format (1 = F32)   [7,10) a_format   [10,13) b_format (0 = F16, 1 = BF16)
 //   [15] a_major  [16] b_major (0 = K)   [17,23) N >> 3   [24,29) M >> 4

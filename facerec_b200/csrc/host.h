@@ -52,6 +52,7 @@ struct frb_ctx {
   long long launches = 0;      // kernels launched through this context (bench bookkeeping)
   bool attr_nms = false;       // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: tracked per context
   bool attr_dist = false;
+  int knn_redo_last = 0;       // queries of the last frb_knn_topk call that needed the exact three-segment pass
   void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };

@@ -200,6 +200,11 @@ def knn_topk(ctx: Context, Q: torch.Tensor, DB: torch.Tensor, k: int):
     return idx, dist
 
 
+def knn_redo_count(ctx: Context) -> int:
+    """Queries of the last knn_topk call that went through the exact split-bf16 pass (diagnostics)."""
+    return int(ctx.lib.frb_knn_redo_count(ctx.handle))
+
+
 def knn_vote(ctx: Context, idx: torch.Tensor, label_idx: torch.Tensor, n_classes: int) -> torch.Tensor:
     _need_cuda(idx, "idx", torch.int32)
     _need_cuda(label_idx, "label_idx", torch.int32)

@@ -185,10 +185,17 @@ int frb_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, 
 int frb_linkage_complete(frb_ctx* ctx, float* d_D /*[N,N]*/, int N, int32_t* d_merge_pairs /*[N-1,2]*/,
                          float* d_merge_dist /*[N-1]*/, void* stream);
 
-/* K14  k smallest Euclidean distances, never materialising Q x M.  Ties -> lower DB index.
+/* K14  k smallest Euclidean distances (k <= 16), never materialising Q x M.  Ties -> lower DB index.
+ * One bf16 tensor-core pass keeps 24 candidates per query, which are re-scored in fp32; queries whose k best cannot be
+ * proven from that (worst-case rounding bound) are re-run through the exact split-bf16 pass.  The call synchronises
+ * `stream` once (it reads the count of such queries).
  * Replaces KNeighborsClassifier.fit/kneighbors (facerec/classify_knn.py:212,227). */
 int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k,
                  int32_t* d_idx /*[Q,k] ascending distance*/, float* d_dist /*[Q,k]*/, void* stream);
+
+/* Diagnostics: how many queries of the LAST frb_knn_topk call on ctx could not be proven from the one-pass bf16 scan
+ * and went through the exact split-bf16 pass (results are exact either way; this only costs time). */
+int frb_knn_redo_count(frb_ctx* ctx);
 
 /* K15  neighbour labels -> class histogram / k (predict_proba with uniform weights,
  * facerec/classify_knn.py:227). */

@@ -98,6 +98,29 @@ def test_knn_topk_matches_bruteforce(ctx, q, m, k):
     assert (idx[:, 0] == ref_idx[:, 0]).mean() > 0.995          # kNN top-1
 
 
+def test_knn_tight_clusters_take_the_exact_pass(ctx):
+    """Database rows closer to each other than the bf16 rounding bound: the one-pass candidates cannot be proven, the
+    queries are re-run through the exact split-bf16 pass and still match the fp64 brute force."""
+    from facerec_b200 import ops
+    rng = np.random.RandomState(77)
+    db = _mixture(rng, 3000, centres=20, noise=0.0005)
+    qs = _mixture(rng, 300, centres=20, noise=0.0005)
+    idx, dist = ops.knn_topk(ctx, torch.from_numpy(qs).cuda(), torch.from_numpy(db).cuda(), 10)
+    assert ops.knn_redo_count(ctx) > 200                       # (almost) every query was undecidable in bf16
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    d = np.sqrt(np.maximum(((qs.astype(np.float64)[:, None, :] - db.astype(np.float64)[None, :, :]) ** 2).sum(-1), 0))
+    ref_idx = np.argsort(d, axis=1, kind="stable")[:, :10]
+    ref_d = np.take_along_axis(d, ref_idx, 1)
+    np.testing.assert_allclose(dist, ref_d, rtol=0, atol=3e-5)
+    got_d = np.take_along_axis(d, idx.astype(np.int64), 1)
+    assert np.abs(got_d - ref_d).max() < 3e-5                  # the same neighbours up to fp32-resolution ties
+    # well separated data: nothing needs the exact pass
+    db2 = rng.standard_normal((3000, 512)).astype(np.float32)
+    db2 /= np.linalg.norm(db2, axis=1, keepdims=True)
+    ops.knn_topk(ctx, torch.from_numpy(_mixture(rng, 300, centres=50)).cuda(), torch.from_numpy(db2).cuda(), 10)
+    assert ops.knn_redo_count(ctx) < 60
+
+
 def test_knn_vote_matches_sklearn_predict_proba(ctx):
     from sklearn.neighbors import KNeighborsClassifier
     from facerec_b200 import ops
