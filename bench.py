@@ -11,6 +11,11 @@ like the reference's --shard-i/--n-shards split (no data-path collective): weak 
   python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
   python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the CPU oracle on the host cores
   torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
+  python bench.py --workload pdist|knn [--impl reference]        # configs[3] / configs[4]: the embedding-distance stage
+
+The default line also carries a `distance` object: configs[3] (50k x 512 pdist, rows sharded over the ranks, one NCCL
+all_gather of the embeddings) and configs[4] (50k queries x 1M actor embeddings, fused top-10, queries sharded), each with its own
+device-timed rate, end-to-end rate and roofline, so that the driver's 1/2/4/8-GPU runs exercise the path's only collective.
 
 `value`  : frames/s with the batch already resident in HBM when the timed region starts.
 `e2e`    : the same through the host-facing call (FacePipeline.detect_embed) with pinned HOST frames:
@@ -219,6 +224,268 @@ def workload_config(a, sample_frames=None):
     return c
 
 
+
+# ------------------------------------------------------------------------------------------ distance stage
+PDIST_N, KNN_Q, KNN_M, KNN_K, EMB_D = 50000, 50000, 1000000, 10, 512
+
+
+def _timed_region(fn, steps, warmup, world, dist, device):
+    """W warm-up calls, then K timed calls between barrier + synchronize; CUDA events on the launching stream; max over ranks."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]) / steps
+
+
+def load_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_burst_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
+    return 1590.0, "fallback (B200_PROFILING.md burst figure)"
+
+
+def bench_pdist(a, ctx, rank, world, steps, warmup):
+    """configs[3]: N x 512 trajectory means -> condensed Euclidean distances (facerec/cluster.py:41), rows sharded over
+    the ranks by equal triangle area, one all_gather of the embeddings (the path's only exchange)."""
+    import torch
+    import torch.distributed as dist
+    from facerec_b200 import synth, distance, _lib
+    dev = torch.device("cuda", ctx.device)
+    N = a.pdist_n
+    X = synth.embeddings(N, 7, mean_of=2, device=dev)                     # same seed on every rank -> same matrix
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    mine = X[lo:hi].contiguous()                                           # the rows this rank's frame shard produced
+    r0, rows = distance.balanced_row_blocks(N, world)[rank]
+    beg, end = distance.condensed_offset(N, r0), distance.condensed_offset(N, r0 + rows)
+    out = torch.empty((max(end - beg, 1),), dtype=torch.float32, device=dev)
+    pairs = N * (N - 1) // 2
+
+    def step():
+        Xall = distance.all_gather_rows(mine) if world > 1 else mine
+        ctx.check(ctx.lib.frb_pdist(ctx.handle, Xall.data_ptr(), N, EMB_D, r0, rows, _lib.FRB_CONDENSED_F32,
+                                    out.data_ptr() - beg * 4, _lib.current_stream()), "frb_pdist")
+
+    l0 = ctx.launch_count()
+    ms = _timed_region(step, steps, warmup, world, dist, dev)
+    launches = (ctx.launch_count() - l0) // (steps + warmup)
+    # the kernel alone (rank 0's block), for the roofline
+    Xall = distance.all_gather_rows(mine) if world > 1 else mine
+    kms = _timed_region(lambda: ctx.check(ctx.lib.frb_pdist(ctx.handle, Xall.data_ptr(), N, EMB_D, r0, rows, _lib.FRB_CONDENSED_F32,
+                                                            out.data_ptr() - beg * 4, _lib.current_stream()), "frb_pdist"),
+                        steps, 1, world, dist, dev)
+    # end to end through the host-facing call: pinned host embeddings in, this rank's slice of the condensed vector out
+    host_in = mine.cpu().pin_memory()
+    host_out = torch.empty((end - beg,), dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        m = host_in.to(dev, non_blocking=True)
+        Xa = distance.all_gather_rows(m) if world > 1 else m
+        ctx.check(ctx.lib.frb_pdist(ctx.handle, Xa.data_ptr(), N, EMB_D, r0, rows, _lib.FRB_CONDENSED_F32,
+                                    out.data_ptr() - beg * 4, _lib.current_stream()), "frb_pdist")
+        host_out.copy_(out[:end - beg], non_blocking=True)
+
+    ems = _timed_region(step_e2e, max(1, min(steps, 3)), 1, world, dist, dev)
+    flop = pairs * 2.0 * EMB_D
+    peak, peak_src = load_burst_peak()
+    hbm, _ = load_hbm_peak()
+    my_flop = (end - beg) * 2.0 * EMB_D
+    rec = {"metric": "pdist_pairs_per_sec", "value": pairs / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms,
+           "config": {"workload": f"configs[3]: {N} x {EMB_D} trajectory-mean embeddings -> condensed fp32 Euclidean distances, "
+                                  f"rows sharded over {world} GPU(s) by equal triangle area" +
+                                  (", one NCCL all_gather of the embeddings per step" if world > 1 else ""),
+                      "N": N, "D": EMB_D, "parallelism": f"row-shard x{world}",
+                      "l2_policy": f"output slice {4e-9 * (end - beg):.2f} GB per rank, larger than L2"},
+           "e2e": {"value": pairs / (ems / 1e3), "unit": "pairs/s", "ms_per_step": ems, "h2d_bytes_per_step": int(host_in.numel() * 4),
+                   "d2h_bytes_per_step": int((end - beg) * 4),
+                   "api": "pinned host embeddings -> H2D -> (all_gather) -> frb_pdist -> D2H of this rank's condensed slice"},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "tensor", "achieved": my_flop / kms / 1e9, "peak": peak, "unit": "TFLOP/s",
+                        "frac": my_flop / kms / 1e9 / peak, "traffic": None,
+                        "kernel": "dist_gemm_kernel (cta_group::2, 256x256 tiles, split-bf16: 3 tensor passes per algorithmic FLOP)",
+                        "algorithmic_flop_per_launch": my_flop, "launch_ms": kms, "peak_source": peak_src,
+                        "issued_tflops": 3 * my_flop / kms / 1e9,
+                        "write_gbs": (end - beg) * 4 / kms / 1e6, "write_frac_of_hbm_copy_peak": (end - beg) * 4 / kms / 1e6 / hbm}}
+    del out, X
+    return rec
+
+
+def bench_knn(a, ctx, rank, world, steps, warmup):
+    """configs[4]: Q cluster means vs M actor-image embeddings, fused cosine/Euclidean top-10 + vote
+    (facerec/classify_knn.py:212,227); queries sharded over the ranks, database replicated (loaded once, like fit())."""
+    import torch
+    import torch.distributed as dist
+    from facerec_b200 import synth, ops
+    dev = torch.device("cuda", ctx.device)
+    Qn, M = a.knn_q, a.knn_m
+    DB = synth.embeddings(M, 11, centres=10000, device=dev)
+    Q = synth.embeddings(Qn, 13, centres=10000, device=dev)
+    labels = (torch.arange(M, device=dev, dtype=torch.int32) % 1000).contiguous()   # 1000 actors
+    lo, hi = rank * Qn // world, (rank + 1) * Qn // world
+    mine = Q[lo:hi].contiguous()
+
+    def step():
+        idx, _ = ops.knn_topk(ctx, mine, DB, KNN_K)
+        return ops.knn_vote(ctx, idx, labels, 1000)
+
+    l0 = ctx.launch_count()
+    ms = _timed_region(step, steps, warmup, world, dist, dev)
+    launches = (ctx.launch_count() - l0) // (steps + warmup)
+    redo = ops.knn_redo_count(ctx)
+    host_q = mine.cpu().pin_memory()
+    host_idx = torch.empty((hi - lo, KNN_K), dtype=torch.int32, pin_memory=True)
+    host_d = torch.empty((hi - lo, KNN_K), dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        q = host_q.to(dev, non_blocking=True)
+        idx, d = ops.knn_topk(ctx, q, DB, KNN_K)
+        host_idx.copy_(idx, non_blocking=True)
+        host_d.copy_(d, non_blocking=True)
+
+    ems = _timed_region(step_e2e, max(1, min(steps, 3)), 1, world, dist, dev)
+    flop = 2.0 * (hi - lo) * M * EMB_D
+    peak, peak_src = load_burst_peak()
+    rec = {"metric": "knn_queries_per_sec", "value": Qn / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms,
+           "config": {"workload": f"configs[4]: {Qn} cluster-mean queries vs {M} actor-image embeddings x {EMB_D}, k = {KNN_K}, "
+                                  f"fused top-k + uniform vote, queries sharded over {world} GPU(s), database replicated",
+                      "Q": Qn, "M": M, "D": EMB_D, "k": KNN_K, "parallelism": f"query-shard x{world}",
+                      "l2_policy": f"database {M * EMB_D * 2 / 1e9:.2f} GB (bf16 hi plane) streamed per query block, larger than L2"},
+           "e2e": {"value": Qn / (ems / 1e3), "unit": "queries/s", "ms_per_step": ems, "h2d_bytes_per_step": int(host_q.numel() * 4),
+                   "d2h_bytes_per_step": int((hi - lo) * KNN_K * 8),
+                   "api": "pinned host queries -> H2D -> frb_knn_topk (database resident, as after fit()) -> D2H of indices + distances"},
+           "gpu_launches": int(launches), "queries_through_exact_pass": int(redo),
+           "roofline": {"bound": "tensor", "achieved": flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": flop / ms / 1e9 / peak,
+                        "traffic": None,
+                        "kernel": "dist_gemm_kernel (cta_group::2, 256x256 tiles, resident A, one bf16 pass) + knn_merge_kernel (exact re-rank); "
+                                  "timed as the whole frb_knn_topk + frb_knn_vote step",
+                        "algorithmic_flop_per_launch": flop, "launch_ms": ms, "peak_source": peak_src}}
+    del DB, Q
+    return rec
+
+
+def cpu_pdist_rate(n_s, threads):
+    """scipy pdist (what linkage(vectors, 'complete') runs first, facerec/cluster.py:41) on a sample: pairs/s."""
+    from scipy.spatial.distance import pdist
+    rng = np.random.RandomState(7)
+    x = rng.standard_normal((n_s, EMB_D)).astype(np.float32)
+    t0 = time.time()
+    pdist(x)
+    dt = time.time() - t0
+    return n_s * (n_s - 1) / 2 / dt, dt
+
+
+def cpu_knn_rate(q_s, m_s, threads):
+    """sklearn KNeighborsClassifier(10).fit().predict_proba() (facerec/classify_knn.py:212,227) on a sample: queries/s
+    against the FULL-size database equivalent (time scales linearly in the database rows)."""
+    from sklearn.neighbors import KNeighborsClassifier
+    rng = np.random.RandomState(11)
+    db = rng.standard_normal((m_s, EMB_D)).astype(np.float32)
+    q = rng.standard_normal((q_s, EMB_D)).astype(np.float32)
+    knn = KNeighborsClassifier(n_neighbors=KNN_K, weights="uniform").fit(db, np.arange(m_s) % 1000)
+    t0 = time.time()
+    knn.predict_proba(q)
+    dt = time.time() - t0
+    return q_s / dt, dt
+
+
+def run_distance_reference(a):
+    """--impl reference for the distance workloads: the library calls the reference makes, on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    if a.workload == "pdist":
+        n_s = 6000
+        for i in range(a.warmup + a.steps):
+            r, dt = cpu_pdist_rate(n_s if i >= a.warmup else 1000, threads)
+            if i >= a.warmup:
+                vals.append((r, dt))
+        value = float(np.mean([v for v, _ in vals]))
+        metric, unit = "pdist_pairs_per_sec", "pairs/s"
+        sample = f"scipy.spatial.distance.pdist on {n_s} x {EMB_D} fp32 rows per step ({n_s * (n_s - 1) // 2} pairs; scipy pdist is single-threaded)"
+        cores = 1
+        cfg = {"workload": f"configs[3]: {a.pdist_n} x {EMB_D} pdist, sampled at N = {n_s}", "N": a.pdist_n, "sample_N": n_s}
+    else:
+        q_s, m_s = 256, 200000
+        for i in range(a.warmup + a.steps):
+            r, dt = cpu_knn_rate(q_s if i >= a.warmup else 16, m_s, threads)
+            if i >= a.warmup:
+                vals.append((r * m_s / a.knn_m, dt))
+        value = float(np.mean([v for v, _ in vals]))
+        metric, unit = "knn_queries_per_sec", "queries/s"
+        sample = (f"sklearn KNeighborsClassifier(10).predict_proba on {q_s} queries x {m_s} database rows per step, rate scaled "
+                  f"linearly to the {a.knn_m}-row database")
+        cores = threads
+        cfg = {"workload": f"configs[4]: {a.knn_q} queries vs {a.knn_m} x {EMB_D}, k = {KNN_K}, sampled", "Q": a.knn_q, "M": a.knn_m}
+    dt = float(np.mean([d for _, d in vals]))
+    print(json.dumps({"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "fp64 (scipy) / fp32 (sklearn)", "data": "synthetic", "config": cfg,
+                      "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_distance(a):
+    """--workload pdist|knn: one JSON line with the same contract as the default line."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from facerec_b200._lib import Context
+    ctx = Context(local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    rec = (bench_pdist if a.workload == "pdist" else bench_knn)(a, ctx, rank, world, a.steps, max(a.warmup, 3))
+    t1 = time.time()
+    if rank == 0:
+        clocks = sampler.window(t0, t1) if sampler else {}
+        if sampler:
+            sampler.stop()
+        line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16 split (hi + lo), fp32 accumulate" if a.workload == "pdist" else
+                "bf16 scan + fp32 exact re-rank (split-bf16 pass for undecidable queries)", "data": "synthetic"}
+        line.update({k: rec[k] for k in rec if k not in line})
+        line["clocks"] = clocks
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            if a.workload == "pdist":
+                v, dt = cpu_pdist_rate(6000, threads)
+                line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                                        "sample": f"scipy pdist (the first half of linkage(vectors, 'complete'), facerec/cluster.py:41) on 6000 x 512 rows, {dt:.1f} s, single-threaded by construction"}
+            else:
+                v, dt = cpu_knn_rate(256, 200000, threads)
+                line["cpu_baseline"] = {"value": v * 200000 / a.knn_m, "unit": "queries/s", "cores": threads, "kind": "reference",
+                                        "sample": f"sklearn KNeighborsClassifier(10).predict_proba, 256 queries x 200000 rows ({dt:.1f} s), rate scaled to {a.knn_m} rows"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_b200(a):
     import torch
@@ -322,6 +589,17 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
+    # ---- the embedding-distance stage at its configured sizes (configs[3], configs[4]); every rank takes part
+    dist_recs = {}
+    if not a.no_distance:
+        del dbuf, frames_d
+        torch.cuda.empty_cache()
+        for name, fn in (("pdist", bench_pdist), ("knn", bench_knn)):
+            try:
+                dist_recs[name] = fn(a, ctx, rank, world, 3, 2)
+            except Exception as e:      # the headline number must survive a failure here; the failure is reported, not hidden
+                dist_recs[name] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
     if rank == 0:
         clocks = sampler.window(t0, t1) if sampler else {}
         if sampler and not clocks.get("samples"):      # nvidia-smi delivered nothing inside the first region: use both
@@ -355,6 +633,8 @@ def run_b200(a):
                          "kernel": f"conv_tma_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
+        if dist_recs:
+            line["distance"] = dist_recs
         if world == 1 and not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
             fps, faces, dt = cpu_reference_fps(frames_h[:a.cpu_baseline_frames], first, a.backbone, a.save_every, threads)
@@ -383,8 +663,19 @@ def main():
     ap.add_argument("--cpu-baseline-frames", type=int, default=25,
                     help="frames of the batch the cpu_baseline leg runs through the oracle (25 = five save_every periods, ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="frames", choices=["frames", "pdist", "knn"],
+                    help="frames = configs[1] (the headline); pdist = configs[3]; knn = configs[4]")
+    ap.add_argument("--no-distance", action="store_true", help="default line without the `distance` object")
+    ap.add_argument("--pdist-n", type=int, default=PDIST_N)
+    ap.add_argument("--knn-q", type=int, default=KNN_Q)
+    ap.add_argument("--knn-m", type=int, default=KNN_M)
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.workload != "frames":
+        if a.impl == "reference":
+            run_distance_reference(a)
+        else:
+            run_distance(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

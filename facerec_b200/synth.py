@@ -57,3 +57,19 @@ def frame(seed: int, idx: int, H: int, W: int, vary_level: bool = False, scene_l
 
 def clip(seed: int, start: int, n: int, H: int, W: int) -> np.ndarray:
     return np.stack([frame(seed, start + i, H, W) for i in range(n)])
+
+
+def embeddings(n: int, seed: int, centres: int = 2800, noise: float = 0.05, d: int = 512, mean_of: int = 0, device="cuda"):
+    """Synthetic face embeddings for the distance stage: a mixture of `centres` identity directions on the
+    unit sphere, rows = normalize(c + noise * g).  `mean_of` > 1 averages that many such rows (trajectory means are
+    not unit norm, facerec/cluster.py:29).  Generated with torch on `device`, same seed -> same matrix on every rank."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    c = torch.nn.functional.normalize(torch.randn(centres, d, generator=g, device=device), dim=1)
+    idx = torch.randint(0, centres, (n,), generator=g, device=device)
+    x = torch.nn.functional.normalize(c[idx] + noise * torch.randn(n, d, generator=g, device=device), dim=1)
+    for _ in range(max(mean_of, 1) - 1):
+        x = x + torch.nn.functional.normalize(c[idx] + noise * torch.randn(n, d, generator=g, device=device), dim=1)
+    if mean_of and mean_of > 1:
+        x = x / mean_of
+    return x.contiguous()

@@ -21,14 +21,7 @@ sys.path.insert(0, ROOT)
 from facerec_b200 import ops, _lib  # noqa: E402
 
 
-def embeddings(n, seed, centres=2800, noise=0.05, d=512, mean_of=None, device="cuda"):
-    g = torch.Generator(device=device).manual_seed(seed)
-    c = torch.nn.functional.normalize(torch.randn(centres, d, generator=g, device=device), dim=1)
-    idx = torch.randint(0, centres, (n,), generator=g, device=device)
-    x = torch.nn.functional.normalize(c[idx] + noise * torch.randn(n, d, generator=g, device=device), dim=1)
-    if mean_of:   # trajectory means are not unit norm (facerec/cluster.py:29)
-        x = (x + torch.nn.functional.normalize(c[idx] + noise * torch.randn(n, d, generator=g, device=device), dim=1)) / 2
-    return x.contiguous()
+from facerec_b200.synth import embeddings  # noqa: E402
 
 
 def timed(fn, iters=3):
