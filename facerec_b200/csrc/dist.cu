@@ -2,17 +2,24 @@
 // distance + top-k for the kNN actor classifier, both as one NT GEMM on tcgen05 tensor cores.
 //
 // Precision.  The reference computes these distances in fp64 (scipy pdist / sklearn brute kNN) and its results depend
-// on the ORDER of distances, so plain bf16 inputs are not enough for the final numbers.  Each fp32 row is split into
-// bf16 hi + bf16 lo (x = hi + lo + O(2^-17 |x|)); the fp32-grade dot product is
+// on the ORDER of distances, so plain 16-bit inputs are not enough for the final numbers.  Each matrix is scaled by a
+// power of two so that its largest element lands in [2^13, 2^14) (exact, and it keeps the small parts out of the fp16
+// subnormals) and every element is split into fp16 hi + fp16 lo (x = hi + lo + O(2^-22 |x|)); the fp32-grade dot product is
 //   hi.hi + hi.lo + lo.hi          (three K-segments accumulated into the same fp32 TMEM tile)
 // and d^2 = |a|^2 + |b|^2 - 2 a.b with fp32 norms of the original data, clamped at 0.
 //   * pdist runs all three segments (every distance is an output).
 //   * kNN runs ONE segment (hi.hi) over the whole database and keeps, per query, the kCand best APPROXIMATE scores;
 //     the candidates are then re-scored exactly (fp32 FMA dot products of the original rows) and the k best are
 //     PROVEN to be the true k nearest: every other database row has approximate score >= tau (the worst kept
-//     candidate), so its exact score is >= tau - eps with eps = the worst-case bf16 rounding error of one dot product;
+//     candidate), so its exact score is >= tau - eps with eps = the worst-case fp16 rounding error of one dot product
+//     (u = 2^-11 per operand; bf16 would make eps eight times larger and most queries undecidable);
 //     a query whose k-th exact score is not below tau - eps is re-run through the three-segment path.  One third of
 //     the tensor work of the exact scheme for (almost) every query, the same answers for all of them.
+//     The candidate lists live in registers (sorted insertion, ~6 instructions per list entry): what keeps that cheap
+//     is a tight threshold.  Lists restart with every (query block, database chunk) item, so every finished item
+//     publishes its kCand-th best score per query (atomicMin) and later chunks of the same queries start from it: any
+//     published value is the kCand-th best of a SUBSET of the database, hence an upper bound of the final one, and no
+//     true candidate is ever filtered out (the merged result does not depend on which value a chunk happened to see).
 //
 // Kernel.  A CTA PAIR (thread-block cluster of 2 on the two SMs of a TPC, cta_group::2) computes 256 x 256 tiles:
 // each CTA holds 128 rows of A, its 128 accumulator lanes (TMEM, two buffers of 256 columns) and HALF of the B tile;
@@ -37,16 +44,17 @@ constexpr int kGN = 256;          // tile columns per pair; each CTA loads kGN /
 constexpr int kGK = 64;           // K elements per pipeline stage
 constexpr int kGEpiWarps = 8;
 constexpr int kGThreads = (kGEpiWarps + 2) * 32;
-constexpr int kCand = 24;         // per-row candidates kept in registers by the kNN epilogue (k <= 16)
+constexpr int kCand = 16;         // per-row candidates kept in registers by the kNN epilogue (k <= 16)
 constexpr int kTopK = 16;         // largest k of frb_knn_topk
 constexpr int kGABytes = kGM * kGK * 2;         // one A k-block of a CTA
 constexpr int kGBBytes = (kGN / 2) * kGK * 2;   // one B k-block half
 constexpr int kGMaxStages = 8;
-constexpr int kGScratchPdist = kGEpiWarps * 32 * 33 * 4;   // per-warp 32 x 33 transposition tiles
-constexpr int kGScratchKnn = kGEpiWarps * 128 * 4;         // per-warp |b|^2 of its 128 tile columns
+constexpr int kGWarpScratchPdist = 32 * 33 * 4 + 128 * 4;          // per warp: 32 x 33 transposition tile + |b|^2 of its 128 columns
+constexpr int kGScratchPdist = kGEpiWarps * kGWarpScratchPdist;
+constexpr int kGScratchKnn = kGEpiWarps * 128 * 4;                 // per-warp |b|^2 of its 128 tile columns
 // worst-case |approximate - exact| score of the one-segment pass, relative to |q| * max|x|:
-// 2 * (u (2 + u) with u = 2^-8 for the two bf16 roundings + 512 * 2^-22 for the fp32 accumulation of 512 products)
-constexpr float kKnnEps = 0.0160f;
+// 2 * (u (2 + u) with u = 2^-11 for the two fp16 roundings + 512 * 2^-21 for the fp32 accumulation of 512 products)
+constexpr float kKnnEps = 0.0025f;
 
 enum DistMode : int { DIST_SQUARE_F32 = 0, DIST_CONDENSED_F32 = 1, DIST_CONDENSED_F64 = 2, DIST_KNN = 3, DIST_SQUARE_SYM_F32 = 4 };
 
@@ -63,20 +71,44 @@ struct DistArgs {
   int items;
   const float* na;       // |a|^2 indexed by global A row (pdist)
   const float* nb;       // |b|^2, padded to n_tiles * 256 entries with +inf (kNN) / 0 (pdist)
+  const int* exp_a;      // power-of-two scale exponents of the split A and B matrices (device, written by split_rows_kernel)
+  const int* exp_b;
+  unsigned int* thr_bits;  // kNN: per-query published threshold (orderable encoding of the best kCand-th score seen so far)
   void* out;
   float* part_d;         // kNN partial lists [Qrows, parts = 2 * chunks, kCand]
   int32_t* part_i;
   int* watchdog;
 };
 
-// ------------------------------------------------------------------ fp32 -> (hi | lo) bf16 + norms
-// scale = -2 for kNN queries: the accumulator then holds -2 q.x and the epilogue only adds |x|^2 (x (-2) is exact).
-// norm2[r] for n <= r < n_pad is filled with `pad_norm` (+inf for a kNN database: padding columns never win).
-__global__ void split_rows_kernel(const float* __restrict__ x, int n, int D, int Dp, float scale, __nv_bfloat16* __restrict__ out,
-                                  float* __restrict__ norm2, int n_pad, float pad_norm, unsigned int* __restrict__ max_norm_bits) {
+// ------------------------------------------------------------------ fp32 -> scaled (hi | lo) fp16 + norms
+// max |x| of a matrix (bits of a non-negative float order like the float)
+__global__ void max_abs_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// Rows are scaled by 2^e, e chosen so that the largest element of the matrix lands in [2^13, 2^14) (exact; fp16 holds up
+// to 65504 and the lo parts of all but vanishing elements stay normal), times `extra` (-2 for kNN queries: the
+// accumulator then holds -2 * 2^(ea+eb) q.x and the epilogue is one FMA).  norm2[r] for n <= r < n_pad is filled with
+// `pad_norm` (+inf for a kNN database: padding columns never win).  *exp_out = e.
+__global__ void split_rows_kernel(const float* __restrict__ x, int n, int D, int Dp, float extra, const unsigned int* __restrict__ max_bits,
+                                  __half* __restrict__ out, float* __restrict__ norm2, int n_pad, float pad_norm,
+                                  unsigned int* __restrict__ max_norm_bits, int* __restrict__ exp_out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float mxa = __uint_as_float(*max_bits);
+  int e = 0;
+  if (mxa > 0.f) {
+    int ex;
+    frexpf(mxa, &ex);                 // mxa = f * 2^ex, f in [0.5, 1)  ->  mxa * 2^(14 - ex) in [2^13, 2^14)
+    e = 14 - ex;
+  }
+  const float scale = ldexpf(extra, e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = e;
   float mx = 0.f;
   for (int r = warp; r < n_pad; r += nwarps) {
     if (r >= n) {
@@ -84,21 +116,31 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int n, int D, int
       continue;
     }
     const float* row = x + static_cast<size_t>(r) * D;
-    __nv_bfloat16* o = out + static_cast<size_t>(r) * 2 * Dp;
+    __half* o = out + static_cast<size_t>(r) * 2 * Dp;
     float ss = 0.f;
     for (int c = lane; c < Dp; c += 32) {
       const float v = c < D ? row[c] : 0.f;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      o[c] = __float2bfloat16_rn(scale * __bfloat162float(hi));
-      o[Dp + c] = __float2bfloat16_rn(scale * __bfloat162float(lo));
+      const float sv = v * scale;                             // exact: power of two (times -2)
+      const __half hi = __float2half_rn(sv);
+      const __half lo = __float2half_rn(sv - __half2float(hi));
+      o[c] = hi;
+      o[Dp + c] = lo;
       ss = fmaf(v, v, ss);
     }
     ss = warp_sum(ss);
     if (lane == 0) norm2[r] = ss;
     mx = fmaxf(mx, ss);
   }
-  if (max_norm_bits != nullptr && lane == 0 && mx > 0.f) atomicMax(max_norm_bits, __float_as_uint(mx));   // non-negative floats order like their bits
+  if (max_norm_bits != nullptr && lane == 0 && mx > 0.f) atomicMax(max_norm_bits, __float_as_uint(mx));
+}
+
+// orderable encoding of a float (unsigned compare == float compare), for atomicMin on scores that may be negative
+__device__ __forceinline__ unsigned int enc_f32(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
 // ------------------------------------------------------------------ item -> tile range
@@ -201,8 +243,11 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
     // ================================================================ epilogue
     const int quarter = warp & 3;            // TMEM lane quarter
     const int half = warp >> 2;              // 128-column half of the 256-column tile
-    float* mysc = scratch + warp * (p.mode == DIST_KNN ? 128 : 32 * 33);
+    float* mysc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + warp * kGWarpScratchPdist);   // pdist: 32 x 33 tile
+    float* mynb = p.mode == DIST_KNN ? scratch + warp * 128 : mysc + 32 * 33;                                     // |b|^2 of 128 columns
     const uint32_t tempty_leader = mapa_shared(smem_u32(tempty_bar), 0);
+    // accumulator -> score units: 2^-(ea+eb); pdist folds the -2 of  |a|^2 + |b|^2 - 2 a.b  in here, kNN has it in A
+    const float unscale = ldexpf(p.mode == DIST_KNN ? 1.f : -2.f, -(__ldg(p.exp_a) + __ldg(p.exp_b)));
     int tile_iter = 0;
     for (int item = cluster_id; item < p.items; item += n_clusters) {
       const ItemRange ir = item_range(p, item);
@@ -211,30 +256,35 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
       const bool row_ok = li < p.rows;
       float td[kCand];
       int tid[kCand];
-      float na = 0.f;
+      float na = 0.f, seed = INFINITY, thr = INFINITY;
       long long rowoff = 0;
       if (p.mode == DIST_KNN) {
 #pragma unroll
         for (int t = 0; t < kCand; ++t) { td[t] = INFINITY; tid[t] = 0x7fffffff; }
+        // whatever an earlier chunk of these queries has published: an upper bound of the final kCand-th best score
+        if (row_ok && ir.n_end > ir.n_begin) seed = dec_f32(*reinterpret_cast<volatile unsigned int*>(p.thr_bits + li));
+        if (!(seed == seed)) seed = INFINITY;
+        thr = seed;
       } else {
         na = row_ok ? __ldg(p.na + gi) : 0.f;
         if (p.mode == DIST_SQUARE_F32 || p.mode == DIST_SQUARE_SYM_F32) rowoff = static_cast<long long>(li) * p.N;
         else rowoff = static_cast<long long>(gi) * p.N - (static_cast<long long>(gi) * (gi + 1)) / 2 - gi - 1;
       }
+      const int row_first = (ir.m_pair * 2 + static_cast<int>(rank)) * kGM + quarter * 32;   // first row of this warp
 
       for (int n_tile = ir.n_begin; n_tile < ir.n_end; ++n_tile, ++tile_iter) {
         const int buf = tile_iter & 1;
         const uint32_t tphase = (tile_iter >> 1) & 1;
         const int n_base = n_tile * kGN + half * 128;                   // first database row of this warp's columns
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kGN + half * 128);
+        // |x|^2 of the warp's 128 columns: one coalesced 512-byte load, broadcast reads below
+        const float4 nb4 = __ldg(reinterpret_cast<const float4*>(p.nb + n_base) + lane);
+        __syncwarp();                                                   // the previous tile's readers are done
+        reinterpret_cast<float4*>(mynb)[lane] = nb4;
+        __syncwarp();
+        mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
+        tc_fence_after();
         if (p.mode == DIST_KNN) {
-          // |x|^2 of the warp's 128 columns: one coalesced 512-byte load, broadcast reads below
-          const float4 nb4 = __ldg(reinterpret_cast<const float4*>(p.nb + n_base) + lane);
-          __syncwarp();                                                 // the previous tile's readers are done
-          reinterpret_cast<float4*>(mysc)[lane] = nb4;
-          __syncwarp();
-          mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
-          tc_fence_after();
           uint32_t v0[16], v1[16];
           tmem_ld16(taddr, v0);
           auto scan16 = [&](const uint32_t* v, int c0) {
@@ -242,19 +292,21 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
             bool any = false;
 #pragma unroll
             for (int c = 0; c < 16; c += 4) {
-              const float4 nb = *reinterpret_cast<const float4*>(mysc + c0 + c);
-              s[c] = __uint_as_float(v[c]) + nb.x;
-              s[c + 1] = __uint_as_float(v[c + 1]) + nb.y;
-              s[c + 2] = __uint_as_float(v[c + 2]) + nb.z;
-              s[c + 3] = __uint_as_float(v[c + 3]) + nb.w;
+              const float4 nb = *reinterpret_cast<const float4*>(mynb + c0 + c);
+              s[c] = fmaf(__uint_as_float(v[c]), unscale, nb.x);
+              s[c + 1] = fmaf(__uint_as_float(v[c + 1]), unscale, nb.y);
+              s[c + 2] = fmaf(__uint_as_float(v[c + 2]), unscale, nb.z);
+              s[c + 3] = fmaf(__uint_as_float(v[c + 3]), unscale, nb.w);
             }
-            const float thr = td[kCand - 1];
 #pragma unroll
             for (int c = 0; c < 16; ++c) any = any || (s[c] < thr);
             if (any) {
 #pragma unroll
               for (int c = 0; c < 16; ++c)
-                if (s[c] < td[kCand - 1]) cand_insert(td, tid, s[c], n_base + c0 + c);
+                if (s[c] < thr) {
+                  cand_insert(td, tid, s[c], n_base + c0 + c);
+                  thr = fminf(td[kCand - 1], seed);
+                }
             }
             __syncwarp();                                               // tcgen05.ld is .sync.aligned: reconverge after the inserts
           };
@@ -268,8 +320,9 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
             scan16(v1, (g + 1) * 16);
           }
         } else {
-          mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
-          tc_fence_after();
+          // every row of the warp valid, every column valid and right of every row's diagonal: no predicates
+          const bool off_diag = p.row0 + row_first + 31 < n_base || (p.mode == DIST_SQUARE_F32 && p.row0 + row_first >= n_base + 128);
+          const bool interior = row_first + 32 <= p.rows && n_base + 128 <= p.N && off_diag;
 #pragma unroll 1
           for (int sub = 0; sub < 4; ++sub) {
             const int c_base = n_base + sub * 32;
@@ -279,24 +332,31 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
             tmem_ld16(taddr + sub * 32 + 16, v + 16);
             tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float nb = __ldg(p.nb + c_base + c);               // padded to whole tiles with zeros
-              const float d2 = fmaf(-2.f, __uint_as_float(v[c]), na + nb);
-              mysc[lane * 33 + c] = sqrtf(fmaxf(d2, 0.f));
+            for (int c = 0; c < 32; c += 4) {
+              const float4 nb = *reinterpret_cast<const float4*>(mynb + sub * 32 + c);
+              mysc[lane * 33 + c] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c]), unscale, na + nb.x), 0.f));
+              mysc[lane * 33 + c + 1] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 1]), unscale, na + nb.y), 0.f));
+              mysc[lane * 33 + c + 2] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 2]), unscale, na + nb.z), 0.f));
+              mysc[lane * 33 + c + 3] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 3]), unscale, na + nb.w), 0.f));
             }
             __syncwarp();
             const int j = c_base + lane;
-            const int row_first = (ir.m_pair * 2 + static_cast<int>(rank)) * kGM + quarter * 32;
-            for (int r = 0; r < 32; ++r) {
-              const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
-              const int rli = row_first + r;
-              const int rgi = p.row0 + rli;
-              const bool ok = rli < p.rows && j < p.N &&
-                              (p.mode == DIST_SQUARE_F32 || j > rgi || (p.mode == DIST_SQUARE_SYM_F32 && j == rgi));
-              if (ok) {
-                const float val = j == rgi ? 0.f : mysc[r * 33 + lane];   // exact zero diagonal (square layouts)
-                if (p.mode == DIST_CONDENSED_F64) static_cast<double*>(p.out)[ro + j] = static_cast<double>(val);
-                else static_cast<float*>(p.out)[ro + j] = val;
+            if (interior && p.mode != DIST_CONDENSED_F64) {
+              float* const o = static_cast<float*>(p.out) + j;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) o[__shfl_sync(0xffffffffu, rowoff, r)] = mysc[r * 33 + lane];
+            } else {
+              for (int r = 0; r < 32; ++r) {
+                const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
+                const int rli = row_first + r;
+                const int rgi = p.row0 + rli;
+                const bool ok = rli < p.rows && j < p.N &&
+                                (p.mode == DIST_SQUARE_F32 || j > rgi || (p.mode == DIST_SQUARE_SYM_F32 && j == rgi));
+                if (ok) {
+                  const float val = j == rgi ? 0.f : mysc[r * 33 + lane];   // exact zero diagonal (square layouts)
+                  if (p.mode == DIST_CONDENSED_F64) static_cast<double*>(p.out)[ro + j] = static_cast<double>(val);
+                  else static_cast<float*>(p.out)[ro + j] = val;
+                }
               }
             }
             if (p.mode == DIST_SQUARE_SYM_F32) {
@@ -319,12 +379,13 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
         const size_t o = (static_cast<size_t>(li) * (2 * p.chunks) + ir.chunk * 2 + half) * kCand;
 #pragma unroll
         for (int t = 0; t < kCand; ++t) { p.part_d[o + t] = td[t]; p.part_i[o + t] = tid[t]; }
+        if (td[kCand - 1] < seed) atomicMin(p.thr_bits + li, enc_f32(td[kCand - 1]));   // publish for the later chunks
       }
     }
   } else if (warp == kMmaWarp) {
     // ============================================================== MMA issuer (leader CTA)
     if (leader) {
-      const uint32_t idesc = make_idesc_f16(2 * kGM, kGN, 1);
+      const uint32_t idesc = make_idesc_f16(2 * kGM, kGN, 0);   // fp16 operands
       const uint32_t hi1024 = desc_hi(1024);
       const uint32_t ring0 = smem_u32(smem_ring), ares0 = smem_u32(smem_ares);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tfull_bar),
@@ -564,23 +625,31 @@ __global__ void segment_mean_kernel(const float* __restrict__ x, const int32_t* 
 }
 
 // ------------------------------------------------------------------ host side
-static int encode_bf16_rows(frb_ctx* ctx, CUtensorMap* tm, const void* base, int rows, int Dp) {
-  // bf16 rows of [hi | lo]; box = 64 elements x 128 rows (one CTA's share of a k-block)
+static int encode_f16_rows(frb_ctx* ctx, CUtensorMap* tm, const void* base, int rows, int Dp) {
+  // fp16 rows of [hi | lo]; box = 64 elements x 128 rows (one CTA's share of a k-block)
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(2 * Dp), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(2 * Dp) * 2};
   cuuint32_t box[2] = {kGK, kGM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(ctx, FRB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d split matrix", (int)r, rows, 2 * Dp);
   return FRB_OK;
 }
 
-static int split_rows(frb_ctx* ctx, const float* d_x, int n, int D, int Dp, float scale, void* d_split, float* d_norm, int n_pad,
-                      float pad_norm, unsigned int* d_max_bits, cudaStream_t st) {
+static int max_abs(frb_ctx* ctx, const float* d_x, size_t n, unsigned int* d_bits, cudaStream_t st) {
+  const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((n + 2047) / 2048, static_cast<size_t>(ctx->num_sms) * 8)));
+  max_abs_kernel<<<grid, 256, 0, st>>>(d_x, n, d_bits);
+  ctx->launches++;
+  return check_last(ctx, "max_abs_kernel");
+}
+
+static int split_rows(frb_ctx* ctx, const float* d_x, int n, int D, int Dp, float extra, const unsigned int* d_max_bits, void* d_split,
+                      float* d_norm, int n_pad, float pad_norm, unsigned int* d_max_norm_bits, int* d_exp, cudaStream_t st) {
   const int grid = std::max(1, std::min((n_pad + 7) / 8, ctx->num_sms * 8));
-  split_rows_kernel<<<grid, 256, 0, st>>>(d_x, n, D, Dp, scale, static_cast<__nv_bfloat16*>(d_split), d_norm, n_pad, pad_norm, d_max_bits);
+  split_rows_kernel<<<grid, 256, 0, st>>>(d_x, n, D, Dp, extra, d_max_bits, static_cast<__half*>(d_split), d_norm, n_pad, pad_norm,
+                                          d_max_norm_bits, d_exp);
   ctx->launches++;
   return check_last(ctx, "split_rows_kernel");
 }
@@ -627,12 +696,18 @@ int run_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, 
   const int n_pad = round_up(N, kGN);
   void* d_split = nullptr;
   void* d_norm = nullptr;
+  void* misc = nullptr;
   int rc;
   if ((rc = ctx_scratch(ctx, 0, static_cast<size_t>(N) * 2 * Dp * 2, &d_split)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 1, static_cast<size_t>(n_pad) * 4, &d_norm)) != FRB_OK) return rc;
-  if ((rc = split_rows(ctx, d_X, N, D, Dp, 1.f, d_split, static_cast<float*>(d_norm), n_pad, 0.f, nullptr, st)) != FRB_OK) return rc;
+  if ((rc = ctx_scratch(ctx, 6, 64, &misc)) != FRB_OK) return rc;
+  unsigned int* d_maxabs = static_cast<unsigned int*>(misc) + 2;
+  int* d_exp = static_cast<int*>(misc) + 4;
+  FRB_CUDA(ctx, cudaMemsetAsync(misc, 0, 64, st));
+  if ((rc = max_abs(ctx, d_X, static_cast<size_t>(N) * D, d_maxabs, st)) != FRB_OK) return rc;
+  if ((rc = split_rows(ctx, d_X, N, D, Dp, 1.f, d_maxabs, d_split, static_cast<float*>(d_norm), n_pad, 0.f, nullptr, d_exp, st)) != FRB_OK) return rc;
   CUtensorMap tm;
-  if ((rc = encode_bf16_rows(ctx, &tm, d_split, N, Dp)) != FRB_OK) return rc;
+  if ((rc = encode_f16_rows(ctx, &tm, d_split, N, Dp)) != FRB_OK) return rc;
   DistArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = layout == FRB_SQUARE_F32 ? DIST_SQUARE_F32
@@ -649,6 +724,8 @@ int run_pdist(frb_ctx* ctx, const float* d_X, int N, int D, int row0, int rows, 
   a.items = static_cast<int>(items);
   a.na = static_cast<const float*>(d_norm);
   a.nb = static_cast<const float*>(d_norm);
+  a.exp_a = d_exp;
+  a.exp_b = d_exp;
   a.out = d_out;
   a.watchdog = ctx->wd_dev;
   return launch_dist(ctx, a, tm, tm, st);
@@ -664,7 +741,7 @@ static void knn_chunks(frb_ctx* ctx, DistArgs& a) {
   for (int c = 1; c <= max_chunks; ++c) {
     const long long it = static_cast<long long>(a.m_pairs) * c;
     const long long waves = (it + pairs - 1) / pairs;
-    const double eff = static_cast<double>(it) / static_cast<double>(waves * pairs) - 0.004 * c;
+    const double eff = static_cast<double>(it) / static_cast<double>(waves * pairs) - 0.01 * c;
     if (eff > best) { best = eff; chunks = c; }
   }
   a.tiles_per_chunk = (a.n_tiles + chunks - 1) / chunks;
@@ -684,12 +761,20 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   if ((rc = ctx_scratch(ctx, 1, static_cast<size_t>(m_pad) * 4, &dn)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 2, static_cast<size_t>(Q) * 2 * Dp * 2, &qs)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 3, static_cast<size_t>(Q) * 4, &qn)) != FRB_OK) return rc;
-  // misc: [0] max |x|^2 bits, [1] redo count, [2 ..] redo list
-  if ((rc = ctx_scratch(ctx, 6, (static_cast<size_t>(Q) + 2) * 4, &misc)) != FRB_OK) return rc;
+  // misc (32-bit words): [0] max |x|^2 bits, [1] redo count, [2] max|q| bits, [3] max|x| bits, [4] exp(Q), [5] exp(DB),
+  //                      [8, 8+Q) redo list, [8+Q, 8+2Q) published thresholds, [8+2Q, 8+3Q) thresholds of the exact pass
+  if ((rc = ctx_scratch(ctx, 6, (static_cast<size_t>(Q) * 3 + 8) * 4, &misc)) != FRB_OK) return rc;
   unsigned int* d_max_bits = static_cast<unsigned int*>(misc);
   int32_t* d_redo_count = static_cast<int32_t*>(misc) + 1;
-  int32_t* d_redo_list = static_cast<int32_t*>(misc) + 2;
-  FRB_CUDA(ctx, cudaMemsetAsync(misc, 0, 8, st));
+  unsigned int* d_maxabs_q = static_cast<unsigned int*>(misc) + 2;
+  unsigned int* d_maxabs_db = static_cast<unsigned int*>(misc) + 3;
+  int* d_exp_q = static_cast<int*>(misc) + 4;
+  int* d_exp_db = static_cast<int*>(misc) + 5;
+  int32_t* d_redo_list = static_cast<int32_t*>(misc) + 8;
+  unsigned int* d_thr = static_cast<unsigned int*>(misc) + 8 + Q;
+  unsigned int* d_thr2 = d_thr + Q;
+  FRB_CUDA(ctx, cudaMemsetAsync(misc, 0, 32, st));
+  FRB_CUDA(ctx, cudaMemsetAsync(d_thr, 0xff, static_cast<size_t>(Q) * 2 * 4, st));   // "nothing published yet"
 
   DistArgs a;
   memset(&a, 0, sizeof(a));
@@ -704,14 +789,19 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   const size_t part = static_cast<size_t>(Q) * parts * kCand;
   if ((rc = ctx_scratch(ctx, 4, part * 4, &pd)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 5, part * 4, &pi)) != FRB_OK) return rc;
-  // database: plain split, |x|^2 padded with +inf; queries: split scaled by -2 (accumulator = -2 q.x)
-  if ((rc = split_rows(ctx, d_DB, M, D, Dp, 1.f, ds, static_cast<float*>(dn), m_pad, INFINITY, d_max_bits, st)) != FRB_OK) return rc;
-  if ((rc = split_rows(ctx, d_Q, Q, D, Dp, -2.f, qs, static_cast<float*>(qn), Q, 0.f, nullptr, st)) != FRB_OK) return rc;
+  // database: plain split, |x|^2 padded with +inf; queries: split scaled by -2 (accumulator = -2 q.x in scaled units)
+  if ((rc = max_abs(ctx, d_DB, static_cast<size_t>(M) * D, d_maxabs_db, st)) != FRB_OK) return rc;
+  if ((rc = max_abs(ctx, d_Q, static_cast<size_t>(Q) * D, d_maxabs_q, st)) != FRB_OK) return rc;
+  if ((rc = split_rows(ctx, d_DB, M, D, Dp, 1.f, d_maxabs_db, ds, static_cast<float*>(dn), m_pad, INFINITY, d_max_bits, d_exp_db, st)) != FRB_OK) return rc;
+  if ((rc = split_rows(ctx, d_Q, Q, D, Dp, -2.f, d_maxabs_q, qs, static_cast<float*>(qn), Q, 0.f, nullptr, d_exp_q, st)) != FRB_OK) return rc;
   CUtensorMap tmA, tmB;
-  if ((rc = encode_bf16_rows(ctx, &tmA, qs, Q, Dp)) != FRB_OK) return rc;
-  if ((rc = encode_bf16_rows(ctx, &tmB, ds, M, Dp)) != FRB_OK) return rc;
+  if ((rc = encode_f16_rows(ctx, &tmA, qs, Q, Dp)) != FRB_OK) return rc;
+  if ((rc = encode_f16_rows(ctx, &tmB, ds, M, Dp)) != FRB_OK) return rc;
   a.na = static_cast<const float*>(qn);
   a.nb = static_cast<const float*>(dn);
+  a.exp_a = d_exp_q;
+  a.exp_b = d_exp_db;
+  a.thr_bits = d_thr;
   a.part_d = static_cast<float*>(pd);
   a.part_i = static_cast<int32_t*>(pi);
   a.watchdog = ctx->wd_dev;
@@ -733,7 +823,8 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   qcn = static_cast<uint8_t*>(qcs) + static_cast<size_t>(redo) * 2 * Dp * 2;
   knn_gather_redo_kernel<<<std::min(redo, ctx->num_sms * 4), 128, 0, st>>>(d_redo_list, d_redo_count, d_Q, D, static_cast<float*>(qc));
   ctx->launches++;
-  if ((rc = split_rows(ctx, static_cast<const float*>(qc), redo, D, Dp, -2.f, qcs, static_cast<float*>(qcn), redo, 0.f, nullptr, st)) != FRB_OK) return rc;
+  // (same power-of-two scale as the whole query matrix: the subset's largest element is not larger)
+  if ((rc = split_rows(ctx, static_cast<const float*>(qc), redo, D, Dp, -2.f, d_maxabs_q, qcs, static_cast<float*>(qcn), redo, 0.f, nullptr, d_exp_q, st)) != FRB_OK) return rc;
   DistArgs e = a;
   e.segs = 3;
   e.a_resident = 0;
@@ -749,8 +840,9 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
     e.part_i = static_cast<int32_t*>(pi);
   }
   e.na = static_cast<const float*>(qcn);
+  e.thr_bits = d_thr2;
   CUtensorMap tmC;
-  if ((rc = encode_bf16_rows(ctx, &tmC, qcs, redo, Dp)) != FRB_OK) return rc;
+  if ((rc = encode_f16_rows(ctx, &tmC, qcs, redo, Dp)) != FRB_OK) return rc;
   if ((rc = launch_dist(ctx, e, tmC, tmB, st)) != FRB_OK) return rc;
   knn_merge_kernel<<<(redo + 3) / 4, 128, 0, st>>>(e.part_d, e.part_i, redo, eparts, k, 1, nullptr, nullptr, D, e.na, e.nb, d_max_bits,
                                                    d_redo_list, d_idx, d_dist, nullptr, nullptr);

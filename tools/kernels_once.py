@@ -30,6 +30,15 @@ KQ, KM = int(os.environ.get("FRB_KNN_Q", "8192")), int(os.environ.get("FRB_KNN_M
 
 def main():
     ctx = _lib.Context(0)
+    info = {}
+    if os.environ.get("FRB_SKIP_GLUE", "0") == "0":
+        info = glue(ctx)
+    if os.environ.get("FRB_SKIP_DIST", "0") == "0":
+        info.update(dist(ctx))
+    print(json.dumps(info))
+
+
+def glue(ctx):
     pipe = FacePipeline("r50", min_face_size=20, save_every=1, ctx=ctx)
     mid = pipe.detector.model_id
     fr = torch.from_numpy(synth.clip(1234, 0, B, H, Wd)).cuda()
@@ -60,8 +69,12 @@ def main():
             "crop_resize_kernel": crop_px * 3 + len(rects) * 160 * 160 * 16,
         },
     }
-    del x16, loc, conf, landm
+    return info
+
+
+def dist(ctx):
     # ---- distance stage, reduced sizes (same kernels, same tile shapes as configs[3] / configs[4])
+    info = {}
     X = embeddings(PN, 7, mean_of=2)
     cond = torch.empty(PN * (PN - 1) // 2, dtype=torch.float32, device="cuda")
     DB = embeddings(KM, 11, centres=10000)
@@ -72,8 +85,8 @@ def main():
         torch.cuda.synchronize()
     info["pdist"] = {"N": PN, "D": 512, "algorithmic_flop": PN * (PN - 1) / 2 * 512 * 2, "out_bytes": PN * (PN - 1) // 2 * 4}
     info["knn"] = {"Q": KQ, "M": KM, "D": 512, "algorithmic_flop": 2.0 * KQ * KM * 512,
-                   "min_bytes": (KQ + KM) * 512 * 2 + KQ * 10 * 8}
-    print(json.dumps(info))
+                   "min_bytes": (KQ + KM) * 512 * 2 + KQ * 10 * 8, "queries_through_exact_pass": ops.knn_redo_count(ctx)}
+    return info
 
 
 if __name__ == "__main__":
