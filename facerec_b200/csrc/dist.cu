@@ -31,6 +31,7 @@
 // (leader CTA only; allocates TMEM in both), warp 9 TMA producer (both CTAs; completion bytes go to the leader's barrier).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
@@ -78,6 +79,7 @@ struct DistArgs {
   float* part_d;         // kNN partial lists [Qrows, parts = 2 * chunks, kCand]
   int32_t* part_i;
   int* watchdog;
+  int dbg;               // debug build only (FRB_DIST_DBG): 1 = the epilogue only hands the accumulators back (timing the MMA + TMA side)
 };
 
 // ------------------------------------------------------------------ fp32 -> scaled (hi | lo) fp16 + norms
@@ -132,6 +134,13 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int n, int D, int
     mx = fmaxf(mx, ss);
   }
   if (max_norm_bits != nullptr && lane == 0 && mx > 0.f) atomicMax(max_norm_bits, __float_as_uint(mx));
+}
+
+// MUFU.SQRT (<= 1 ulp): the IEEE sqrtf sequence was a third of the pdist epilogue's instructions
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // orderable encoding of a float (unsigned compare == float compare), for atomicMin on scores that may be negative
@@ -284,6 +293,14 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
         __syncwarp();
         mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
         tc_fence_after();
+#ifdef FRB_DEBUG_BUILD
+        if (p.dbg & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);
+          continue;
+        }
+#endif
         if (p.mode == DIST_KNN) {
           uint32_t v0[16], v1[16];
           tmem_ld16(taddr, v0);
@@ -334,17 +351,24 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
               const float4 nb = *reinterpret_cast<const float4*>(mynb + sub * 32 + c);
-              mysc[lane * 33 + c] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c]), unscale, na + nb.x), 0.f));
-              mysc[lane * 33 + c + 1] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 1]), unscale, na + nb.y), 0.f));
-              mysc[lane * 33 + c + 2] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 2]), unscale, na + nb.z), 0.f));
-              mysc[lane * 33 + c + 3] = sqrtf(fmaxf(fmaf(__uint_as_float(v[c + 3]), unscale, na + nb.w), 0.f));
+              mysc[lane * 33 + c] = sqrt_fast(fmaxf(fmaf(__uint_as_float(v[c]), unscale, na + nb.x), 0.f));
+              mysc[lane * 33 + c + 1] = sqrt_fast(fmaxf(fmaf(__uint_as_float(v[c + 1]), unscale, na + nb.y), 0.f));
+              mysc[lane * 33 + c + 2] = sqrt_fast(fmaxf(fmaf(__uint_as_float(v[c + 2]), unscale, na + nb.z), 0.f));
+              mysc[lane * 33 + c + 3] = sqrt_fast(fmaxf(fmaf(__uint_as_float(v[c + 3]), unscale, na + nb.w), 0.f));
             }
             __syncwarp();
             const int j = c_base + lane;
             if (interior && p.mode != DIST_CONDENSED_F64) {
-              float* const o = static_cast<float*>(p.out) + j;
+              // running row offset: square rows are N apart, condensed row g + 1 starts N - g - 2 entries after row g
+              float* o = static_cast<float*>(p.out) + j + __shfl_sync(0xffffffffu, rowoff, 0);
+              const bool square = p.mode == DIST_SQUARE_F32 || p.mode == DIST_SQUARE_SYM_F32;
+              int step = square ? p.N : p.N - (p.row0 + row_first) - 2;
 #pragma unroll 8
-              for (int r = 0; r < 32; ++r) o[__shfl_sync(0xffffffffu, rowoff, r)] = mysc[r * 33 + lane];
+              for (int r = 0; r < 32; ++r) {
+                *o = mysc[r * 33 + lane];
+                o += step;
+                step -= square ? 0 : 1;
+              }
             } else {
               for (int r = 0; r < 32; ++r) {
                 const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
@@ -461,12 +485,14 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
           if (elect_one()) {
             const uint32_t st = ring0 + static_cast<uint32_t>(stage * stage_bytes);
             const uint32_t fb = full_leader + static_cast<uint32_t>(stage) * 8u;
+            {
             if (leader) mbar_expect_tx_a(smem_u32(full_bar) + stage * 8, static_cast<uint32_t>(2 * stage_bytes));
             if (!p.a_resident) {
               tma_load_2d_2cta(st, &tmA, fb, a_x, a_row);
               tma_load_2d_2cta(st + kGABytes, &tmB, fb, b_x, b_row);
             } else {
               tma_load_2d_2cta(st, &tmB, fb, b_x, b_row);
+            }
             }
           }
           __syncwarp();
@@ -675,6 +701,10 @@ static int launch_dist(frb_ctx* ctx, DistArgs& a, const CUtensorMap& tmA, const 
     smem = dist_plan(a);
   }
   if (smem == 0) return set_err(ctx, FRB_ERR_INVALID, "distance kernel: shared-memory plan does not fit (D = %d)", a.Dp);
+#ifdef FRB_DEBUG_BUILD
+  if (const char* e = getenv("FRB_DIST_DBG")) a.dbg = atoi(e);
+  if (const char* e = getenv("FRB_DIST_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
+#endif
   if (!ctx->attr_dist) {
     FRB_CUDA(ctx, cudaFuncSetAttribute(dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ctx->attr_dist = true;
@@ -817,6 +847,9 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   FRB_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->knn_redo_last = redo;
   if (redo == 0) return FRB_OK;
+#ifdef FRB_DEBUG_BUILD
+  if (a.dbg) return FRB_OK;              // timing experiments produce garbage candidates: do not chase them
+#endif
   void *qc = nullptr, *qcs = nullptr, *qcn = nullptr;
   if ((rc = ctx_scratch(ctx, 7, static_cast<size_t>(redo) * D * 4 + static_cast<size_t>(redo) * 2 * Dp * 2 + static_cast<size_t>(redo) * 4 + 512, &qc)) != FRB_OK) return rc;
   qcs = static_cast<uint8_t*>(qc) + ((static_cast<size_t>(redo) * D * 4 + 255) & ~static_cast<size_t>(255));
