@@ -61,6 +61,7 @@ class VideoSource:
     def __init__(self, path: str, display_width: Optional[int] = None, display_height: Optional[int] = None):
         import cv2
         self.cv2 = cv2
+        self.path = path
         self.cap = cv2.VideoCapture(path)
         self.n_frames = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
         assert self.n_frames > 0, "Invalid video file <" + path + "> cwd=" + os.getcwd()
@@ -73,6 +74,10 @@ class VideoSource:
             self.width = round(self.video_h * (self.video_w / self.video_h) * par)
         else:
             self.width, self.height = display_width, display_height
+
+    def reopen(self) -> "VideoSource":
+        """A second, independent handle on the same file (one per decoder thread)."""
+        return VideoSource(self.path, self.width, self.height)
 
     def seek(self, index: int):
         assert self.cap.set(self.cv2.CAP_PROP_POS_FRAMES, index), f"Couldn't set start frame to: {index}"
@@ -150,6 +155,100 @@ class PreloadedSource:
         pass
 
 
+class BatchReader:
+    """T decoder threads filling a ring of batch buffers in order.  Thread t decodes batches t, t + T, ... (each with its
+    own handle on the source when T > 1, seeking to the batch's first frame); `next()` hands the batches out in order as
+    (numpy view, torch view) of a ring slot, None at the end of the stream, and re-raises a decoder's exception.
+    A thread may run at most T batches ahead of the consumer, which is what keeps a slot from being overwritten while
+    the extractor still reads it (ring = T + 5 slots, see Extractor.process_video)."""
+
+    def __init__(self, src, ring, batch: int, first_frame: int, n_frames: int, n_threads: int = 1):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.src, self.ring, self.batch = src, ring, batch
+        self.first, self.n_frames = first_frame, n_frames
+        self.n_batches = (n_frames + batch - 1) // batch
+        self.T = max(1, min(n_threads, max(self.n_batches, 1)))
+        self.cv = threading.Condition()
+        self.ready = {}               # batch index -> frames decoded (or an exception)
+        self.taken = 0                # batches handed to the consumer so far
+        self.stop = False
+        self.copiers = ThreadPoolExecutor(max_workers=4)     # numpy releases the GIL while it copies a frame into its slot
+        self.threads = [threading.Thread(target=self._run, args=(t,), daemon=True) for t in range(self.T)]
+        for th in self.threads:
+            th.start()
+
+    def _run(self, tid: int):
+        src = None
+        try:
+            src = self.src if tid == 0 else self.src.reopen()
+            into = getattr(src, "read_into", None)
+            pos = None                                  # frame index the handle is positioned at
+            for k in range(tid, self.n_batches, self.T):
+                with self.cv:
+                    while not self.stop and k >= self.taken + self.T + 1:
+                        self.cv.wait()
+                    if self.stop:
+                        return
+                start = self.first + k * self.batch
+                want = min(self.batch, self.n_frames - k * self.batch)
+                if pos != start and (self.T > 1 or k > 0):
+                    src.seek(start)                     # thread 0 of a single-thread reader was positioned by the caller
+                arr = self.ring[k % len(self.ring)].numpy()
+                n = 0
+                copies = []
+                while n < want:
+                    if into is not None:
+                        if not into(arr[n]):
+                            break
+                    else:
+                        fr = src.read()
+                        if fr is None:
+                            break
+                        copies.append(self.copiers.submit(np.copyto, arr[n], fr))
+                    n += 1
+                for c in copies:
+                    c.result()
+                pos = start + n
+                with self.cv:
+                    self.ready[k] = n
+                    self.cv.notify_all()
+                if n < want:                            # the stream ended early: later batches do not exist
+                    return
+        except BaseException as e:                      # noqa: BLE001 - surface decode errors on the consumer side
+            with self.cv:
+                self.ready[-1] = e
+                self.cv.notify_all()
+        finally:
+            if src is not None and tid != 0:
+                src.close()
+
+    def next(self):
+        k = self.taken
+        if k >= self.n_batches:
+            return None
+        with self.cv:
+            while k not in self.ready and -1 not in self.ready:
+                self.cv.wait()
+            if k not in self.ready:
+                raise self.ready[-1]
+            n = self.ready.pop(k)
+            self.taken += 1
+            if n < min(self.batch, self.n_frames - k * self.batch):
+                self.n_batches = k + 1              # short read: this is the last batch
+            self.cv.notify_all()
+        if n == 0:
+            return None
+        t = self.ring[k % len(self.ring)]
+        return t.numpy()[:n], t[:n]
+
+    def close(self):
+        with self.cv:
+            self.stop = True
+            self.cv.notify_all()
+        self.copiers.shutdown(wait=False)
+
+
 # --------------------------------------------------------------------------------------- writers
 def trajectory_record(trk, max_w: int, max_h: int) -> dict:
     """One trajectories.jsonl line (facerec/extract.py:55-80); `index`/`movie_id` are added by merge_shards.py."""
@@ -212,7 +311,8 @@ def save_thumbnail(img_np, filtered_box, d_width, d_height, path):
 class Extractor:
     def __init__(self, detector, embedder, tracker, out_path: str = "./data", n_shards: int = 256, shard_i: int = 0,
                  save_every: int = 5, min_trajectory: int = 3, max_trajectory_age: int = 5, save_images: bool = True,
-                 emb_keys: Optional[List[str]] = None, batch: int = 64, display_width=None, display_height=None):
+                 emb_keys: Optional[List[str]] = None, batch: int = 64, display_width=None, display_height=None,
+                 decode_threads: int = 1):
         self.detector, self.embedder, self.tracker = detector, embedder, tracker
         self.out_path = out_path.rstrip("/")
         self.n_shards, self.shard_i = n_shards, shard_i
@@ -221,6 +321,7 @@ class Extractor:
         self.emb_keys = list(emb_keys) if emb_keys else list(FACENET_KEYS)
         self.batch = batch
         self.display_width, self.display_height = display_width, display_height
+        self.decode_threads = decode_threads
 
     def process_video(self, file: str):
         import torch
@@ -320,58 +421,20 @@ class Extractor:
                 features_file.write("\n")
             pending.clear()
 
-        # Frame ingest: a reader thread decodes the next batches into (pinned) host buffers while the
-        # GPU works on the current one; cv2 releases the GIL while decoding.
-        import queue
-        import threading
-        n_to_read = end_overlap - beg
-        batches_q: "queue.Queue" = queue.Queue(maxsize=1)
+        # Frame ingest: decoder threads fill (pinned) batch buffers while the GPU works on earlier ones;
+        # cv2 releases the GIL while decoding.  Thread t owns batches t, t + T, ...: it opens the file itself, seeks to
+        # the first frame of its batch (the reference relies on the same CAP_PROP_POS_FRAMES seek for its shards,
+        # facerec/extract.py:233) and decodes straight INTO the batch's ring slot (no np.stack, no pin_memory copy: both
+        # were a full extra pass over 400 MB per 64 x 1080p batch).  One thread decodes 1080p mp4v at ~180 frames/s, far
+        # below what the GPU path consumes, hence --decode-threads.
         pin = device.type == "cuda"
-
-        # Ring of batch buffers the frames are decoded INTO (no np.stack, no pin_memory copy: both were a full extra
-        # pass over 400 MB per 64 x 1080p batch and capped the extractor at ~400 frames/s).  6 slots: one being filled,
-        # one queued, two in flight on the GPU, one being walked by the host, one still referenced by the
-        # min_trajectory-delayed frames of the batch before it.
-        ring = [torch.empty((self.batch, d_height, d_width, 3), dtype=torch.uint8, pin_memory=pin) for _ in range(6)]
-        into = getattr(src, "read_into", None)
-
-        from concurrent.futures import ThreadPoolExecutor
-        copiers = ThreadPoolExecutor(max_workers=4)     # numpy releases the GIL while it copies a frame into its slot
-
-        def reader():
-            left = n_to_read
-            k = 0
-            try:
-                while left > 0:
-                    t = ring[k % len(ring)]
-                    arr = t.numpy()
-                    n = 0
-                    copies = []
-                    while n < self.batch and n < left:
-                        if into is not None:
-                            if not into(arr[n]):
-                                left = n
-                                break
-                        else:
-                            fr = src.read()
-                            if fr is None:
-                                left = n
-                                break
-                            copies.append(copiers.submit(np.copyto, arr[n], fr))
-                        n += 1
-                    for c in copies:
-                        c.result()
-                    if n == 0:
-                        break
-                    batches_q.put((arr[:n], t[:n]))
-                    left -= n
-                    k += 1
-            except BaseException as e:      # noqa: BLE001 - surface decode errors on the consumer side
-                batches_q.put(e)
-                return
-            batches_q.put(None)
-
-        threading.Thread(target=reader, daemon=True).start()
+        n_to_read = end_overlap - beg
+        reopen = getattr(src, "reopen", None)
+        n_threads = max(1, int(getattr(self, "decode_threads", 1))) if reopen is not None else 1
+        # slots: T being filled + 1 ready + two in flight on the GPU + one walked by the host + one still referenced by
+        # the min_trajectory-delayed frames of the batch before it
+        ring = [torch.empty((self.batch, d_height, d_width, 3), dtype=torch.uint8, pin_memory=pin) for _ in range(n_threads + 5)]
+        reader = BatchReader(src, ring, self.batch, beg, n_to_read, n_threads)
         from collections import deque
         from time import perf_counter
         tm = self.timing = {"wait_reader": 0.0, "launch": 0.0, "wait_detect": 0.0, "host_loop": 0.0, "wait_embed_write": 0.0}
@@ -385,7 +448,7 @@ class Extractor:
             if state["done"]:
                 return
             t0 = perf_counter()
-            item = batches_q.get()
+            item = reader.next()
             t1 = perf_counter()
             tm["wait_reader"] += t1 - t0
             if item is None:
@@ -464,6 +527,7 @@ class Extractor:
             json.dump({"frame_indices": [c for c in scene_changes if beg <= c < end]}, fh, indent=None, separators=(",", ":"))
         features_file.close()
         trajectories_file.close()
+        reader.close()
         src.close()
         print(f"Saved {counts['boxes']} boxes from {counts['frames']} different frames")
         print(f"and {counts['traj']} trajectories.")
@@ -501,7 +565,14 @@ def main(argv=None):
     p.add_argument("--batch", type=int, default=64, help="frames per GPU batch")
     p.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")), help="CUDA device of this shard")
     p.add_argument("--emb-keys", nargs="*", default=FACENET_KEYS, help="keys the embedding is stored under")
-    p.add_argument("--weight-seed", type=int, default=0, help="seed of the random-init weights (no checkpoints offline)")
+    p.add_argument("--detector-weights", default=None,
+                   help="RetinaFace weights: .frbw blob, .npz under this repo's layer names, or a PyTorch state dict under the "
+                        "public RetinaFace names (facerec_b200/convert.py)")
+    p.add_argument("--embedder-weights", default=None,
+                   help="InceptionResnetV1 weights (.frbw / .npz / PyTorch state dict with the public FaceNet names)")
+    p.add_argument("--weight-seed", type=int, default=0,
+                   help="seed of the RANDOM-INIT weights used when no weight file is given (benchmarks and parity tests only)")
+    p.add_argument("--decode-threads", type=int, default=1, help="decoder threads feeding the pinned frame ring (each opens the file and decodes its own frame ranges)")
     p.add_argument("file")
     args = p.parse_args(argv)
 
@@ -510,14 +581,25 @@ def main(argv=None):
     from .detector import B200RetinaFaceDetector
     from .embedder import B200FaceNet
     from .sort import NativeSort as Sort   # csrc/sort.cu; the numpy restatement in sort.py stays as the cross-check
+    from . import convert
     ctx = Context(args.device)
-    detector = B200RetinaFaceDetector(args.min_face_size, args.backbone, seed=args.weight_seed,
+    det_w = convert.load_weights(args.detector_weights, "retina_" + args.backbone) if args.detector_weights else None
+    emb_w = convert.load_weights(args.embedder_weights, "irv1") if args.embedder_weights else None
+    if det_w is None or emb_w is None:
+        import sys
+        print("WARNING: running on seeded RANDOM-INIT weights (" +
+              ", ".join(n for n, w in (("detector", det_w), ("embedder", emb_w)) if w is None) +
+              "): detections and embeddings are only meaningful for benchmarking and parity tests. "
+              "Pass --detector-weights / --embedder-weights for real use; stored actor embeddings must come from the same "
+              "embedder weights.", file=sys.stderr)
+    detector = B200RetinaFaceDetector(args.min_face_size, args.backbone, weights=det_w, seed=args.weight_seed,
                                       threshold=args.face_threshold, ctx=ctx)
-    embedder = B200FaceNet(seed=args.weight_seed, ctx=ctx)
+    embedder = B200FaceNet(weights=emb_w, seed=args.weight_seed, ctx=ctx)
     tracker = Sort(max_age=args.max_trajectory_age, min_hits=args.min_trajectory, iou_threshold=args.iou_threshold)
     dw, dh = read_display_size(os.path.basename(args.file))
     ex = Extractor(detector, embedder, tracker, args.out_path, args.n_shards, args.shard_i, args.save_every,
-                   args.min_trajectory, args.max_trajectory_age, not args.no_images, args.emb_keys, args.batch, dw, dh)
+                   args.min_trajectory, args.max_trajectory_age, not args.no_images, args.emb_keys, args.batch, dw, dh,
+                   decode_threads=args.decode_threads)
     ex.process_video(args.file)
     minutes, seconds = divmod(time() - start, 60)
     print(f"Completed in {int(minutes)} minutes, {int(seconds)} seconds.")

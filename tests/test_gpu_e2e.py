@@ -29,8 +29,12 @@ def test_detect_embed_parity_vs_oracle(ctx, backbone, H, W, n, stride):
     assert s["frac_identical_outside_band"] >= 0.95, s  # identical kept-face sets outside the declared bands
     assert s["face_match_rate"] >= 0.95, s              # >= 95 % of oracle faces reproduced with IoU >= 0.99
     assert abs(s["gpu_faces"] - s["oracle_faces"]) <= max(1, 0.05 * s["oracle_faces"]), s
-    assert s["cos_n_same_rect"] > 0 and s["cos_min_same_rect"] >= 0.999, s
-    assert s["cos_n_all"] >= s["cos_n_same_rect"] and s["cos_min_all"] >= 0.999, s   # unconditional: GPU crop vs oracle crop
+    assert not s["unexplained"], s["unexplained"][:5]   # every difference traced to a decision inside a declared band
+    assert s["cos_n_same_rect"] > 0 and s["cos_min_same_rect"] >= 0.999, s   # same crop rectangle: the embedder alone
+    # unconditional (GPU crop vs oracle crop): a box coordinate within the box noise of a rounding boundary (k + 0.5,
+    # facerec/extract.py:38-53 np.round) moves the crop by one pixel; every such face must sit at such a boundary
+    assert s["cos_n_all"] >= s["cos_n_same_rect"] and s["rect_differs_unexplained"] == 0, s
+    assert s["cos_frac_ge_0999_all"] >= 0.95 and s["cos_min_all"] >= 0.99, s
     assert s["max_landmark_err_px"] < 1.0, s
 
 

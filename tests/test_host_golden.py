@@ -190,17 +190,20 @@ class _FakeEmbedder:
         return np.stack([self.mg.fake_embedding(frames[f, y:y + h, x:x + w].numpy()) for f, x, y, w, h in rects])
 
 
-@pytest.mark.parametrize("n_shards,shard_i,batch,native", [(1, 0, 64, False), (1, 0, 7, True), (2, 0, 5, False), (2, 1, 16, True)])
-def test_extractor_reproduces_reference_process_video(tmp_path, n_shards, shard_i, batch, native):
+@pytest.mark.parametrize("n_shards,shard_i,batch,native,threads", [(1, 0, 64, False, 1), (1, 0, 7, True, 1), (2, 0, 5, False, 1),
+                                                                    (2, 1, 16, True, 1), (1, 0, 7, True, 3), (2, 1, 5, True, 4)])
+def test_extractor_reproduces_reference_process_video(tmp_path, n_shards, shard_i, batch, native, threads):
     """facerec/extract.py:199-369 was run verbatim (fake detector / embedder) by tools/make_golden.py on a lossless
-    clip; the batched extractor must write byte-identical features / trajectories / scene_changes files."""
+    clip; the batched extractor must write byte-identical features / trajectories / scene_changes files, with one
+    decoder thread or several (each seeks to its own batches of the file)."""
     from facerec_b200 import extract, sort as S
     mg = _scripted_faces(0)
     clip = str(tmp_path / "100002-fixture.avi")
     mg.write_fixture_clip(clip, mg.fixture_clip_frames())
     S.KalmanBoxTracker.count = 0
     ex = extract.Extractor(_FakeDetector(mg), _FakeEmbedder(mg), (S.NativeSort if native else S.Sort)(5, 3, 0.5), str(tmp_path / "out"), n_shards, shard_i,
-                           save_every=5, min_trajectory=3, max_trajectory_age=5, save_images=False, batch=batch)
+                           save_every=5, min_trajectory=3, max_trajectory_age=5, save_images=False, batch=batch,
+                           decode_threads=threads)
     with contextlib.redirect_stdout(io.StringIO()):
         ex.process_video(clip)
     gold = _gold("extract_runs.json")[f"{n_shards}_{shard_i}"]

@@ -252,3 +252,93 @@ def test_oracle_r50_backbone_matches_torchvision():
     assert [tuple(t.shape) for t in got] == [(2, 512, 12, 16), (2, 1024, 6, 8), (2, 2048, 3, 4)]
     for a, b in zip(got, ref):
         assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max())
+
+
+def _fake_state_dict(model, rng):
+    """A PyTorch-style state dict under the PUBLIC layer names, random values, plus what folding it must give."""
+    from facerec_b200 import weights as W
+    sd, want = {}, {}
+
+    def conv_bn(conv, bn, ours, sp, eps):
+        w = rng.standard_normal((sp.cout, sp.cin, sp.kh, sp.kw)).astype(np.float32)
+        g, b = rng.uniform(0.5, 1.5, sp.cout).astype(np.float32), rng.standard_normal(sp.cout).astype(np.float32)
+        m, v = rng.standard_normal(sp.cout).astype(np.float32), rng.uniform(0.5, 1.5, sp.cout).astype(np.float32)
+        sd[conv + ".weight"] = torch.from_numpy(w)
+        for k, a in (("weight", g), ("bias", b), ("running_mean", m), ("running_var", v)):
+            sd[f"{bn}.{k}"] = torch.from_numpy(a)
+        sd[bn + ".num_batches_tracked"] = torch.tensor(1)
+        want[ours + ".w"], want[ours + ".b"] = W.fold_bn(w.transpose(0, 2, 3, 1), g, b, m, v, eps)
+
+    def conv_bias(name, ours, sp):
+        w = rng.standard_normal((sp.cout, sp.cin, sp.kh, sp.kw)).astype(np.float32)
+        b = rng.standard_normal(sp.cout).astype(np.float32)
+        sd[name + ".weight"], sd[name + ".bias"] = torch.from_numpy(w), torch.from_numpy(b)
+        want[ours + ".w"], want[ours + ".b"] = w.transpose(0, 2, 3, 1), b
+
+    specs = {sp.name: sp for sp in W.model_specs(model)}
+    if model == "irv1":
+        for n, sp in specs.items():
+            if n == "last_linear":
+                w = rng.standard_normal((512, 1792)).astype(np.float32)
+                g, b = rng.uniform(0.5, 1.5, 512).astype(np.float32), rng.standard_normal(512).astype(np.float32)
+                m, v = rng.standard_normal(512).astype(np.float32), rng.uniform(0.5, 1.5, 512).astype(np.float32)
+                sd["last_linear.weight"] = torch.from_numpy(w)
+                for k, a in (("weight", g), ("bias", b), ("running_mean", m), ("running_var", v)):
+                    sd[f"last_bn.{k}"] = torch.from_numpy(a)
+                want[n + ".w"], want[n + ".b"] = W.fold_bn(w[:, None, None, :], g, b, m, v, 1e-3)
+            elif sp.bn:
+                conv_bn(n + ".conv", n + ".bn", n, sp, 1e-3)
+            else:
+                conv_bias(n, n, sp)
+        return sd, want
+    if model == "retina_mnet025":
+        conv_bn("body.stage1.0.0", "body.stage1.0.1", "body.0", specs["body.0"], 1e-5)
+        blocks = [("stage1", i) for i in range(1, 6)] + [("stage2", i) for i in range(6)] + [("stage3", i) for i in range(2)]
+        for n, (st, i) in enumerate(blocks, start=1):
+            conv_bn(f"body.{st}.{i}.0", f"body.{st}.{i}.1", f"body.{n}.dw", specs[f"body.{n}.dw"], 1e-5)
+            conv_bn(f"body.{st}.{i}.3", f"body.{st}.{i}.4", f"body.{n}.pw", specs[f"body.{n}.pw"], 1e-5)
+    else:
+        conv_bn("body.conv1", "body.bn1", "conv1", specs["conv1"], 1e-5)
+        for l, nb in enumerate(W.R50_BLOCKS, start=1):
+            for i in range(nb):
+                for c in (1, 2, 3):
+                    conv_bn(f"body.layer{l}.{i}.conv{c}", f"body.layer{l}.{i}.bn{c}", f"layer{l}.{i}.conv{c}", specs[f"layer{l}.{i}.conv{c}"], 1e-5)
+                if i == 0:
+                    conv_bn(f"body.layer{l}.{i}.downsample.0", f"body.layer{l}.{i}.downsample.1", f"layer{l}.{i}.down", specs[f"layer{l}.{i}.down"], 1e-5)
+    for k in (1, 2, 3):
+        conv_bn(f"fpn.output{k}.0", f"fpn.output{k}.1", f"fpn.out{k}", specs[f"fpn.out{k}"], 1e-5)
+    for k in (1, 2):
+        conv_bn(f"fpn.merge{k}.0", f"fpn.merge{k}.1", f"fpn.merge{k}", specs[f"fpn.merge{k}"], 1e-5)
+    for k in (1, 2, 3):
+        for ours, theirs in (("c3", "conv3X3"), ("c5_1", "conv5X5_1"), ("c5_2", "conv5X5_2"), ("c7_2", "conv7X7_2"), ("c7_3", "conv7x7_3")):
+            conv_bn(f"ssh{k}.{theirs}.0", f"ssh{k}.{theirs}.1", f"ssh{k}.{ours}", specs[f"ssh{k}.{ours}"], 1e-5)
+        for ours, theirs in (("cls", "ClassHead"), ("box", "BboxHead"), ("ldm", "LandmarkHead")):
+            conv_bias(f"{theirs}.{k - 1}.conv1x1", f"head{k}.{ours}", specs[f"head{k}.{ours}"])
+    return sd, want
+
+
+@pytest.mark.parametrize("model", ["retina_mnet025", "retina_r50", "irv1"])
+def test_checkpoint_converter_folds_public_state_dicts(model, tmp_path):
+    """--detector-weights / --embedder-weights: a state dict under the public RetinaFace / InceptionResnetV1 names (with a
+    DataParallel 'module.' prefix) converts to exactly the BN-folded [Cout,kh,kw,Cin] tensors frb_load_model expects, and
+    survives the .pt -> .frbw -> .npz round trip."""
+    from facerec_b200 import convert, weights as W
+    rng = np.random.RandomState(3)
+    sd, want = _fake_state_dict(model, rng)
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"module." + k: v for k, v in sd.items()}, path)
+    got = convert.load_weights(path, model)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].shape == want[k].shape and np.array_equal(got[k], np.ascontiguousarray(want[k], dtype=np.float32)), k
+    blob = str(tmp_path / "w.frbw")
+    open(blob, "wb").write(W.write_blob(got))
+    again = convert.load_weights(blob, model)
+    assert all(np.array_equal(again[k], got[k]) for k in got)
+    np.savez(str(tmp_path / "w.npz"), **got)
+    assert all(np.array_equal(convert.load_weights(str(tmp_path / "w.npz"), model)[k], got[k]) for k in got)
+    bad = dict(got)
+    bad.pop(next(iter(bad)))
+    np.savez(str(tmp_path / "bad.npz"), **bad)
+    with pytest.raises(ValueError):
+        convert.load_weights(str(tmp_path / "bad.npz"), model)

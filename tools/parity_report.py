@@ -15,8 +15,10 @@ decision whose margin is smaller than its own rounding noise, so a face may legi
 ITS path sits inside a declared band:
     score band   |score - 0.95|          < 1e-3   (of the oracle's or the GPU's score of that prior)
     size band    |min(w, h) - min_size|   < 0.25 px
-    nms band     some other candidate decides its fate with |IoU - 0.4| < 0.01, or with a score gap < 1e-3 to it
-                 (the greedy order of the two flips)
+    nms band     some other candidate q decides its fate: nms_iou = |IoU(p, q) - 0.4| < 0.01 on either side;
+                 nms_order = the scores of p and q are within 1e-3 of each other (the greedy order of the two flips);
+                 nms_cascade = q itself is kept on one side only (its own difference is explained where q is judged) or
+                 q's score sits in the score band
     iou band     the SAME prior is kept on both sides but the two boxes have IoU in [0.97, 0.99) (sub-pixel wobble
                  of a small box; reported separately, never counted as identical)
 `frames_identical`: kept sets equal, every face IoU >= 0.99.  `frames_identical_outside_band`: every difference of the
@@ -26,7 +28,10 @@ which frb_prior_decode_filter / frb_nms reproduce bit for bit (tests/test_gpu_gl
 
 Embedding cosine: `cos_min_same_rect` compares faces whose integer crop rectangle is the same on both sides (the
 embedder alone); `cos_min_all` is unconditional: GPU embedding of the GPU's crop vs oracle embedding of the oracle's
-crop, for every reproduced face (a box coordinate that rounds to the other integer moves the crop by one pixel).
+crop, for every reproduced face.  The crop rectangle is np.round() of the float box (facerec/extract.py:38-53): a
+coordinate within the box noise of a rounding boundary (k + 0.5) lands on the other integer and moves the crop by one
+pixel; `rect_differs_max_dist_to_half` is the largest distance to such a boundary among the faces whose rectangles
+differ (it must stay within the box noise: `rect_differs_unexplained` counts those further than 0.06 px).
 """
 import argparse
 import json
@@ -97,8 +102,14 @@ def _explain(p, me, other, min_size):
             # q decides p's fate on one side and not on the other: its own presence may be borderline too
             q_border = abs(float(me["scores"][q]) - SCORE_THR) < SCORE_BAND or abs(float(other["scores"][q]) - SCORE_THR) < SCORE_BAND
             vm = iou(me["cand"][p][0], me["cand"][q][0], 1.0) if (q in me["cand"] and p in me["cand"]) else v
-            if near_thr or abs(vm - NMS_IOU) < NMS_BAND or flip or q_border or ((q in other["kept"]) != (q in me["kept"])):
-                why.append("nms")
+            if near_thr or abs(vm - NMS_IOU) < NMS_BAND:
+                why.append("nms_iou")
+                break
+            if flip:
+                why.append("nms_order")
+                break
+            if q_border or ((q in other["kept"]) != (q in me["kept"])):
+                why.append("nms_cascade")
                 break
     return why
 
@@ -112,7 +123,8 @@ def run(backbone, H, Wd, n_frames, first=0, stride=7, seed=1234, min_size=20, ba
     st = {"frames": n_frames, "frames_identical": 0, "frames_identical_outside_band": 0, "oracle_faces": 0, "gpu_faces": 0,
           "matched_iou99": 0, "min_iou_matched": 1.0, "max_landmark_err_px": 0.0,
           "cos_min_same_rect": 1.0, "cos_n_same_rect": 0, "cos_min_all": 1.0, "cos_n_all": 0, "cos_below_0999_all": 0,
-          "rect_differs": 0, "explained": {"score": 0, "size": 0, "nms": 0, "iou_wobble": 0}, "unexplained": [],
+          "rect_differs": 0, "rect_differs_max_dist_to_half": 0.0, "rect_differs_unexplained": 0,
+          "explained": {"score": 0, "size": 0, "nms_iou": 0, "nms_order": 0, "nms_cascade": 0, "iou_wobble": 0}, "unexplained": [],
           "max_abs_logit_err": 0.0, "max_abs_score_err": 0.0}
     mid = pipe.detector.model_id
     with torch.no_grad():
@@ -167,6 +179,14 @@ def run(backbone, H, Wd, n_frames, first=0, stride=7, seed=1234, min_size=20, ba
                             st["cos_n_same_rect"] += 1
                         else:
                             st["rect_differs"] += 1
+                            # which coordinate rounded the other way, and how close to the boundary was it?
+                            tb = np.minimum(np.maximum(d[:4], 0), [Wd, H, Wd, H])
+                            tg = np.minimum(np.maximum(got[bj][:4], 0), [Wd, H, Wd, H])
+                            moved = np.round(tb) != np.round(tg)
+                            dist_half = np.abs((tb - np.floor(tb)) - 0.5)
+                            dd = float(dist_half[moved].max()) if moved.any() else 1.0
+                            st["rect_differs_max_dist_to_half"] = max(st["rect_differs_max_dist_to_half"], dd)
+                            st["rect_differs_unexplained"] += int(dd > 0.06)
                 if len(got) != len(used):
                     identical = False
                 st["frames_identical"] += int(identical)
@@ -204,6 +224,7 @@ def run(backbone, H, Wd, n_frames, first=0, stride=7, seed=1234, min_size=20, ba
     st["face_match_rate"] = st["matched_iou99"] / max(st["oracle_faces"], 1)
     st["frac_identical"] = st["frames_identical"] / n_frames
     st["frac_identical_outside_band"] = st["frames_identical_outside_band"] / n_frames
+    st["cos_frac_ge_0999_all"] = 1.0 - st["cos_below_0999_all"] / max(st["cos_n_all"], 1)
     st["cos_min"] = st["cos_min_all"]
     st["cos_n"] = st["cos_n_all"]
     st.update({"backbone": backbone, "H": H, "W": Wd, "first": first, "stride": stride,
