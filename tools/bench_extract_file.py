@@ -1,0 +1,121 @@
+"""End-to-end extractor throughput FROM AN ENCODED FILE (facerec/extract.py:204,233,284,300): writes a
+1080p synthetic clip with cv2.VideoWriter (mp4v by default, as measured in the survey), then runs
+`Extractor.process_video(<file>)` -- decode -> H2D -> detect -> scene cuts -> SORT -> crop/embed -> JSONL -- with 1, 4, 8 ...
+decoder threads, next to (a) the bare decode rate of one cv2 handle and (b) the same extractor on preloaded frames
+("a decoder that keeps up").  `--shards N` runs the N shard invocations of the reference's split back to back in this
+process and leaves their outputs under --out so that the reference's merge_shards.py can be run on them.
+
+  python tools/bench_extract_file.py --frames 1536 --threads 1 4 8 --out gpurun_out/extract_file
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from facerec_b200 import synth, extract  # noqa: E402
+
+
+def write_clip(path, n, W, H, fourcc):
+    import cv2
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*fourcc), 24.0, (W, H))
+    assert vw.isOpened(), f"cannot open VideoWriter for {path} ({fourcc})"
+    t0 = time.time()
+    for i in range(n):
+        vw.write(np.ascontiguousarray(synth.frame(1234, i, H, W)[..., ::-1]))
+    vw.release()
+    return time.time() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=1536)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--backbone", default="r50")
+    ap.add_argument("--fourcc", default="mp4v")
+    ap.add_argument("--threads", type=int, nargs="*", default=[1, 4, 8])
+    ap.add_argument("--shards", type=int, default=0, help="also run the N-shard split with the best thread count and keep its outputs")
+    ap.add_argument("--work", default="/tmp/frb_extract_file", help="scratch directory for the clip and the per-thread-count runs")
+    ap.add_argument("--out", default="gpurun_out/extract_shards", help="where the outputs of the --shards run are kept")
+    a = ap.parse_args()
+    import torch
+    from facerec_b200._lib import Context
+    from facerec_b200.detector import B200RetinaFaceDetector
+    from facerec_b200.embedder import B200FaceNet
+    from facerec_b200.sort import NativeSort as Sort
+    os.makedirs(a.work, exist_ok=True)
+    ext = "avi" if a.fourcc in ("FFV1", "MJPG") else "mp4"
+    clip = os.path.join(a.work, f"100001-synth.{ext}")
+    res = {"clip": {"frames": a.frames, "size": f"{a.width}x{a.height}", "fourcc": a.fourcc, "cpu_cores": os.cpu_count()}}
+    res["clip"]["encode_seconds"] = write_clip(clip, a.frames, a.width, a.height, a.fourcc)
+    res["clip"]["bytes"] = os.path.getsize(clip)
+
+    # (a) bare decode rate of one handle (cap.read + cvtColor into a preallocated frame), facerec/extract.py:284,300
+    src = extract.VideoSource(clip)
+    assert src.n_frames == a.frames, (src.n_frames, a.frames)
+    dst = np.empty((a.height, a.width, 3), np.uint8)
+    t0 = time.time()
+    n = 0
+    while n < min(a.frames, 480) and src.read_into(dst):
+        n += 1
+    res["decode_one_handle_fps"] = n / (time.time() - t0)
+    src.close()
+
+    ctx = Context(0)
+    det = B200RetinaFaceDetector(20, a.backbone, ctx=ctx)
+    emb = B200FaceNet(ctx=ctx)
+
+    def run(source, threads, out_dir, n_shards=1, shard_i=0, keys=None):
+        ex = extract.Extractor(det, emb, Sort(5, 3, 0.5), out_dir, n_shards, shard_i, save_images=False, batch=64,
+                               decode_threads=threads, emb_keys=keys)
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            counts = ex.process_video(source)
+        dt = time.time() - t0
+        torch.cuda.synchronize()
+        return dt, counts, {k: round(v, 3) for k, v in ex.timing.items()}
+
+    # (b) preloaded frames: the extractor without a decoder (first pass warms plans and the arena)
+    pre = extract.PreloadedSource(100001, min(a.frames, 768), a.width, a.height)
+    for rep in range(2):
+        pre.seek(0)
+        dt, counts, tm = run(pre, 1, os.path.join(a.work, "pre"))
+    res["preloaded"] = {"frames": pre.n_frames, "frames_per_s": pre.n_frames / dt, **counts, "main_thread_seconds": tm}
+    del pre
+
+    best = (0.0, 1)
+    for t in a.threads:
+        dt, counts, tm = run(clip, t, os.path.join(a.work, f"t{t}"))
+        fps = a.frames / dt
+        res[f"file_threads{t}"] = {"frames_per_s": fps, "seconds": dt, **counts, "main_thread_seconds": tm,
+                                   "decode_share_of_wall": round(tm["wait_reader"] / dt, 3)}
+        best = max(best, (fps, t))
+    # outputs must not depend on the number of decoder threads
+    ref_dir = os.path.join(a.work, f"t{a.threads[0]}", "100001-data")
+    same = True
+    for t in a.threads[1:]:
+        for sub in ("features", "trajectories", "scene_changes"):
+            for name in sorted(os.listdir(os.path.join(ref_dir, sub))):
+                same = same and open(os.path.join(ref_dir, sub, name)).read() == open(os.path.join(a.work, f"t{t}", "100001-data", sub, name)).read()
+    res["outputs_identical_across_thread_counts"] = same
+    if a.shards > 1:
+        t0 = time.time()
+        tot = {"boxes": 0, "traj": 0}
+        for i in range(a.shards):
+            # one embedding key keeps the kept files small (the reference stores the same vector under four keys)
+            dt, counts, _ = run(clip, best[1], a.out, a.shards, i, keys=[extract.FACENET_KEYS[3]])
+            tot["boxes"] += counts["boxes"]; tot["traj"] += counts["traj"]
+        res["sharded_sequential"] = {"n_shards": a.shards, "threads": best[1], "seconds": time.time() - t0, **tot,
+                                     "out": a.out}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
