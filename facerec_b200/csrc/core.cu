@@ -533,6 +533,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_PDL: ctx->pdl = value; return FRB_OK;
     case FRB_OPT_MPAIR: ctx->mpair = value; return FRB_OK;
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
+    case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
 #ifndef FRB_DEBUG_BUILD
     case FRB_OPT_FORCE_GATHER:
     case FRB_OPT_SKIP_LOADS:

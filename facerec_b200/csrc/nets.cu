@@ -138,6 +138,13 @@ struct Plan {
   std::vector<TensorInfo> tensors;
   std::vector<Op> ops;
   size_t arena_bytes = 0;
+  // CUDA graph of the forward (short forwards only, see use_graph): captured on the second call of a plan, replayed
+  // afterwards.  The graph reads / writes net-owned staging buffers, so it does not depend on the caller's pointers.
+  int calls = 0;
+  cudaGraphExec_t graph = nullptr;
+  long long graph_launches = 0;     // kernels per replay (bench bookkeeping)
+  void* graph_arena = nullptr;      // arena / staging addresses baked into the graph
+  void* graph_io = nullptr;
 };
 
 struct Net {
@@ -149,7 +156,17 @@ struct Net {
   std::map<std::tuple<int, int, int>, Plan> plans;
   void* arena = nullptr;
   size_t arena_bytes = 0;
+  void* io = nullptr;               // staging for the network input and outputs of graph-replayed forwards
+  size_t io_bytes = 0;
 };
+
+static void drop_graphs(Net* net) {
+  for (auto& kv : net->plans)
+    if (kv.second.graph) {
+      cudaGraphExecDestroy(kv.second.graph);
+      kv.second.graph = nullptr;
+    }
+}
 
 static void add_conv(Net* net, const std::string& name, const HostConv& h, int sh, int sw, int ph, int pw, int bn_cap = 0) {
   ConvLayer L;
@@ -640,6 +657,7 @@ static Plan* get_plan(Net* net, int B, int H, int W) {
   if (plan.arena_bytes > net->arena_bytes) {
     if (net->arena) {
       if (cudaDeviceSynchronize() != cudaSuccess) throw std::runtime_error("device sync failed before arena growth");
+      drop_graphs(net);             // they address the old arena
       cudaFree(net->arena);
       net->arena = nullptr;
       net->arena_bytes = 0;
@@ -739,6 +757,107 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
   return FRB_OK;
 }
 
+// ------------------------------------------------------------------------------------ graph replay of short forwards
+// InceptionResnetV1 is 105 launches of 10-35 us, RetinaFace-MobileNet0.25 at 360p 56 launches: per launch the host
+// encodes 3-4 tensor maps and the GPU idles between kernels.  Such a forward is captured once per plan into a CUDA graph
+// (tensor maps and arguments become node parameters) and replayed; network input and outputs go through net-owned
+// staging buffers so that the graph does not depend on the caller's pointers (one small D2D copy on each side).
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct IoLayout {
+  size_t in_bytes = 0, out_bytes[3] = {0, 0, 0}, off[4] = {0, 0, 0, 0}, total = 0;
+};
+
+static IoLayout io_layout(const Net* net, const Plan& plan) {
+  IoLayout l;
+  for (const TensorInfo& t : plan.tensors)
+    if (t.ext == 1) l.in_bytes = static_cast<size_t>(plan.B) * t.H * t.W * t.C * t.elem;
+  if (net->model == FRB_IRV1) {
+    l.out_bytes[0] = static_cast<size_t>(plan.B) * 512 * 4;
+  } else {
+    l.out_bytes[0] = static_cast<size_t>(plan.B) * plan.P_total * 4 * 4;
+    l.out_bytes[1] = static_cast<size_t>(plan.B) * plan.P_total * 2 * 4;
+    l.out_bytes[2] = static_cast<size_t>(plan.B) * plan.P_total * 10 * 4;
+  }
+  l.off[0] = 0;
+  l.off[1] = align256(l.in_bytes);
+  l.off[2] = l.off[1] + align256(l.out_bytes[0]);
+  l.off[3] = l.off[2] + align256(l.out_bytes[1]);
+  l.total = l.off[3] + align256(l.out_bytes[2]);
+  return l;
+}
+
+static bool use_graph(frb_ctx* ctx, const Net* net, const Plan& plan) {
+  if (!ctx->graphs || ctx->layer_times || ctx->trace_mode) return false;
+  const IoLayout l = io_layout(net, plan);
+  if (l.total > (static_cast<size_t>(1) << 30)) return false;                           // staging copies must stay cheap
+  if (net->model == FRB_IRV1) return true;
+  return static_cast<double>(plan.B) * plan.H * plan.W <= 64.0 * 360 * 640 && net->model == FRB_RETINA_MNET025;
+}
+
+static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep, cudaStream_t st);
+
+static int run_plan_graphed(frb_ctx* ctx, Net* net, Plan& plan, const ExecPtrs& ep, cudaStream_t st) {
+  plan.calls++;
+  if (!use_graph(ctx, net, plan) || plan.calls < 2) return run_plan(ctx, net, plan, ep, st);   // the first call also warms caches
+  const IoLayout l = io_layout(net, plan);
+  if (net->io_bytes < l.total) {
+    if (net->io) {
+      FRB_CUDA(ctx, cudaDeviceSynchronize());
+      drop_graphs(net);
+      FRB_CUDA(ctx, cudaFree(net->io));
+      net->io = nullptr;
+      net->io_bytes = 0;
+    }
+    FRB_CUDA(ctx, cudaMalloc(&net->io, l.total));
+    net->io_bytes = l.total;
+  }
+  uint8_t* io = static_cast<uint8_t*>(net->io);
+  if (plan.graph != nullptr && (plan.graph_arena != net->arena || plan.graph_io != net->io)) {
+    cudaGraphExecDestroy(plan.graph);
+    plan.graph = nullptr;
+  }
+  ExecPtrs gp;
+  gp.in = io + l.off[0];
+  if (net->model == FRB_IRV1) {
+    gp.emb = reinterpret_cast<float*>(io + l.off[1]);
+  } else {
+    gp.loc = reinterpret_cast<float*>(io + l.off[1]);
+    gp.conf = reinterpret_cast<float*>(io + l.off[2]);
+    gp.landm = reinterpret_cast<float*>(io + l.off[3]);
+  }
+  if (plan.graph == nullptr) {
+    const long long l0 = ctx->launches;
+    cudaGraph_t g = nullptr;
+    FRB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc = run_plan(ctx, net, plan, gp, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc != FRB_OK) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    FRB_CUDA(ctx, ce);
+    const cudaError_t ie = cudaGraphInstantiate(&plan.graph, g, 0);
+    cudaGraphDestroy(g);
+    FRB_CUDA(ctx, ie);
+    plan.graph_launches = ctx->launches - l0;
+    ctx->launches = l0;                          // counted per replay below
+    plan.graph_arena = net->arena;
+    plan.graph_io = net->io;
+  }
+  FRB_CUDA(ctx, cudaMemcpyAsync(io + l.off[0], ep.in, l.in_bytes, cudaMemcpyDeviceToDevice, st));
+  FRB_CUDA(ctx, cudaGraphLaunch(plan.graph, st));
+  ctx->launches += plan.graph_launches;
+  if (net->model == FRB_IRV1) {
+    FRB_CUDA(ctx, cudaMemcpyAsync(ep.emb, io + l.off[1], l.out_bytes[0], cudaMemcpyDeviceToDevice, st));
+  } else {
+    FRB_CUDA(ctx, cudaMemcpyAsync(ep.loc, io + l.off[1], l.out_bytes[0], cudaMemcpyDeviceToDevice, st));
+    FRB_CUDA(ctx, cudaMemcpyAsync(ep.conf, io + l.off[2], l.out_bytes[1], cudaMemcpyDeviceToDevice, st));
+    FRB_CUDA(ctx, cudaMemcpyAsync(ep.landm, io + l.off[3], l.out_bytes[2], cudaMemcpyDeviceToDevice, st));
+  }
+  return FRB_OK;
+}
+
 Net* build_net(frb_ctx* ctx, int model_id, const void* blob, size_t bytes) {
   Net* net = new Net();
   net->model = model_id;
@@ -759,6 +878,8 @@ Net* build_net(frb_ctx* ctx, int model_id, const void* blob, size_t bytes) {
 
 void destroy_net(Net* net) {
   if (net == nullptr) return;
+  drop_graphs(net);
+  if (net->io) cudaFree(net->io);
   std::vector<bool> seen(net->convs.size(), false);
   for (auto& L : net->convs) conv_release(L);
   for (auto& L : net->dws) {
@@ -776,7 +897,7 @@ int net_forward_retina(frb_ctx* ctx, Net* net, const void* d_in, int B, int H, i
     Plan* plan = get_plan(net, B, H, W);
     ExecPtrs ep;
     ep.in = d_in; ep.loc = d_loc; ep.conf = d_conf; ep.landm = d_landm;
-    return run_plan(ctx, net, *plan, ep, stream);
+    return run_plan_graphed(ctx, net, *plan, ep, stream);
   } catch (const std::exception& e) {
     return set_err(ctx, FRB_ERR_INVALID, "retina_forward: %s", e.what());
   }
@@ -788,7 +909,7 @@ int net_forward_irv1(frb_ctx* ctx, Net* net, const void* d_in, int F, float* d_e
     Plan* plan = get_plan(net, F, 160, 160);
     ExecPtrs ep;
     ep.in = d_in; ep.emb = d_emb;
-    return run_plan(ctx, net, *plan, ep, stream);
+    return run_plan_graphed(ctx, net, *plan, ep, stream);
   } catch (const std::exception& e) {
     return set_err(ctx, FRB_ERR_INVALID, "irv1_forward: %s", e.what());
   }

@@ -62,8 +62,10 @@ enum frb_option {
                            /* tail): 0 never, 1 (default) launches estimated under 100 us, 2 always                  */
   FRB_OPT_WEIGHT_SLICE = 11,/* 0: stream the weights of every tile (default 1: a CTA keeps its N tile's weights in    */
                            /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
-  FRB_OPT_MPAIR = 12       /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
+  FRB_OPT_MPAIR = 12,      /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
                            /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
+  FRB_OPT_GRAPHS = 13      /* 0: every forward launches its kernels one by one (default 1: short forwards - InceptionResnetV1, */
+                           /* RetinaFace-MobileNet0.25 up to 64 x 360p - are captured once per shape into a CUDA graph)        */
   /* values 2, 4, 7, 8 are timing / tracing experiments that only a debug build of the library honours:
      include/facerec_b200_debug.h */
 };

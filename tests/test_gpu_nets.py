@@ -123,3 +123,39 @@ def test_dependent_launch_policy_does_not_change_results(ctx, pdl):
             if opt is not None:
                 c.close()
     assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+def test_graph_replay_equals_eager_launches(ctx):
+    """FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 at 360p) are captured into a CUDA graph
+    on their second call and replayed through net-owned staging buffers; results are the bits of the eager launches, for
+    changing input / output pointers and interleaved batch sizes (one graph per shape)."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(8)
+    irv1 = weights.MODEL_IDS["irv1"]
+    mnet = weights.MODEL_IDS["retina_mnet025"]
+    gen = torch.Generator().manual_seed(4)
+    faces = {n: torch.zeros(n, 160, 160, 8) for n in (8, 32)}
+    for n in faces:
+        faces[n][..., :3] = torch.randn(n, 160, 160, 3, generator=gen) * 0.5
+    fr = [torch.from_numpy(_frames(rng, 4, 360, 640)).cuda() for _ in range(2)]
+    eager = _lib.Context(0)
+    try:
+        eager.set_option(_lib.FRB_OPT_GRAPHS, 0)
+        want = {}
+        for c in (eager, ctx):
+            ops.load_model(c, irv1, weights.write_blob(weights.synth_weights("irv1", 0)))
+            ops.load_model(c, mnet, weights.write_blob(weights.synth_weights("retina_mnet025", 0)))
+        for n in faces:
+            want[n] = ops.irv1_forward(eager, faces[n].half().cuda()).clone()
+        want_det = [[t.clone() for t in ops.retina_forward(eager, mnet, ops.preprocess_u8(eager, f, True), 360, 640)] for f in fr]
+        l0 = ctx.launch_count()
+        for rep in range(4):                          # call 1 eager, call 2 captures, calls 3+ replay; shapes interleaved
+            for n in (8, 32):
+                got = ops.irv1_forward(ctx, faces[n].half().cuda().clone())      # a fresh input pointer every time
+                assert torch.equal(got, want[n]), (rep, n)
+            for f, w in zip(fr, want_det):
+                got = ops.retina_forward(ctx, mnet, ops.preprocess_u8(ctx, f, True), 360, 640)
+                assert all(torch.equal(a, b) for a, b in zip(got, w)), rep
+        assert ctx.launch_count() - l0 > 4 * 2 * 100   # replays are counted with the kernels they contain
+    finally:
+        eager.close()
