@@ -58,35 +58,42 @@ static inline int grid_for(long long work, int block, int num_sms, int per_sm = 
 
 // ------------------------------------------------------------------------------------------ K1
 // u8 HWC -> 16-bit NHWC(8): RetinaFace input is BGR minus (104,117,123), channels 3..7 zero.
-// One thread = 4 pixels: three 32-bit loads (12 B), four 16 B stores.
+// A block stages 1024 pixels (3 KB, coalesced 32-bit loads) in shared memory; then consecutive lanes write consecutive
+// 16-byte pixels, i.e. 512 contiguous bytes per warp store (the first version let every thread write its own four
+// pixels: half-filled sectors per store, 2.5x the algorithmic bytes through L2, 3.3 TB/s;
+// profiles/r02_glue_dist_launches_v0.csv).
+constexpr int kPreTile = 1024;      // pixels per block iteration
+
 template <bool kBF16>
-__global__ void preprocess_kernel(const uint8_t* __restrict__ in, long long npix, int src_is_rgb,
-                                  uint4* __restrict__ out) {
-  const long long nquad = (npix + 3) >> 2;
-  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < nquad;
-       q += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p0 = q << 2;
-    uint8_t px[12];
-    if (p0 + 4 <= npix) {
-      const uint32_t* s = reinterpret_cast<const uint32_t*>(in + p0 * 3);   // p0*3 is a multiple of 12
-      const uint32_t a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
-      memcpy(px, &a, 4); memcpy(px + 4, &b, 4); memcpy(px + 8, &c, 4);
-    } else {
-      for (int i = 0; i < 12; ++i) px[i] = (p0 * 3 + i < npix * 3) ? in[p0 * 3 + i] : 0;
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ in, long long npix, int src_is_rgb,
+                                                          uint4* __restrict__ out) {
+  __shared__ uint32_t s_px[kPreTile * 3 / 4];
+  const uint8_t* s_b = reinterpret_cast<const uint8_t*>(s_px);
+  const long long ntiles = (npix + kPreTile - 1) / kPreTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long p0 = tile * kPreTile;
+    const int n = static_cast<int>(min(static_cast<long long>(kPreTile), npix - p0));
+    const uint8_t* src = in + p0 * 3;                                   // p0 * 3 is a multiple of 4
+    const int nbytes = n * 3;
+    for (int w = threadIdx.x; w < (nbytes + 3) / 4; w += 256) {
+      uint32_t v;
+      if (w * 4 + 4 <= nbytes) v = __ldg(reinterpret_cast<const uint32_t*>(src) + w);
+      else {
+        v = 0;
+        for (int i = 0; w * 4 + i < nbytes; ++i) v |= static_cast<uint32_t>(src[w * 4 + i]) << (8 * i);
+      }
+      s_px[w] = v;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (p0 + i >= npix) break;
-      const float c0 = px[i * 3 + 0], c1 = px[i * 3 + 1], c2 = px[i * 3 + 2];
-      const float bl = (src_is_rgb ? c2 : c0) - 104.f;
-      const float gr = c1 - 117.f;
-      const float rd = (src_is_rgb ? c0 : c2) - 123.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float c0 = s_b[i * 3 + 0], c1 = s_b[i * 3 + 1], c2 = s_b[i * 3 + 2];
       uint4 o;
-      o.x = H16<kBF16>::down(bl, gr);
-      o.y = H16<kBF16>::down(rd, 0.f);
+      o.x = H16<kBF16>::down((src_is_rgb ? c2 : c0) - 104.f, c1 - 117.f);
+      o.y = H16<kBF16>::down((src_is_rgb ? c0 : c2) - 123.f, 0.f);
       o.z = 0u; o.w = 0u;
       out[p0 + i] = o;
     }
+    __syncthreads();
   }
 }
 
@@ -95,7 +102,7 @@ int launch_preprocess(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W
   if (out_c != 8) return set_err(ctx, FRB_ERR_INVALID, "preprocess: out_c must be 8");
   if (reinterpret_cast<uintptr_t>(d_frames) & 3) return set_err(ctx, FRB_ERR_INVALID, "preprocess: frames must be 4-byte aligned");
   const long long npix = static_cast<long long>(B) * H * W;
-  const int grid = grid_for((npix + 3) / 4, 256, ctx->num_sms);
+  const int grid = grid_for((npix + kPreTile - 1) / kPreTile, 1, ctx->num_sms, 8);
   if (ctx->use_bf16) preprocess_kernel<true><<<grid, 256, 0, st>>>(d_frames, npix, src_is_rgb, static_cast<uint4*>(d_out));
   else preprocess_kernel<false><<<grid, 256, 0, st>>>(d_frames, npix, src_is_rgb, static_cast<uint4*>(d_out));
   ctx->launches++;
@@ -106,50 +113,76 @@ int launch_preprocess(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W
 // Every output pixel holds the 2x2 input block (dy, dx) x (B-104, G-117, R-123, 0); two zero
 // pixels on the left and one on the right are the horizontal padding of the 7x7/s2 stem, which
 // thereby turns into a 4-row x 64-element window conv that TMA can feed directly (nets.cu).
+// One thread = TWO adjacent output pixels: per input row 12 contiguous bytes (three aligned 32-bit loads instead of
+// twelve byte loads), two 256-bit stores (one whole sector each).
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 template <bool kBF16>
 __global__ void preprocess_s2d_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int H2, int Wp,
-                                      int src_is_rgb, uint4* __restrict__ out) {
-  const long long total = static_cast<long long>(B) * H2 * Wp;
+                                      int src_is_rgb, int aligned, uint8_t* __restrict__ out) {
+  const int pairs = (Wp + 1) >> 1;
+  const long long total = static_cast<long long>(B) * H2 * pairs;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xp = static_cast<int>(i % Wp);
-    long long t = i / Wp;
+    const int pr = static_cast<int>(i % pairs);
+    long long t = i / pairs;
     const int y2 = static_cast<int>(t % H2);
     const int b = static_cast<int>(t / H2);
-    const int x2 = xp - 2;
-    float v[16];
+    const int xp0 = 2 * pr;
+    const int x0 = 2 * (xp0 - 2);                      // first input column of the pair (4 columns, 12 bytes per row)
+    float v[2][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-    if (x2 >= 0 && 2 * x2 < W) {
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const int y = 2 * y2 + dy;
-        if (y >= H) continue;
-        const uint8_t* row = in + (static_cast<size_t>(b) * H + y) * W * 3;
+      for (int j = 0; j < 16; ++j) v[h][j] = 0.f;
+    const bool inside = aligned && x0 >= 0 && x0 + 4 <= W;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int x = 2 * x2 + dx;
-          if (x >= W) continue;
-          const float c0 = __ldg(row + x * 3 + 0), c1 = __ldg(row + x * 3 + 1), c2 = __ldg(row + x * 3 + 2);
-          float* o = v + (dy * 2 + dx) * 4;
-          o[0] = (src_is_rgb ? c2 : c0) - 104.f;
-          o[1] = c1 - 117.f;
-          o[2] = (src_is_rgb ? c0 : c2) - 123.f;
+    for (int dy = 0; dy < 2; ++dy) {
+      const int y = 2 * y2 + dy;
+      if (y >= H) continue;
+      const uint8_t* row = in + (static_cast<size_t>(b) * H + y) * W * 3;
+      uint8_t px[12];
+      if (inside) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(row + x0 * 3);   // 12 * (xp0 - 2) / ... : multiple of 4
+        const uint32_t a = __ldg(s), c = __ldg(s + 1), d = __ldg(s + 2);
+        memcpy(px, &a, 4); memcpy(px + 4, &c, 4); memcpy(px + 8, &d, 4);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const int x = x0 + k / 3;
+          px[k] = (x >= 0 && x < W) ? __ldg(row + x * 3 + k % 3) : 0;
         }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                    // input column x0 + k -> output pixel k / 2, dx = k % 2
+        const int x = x0 + k;
+        if (x < 0 || x >= W) continue;
+        const float c0 = px[k * 3 + 0], c1 = px[k * 3 + 1], c2 = px[k * 3 + 2];
+        float* o = v[k >> 1] + (dy * 2 + (k & 1)) * 4;
+        o[0] = (src_is_rgb ? c2 : c0) - 104.f;
+        o[1] = c1 - 117.f;
+        o[2] = (src_is_rgb ? c0 : c2) - 123.f;
+      }
     }
-    out[i * 2] = pack8<kBF16>(v);
-    out[i * 2 + 1] = pack8<kBF16>(v + 8);
+    uint8_t* o = out + ((static_cast<size_t>(b) * H2 + y2) * Wp + xp0) * 32;
+    st_global_256(o, pack8<kBF16>(v[0]), pack8<kBF16>(v[0] + 8));
+    if (xp0 + 1 < Wp) st_global_256(o + 32, pack8<kBF16>(v[1]), pack8<kBF16>(v[1] + 8));
   }
 }
 
 int launch_preprocess_s2d(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out,
                           cudaStream_t st) {
   const int H2 = (H + 1) / 2, Wp = (W + 1) / 2 + 3;
-  const long long total = static_cast<long long>(B) * H2 * Wp;
+  if (reinterpret_cast<uintptr_t>(d_out) & 31) return set_err(ctx, FRB_ERR_INVALID, "preprocess: the S2D16 output must be 32-byte aligned");
+  const long long total = static_cast<long long>(B) * H2 * ((Wp + 1) / 2);
   const int grid = grid_for(total, 256, ctx->num_sms);
-  if (ctx->use_bf16) preprocess_s2d_kernel<true><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, static_cast<uint4*>(d_out));
-  else preprocess_s2d_kernel<false><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, static_cast<uint4*>(d_out));
+  const int aligned = ((W * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0;
+  if (ctx->use_bf16) preprocess_s2d_kernel<true><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, aligned, static_cast<uint8_t*>(d_out));
+  else preprocess_s2d_kernel<false><<<grid, 256, 0, st>>>(d_frames, B, H, W, H2, Wp, src_is_rgb, aligned, static_cast<uint8_t*>(d_out));
   ctx->launches++;
   return check_last(ctx, "preprocess_s2d_kernel");
 }

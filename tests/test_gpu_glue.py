@@ -129,18 +129,22 @@ def test_crop_resize_standardize_matches_cv2_semantics(ctx):
         assert not out[i, :, :, 3:].any()
 
 
-def test_preprocess_space_to_depth_layout(ctx):
+@pytest.mark.parametrize("B,H,W", [(2, 18, 26), (1, 16, 24), (2, 17, 25), (1, 20, 40), (1, 7, 4)])
+def test_preprocess_space_to_depth_layout(ctx, B, H, W):
+    """W * 3 a multiple of 4 takes the 32-bit-load path, the others the byte path; odd sizes leave the missing row /
+    column of the last 2x2 block zero."""
     from facerec_b200 import ops, _lib
     rng = np.random.RandomState(4)
-    B, H, W = 2, 18, 26
     fr = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
     out = ops.preprocess_u8(ctx, torch.from_numpy(fr).cuda(), True, _lib.FRB_LAYOUT_S2D16).float().cpu().numpy()
-    assert out.shape == (B, H // 2, W // 2 + 3, 16)
-    bgr = fr[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32)
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    assert out.shape == (B, H2, W2 + 3, 16)
+    bgr = np.zeros((B, 2 * H2, 2 * W2, 4), np.float32)
+    bgr[:, :H, :W, :3] = fr[..., ::-1].astype(np.float32) - np.array([104, 117, 123], np.float32)
     ref = np.zeros_like(out)
     for dy in range(2):
         for dx in range(2):
-            ref[:, :, 2:-1, (dy * 2 + dx) * 4:(dy * 2 + dx) * 4 + 3] = bgr[:, dy::2, dx::2, :]
+            ref[:, :, 2:-1, (dy * 2 + dx) * 4:(dy * 2 + dx) * 4 + 4] = bgr[:, dy::2, dx::2, :]
     assert np.array_equal(out, ref)
 
 
