@@ -97,6 +97,12 @@ struct ConvTmaArgs {
   int pdl;               // 1: launched with programmatic stream serialization (FRB_OPT_PDL)
   int skip_loads;        // debug build, stall variants only (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
+  // fused RetinaFace heads (1x1, 32 columns = cls 4 | box 8 | ldm 20 per pixel): fp32 rows written straight from the
+  // accumulator registers to loc [B,P,4] / conf [B,P,2] / landm [B,P,10] at prior P_off + 2 * pixel (linear tiling only)
+  float* head_loc;
+  float* head_conf;
+  float* head_landm;
+  int head_P_total, head_P_off, head_hw;
 };
 
 // Host entry points (conv_tma_f16.cu / conv_tma_bf16.cu / conv_tma_stall.cu): pick the kernel variant for
@@ -367,6 +373,43 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           *reinterpret_cast<uint4*>(dst) = o;
         }
       };
+      if constexpr (kRes == 0 && kAct == 2) {
+        if (p.head_loc != nullptr) {
+          // head layer: 32 fp32 columns per pixel go from the registers to the three prior-major outputs (16-byte
+          // stores, consecutive lanes = consecutive pixels = consecutive addresses); no staging slab, no TMA store
+          float y[32];
+          tc_wait_ld16(v0);
+          tmem_ld16(taddr + 16, v1);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) y[c] = __uint_as_float(v0[c]) + g_bias[c];
+          tc_wait_ld16(v1);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) y[16 + c] = __uint_as_float(v1[c]) + g_bias[16 + c];
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          const int m = cur.c1 + row;
+          if (m < p.M) {
+            const int hb = m / p.head_hw;
+            const size_t prior0 = static_cast<size_t>(hb) * p.head_P_total + p.head_P_off + 2 * static_cast<size_t>(m - hb * p.head_hw);
+            *reinterpret_cast<float4*>(p.head_conf + prior0 * 2) = make_float4(y[0], y[1], y[2], y[3]);
+            float4* lc = reinterpret_cast<float4*>(p.head_loc + prior0 * 4);
+            lc[0] = make_float4(y[4], y[5], y[6], y[7]);
+            lc[1] = make_float4(y[8], y[9], y[10], y[11]);
+            float4* lm = reinterpret_cast<float4*>(p.head_landm + prior0 * 10);
+#pragma unroll
+            for (int t = 0; t < 5; ++t) lm[t] = make_float4(y[12 + 4 * t], y[13 + 4 * t], y[14 + 4 * t], y[15 + 4 * t]);
+          }
+          s_in += kEpiGroups;
+          while (s_in >= nslab) { s_in -= nslab; ++ti; }
+          if (q + kEpiGroups < my_slabs) {
+            cur = slab_at(ti, s_in);
+            prefetch(cur);
+          }
+          named_bar_sync(1 + grp, kGroupThreads);   // barrier B: the group's bias copy may be overwritten
+          continue;
+        }
+      }
       // 16 columns at a time, the next tcgen05.ld in flight while the current chunk is finished (ncols % 16 == 0;
       // columns past ncols of a partial last slab are never stored: the output tensor map clips them)
       tc_wait_ld16(v0);

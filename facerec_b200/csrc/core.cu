@@ -201,8 +201,11 @@ static void fastdiv_make(int d, uint32_t* fd) {
 }
 
 static bool tma_path_ok(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io) {
-  if (ctx->force_gather || io.out_mode != OUT_16BIT) return false;
   const bool linear = L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0;
+  // the fused RetinaFace heads (32 linear columns) leave through the fp32 head epilogue of the TMA kernel
+  const bool head = io.out_mode == OUT_HEAD_SCATTER && linear && L.Cout == 32 && L.BN == 32 && L.n_tiles == 1 &&
+                    L.act_kind == 2 && io.res_mode == RES_NONE && (L.Cin % kBK) == 0 && (io.P_total % 2) == 0 && (io.P_off % 2) == 0;
+  if (ctx->force_gather || (io.out_mode != OUT_16BIT && !head)) return false;
   if (!linear && (L.Cin % kBK) != 0) return false;                 // taps are fetched as whole 64-channel blocks
   if (!linear && io.res_mode == RES_POST_ACT_UPSAMPLE) return false;
   if (L.n_tiles > 1 && (L.BN % kSlab) != 0) return false;          // store slabs must not spill into the next N tile
@@ -266,7 +269,11 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     a.a_bytes = kAStageBytes;
     a.bw = kBM; a.bh = 1; a.bb = 1; a.tiles_w = 1; a.tiles_h = 1;
     if ((rc = encode_2d(ctx, &tmA, io.in, L.Cin, M, static_cast<uint64_t>(io.in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
-    if ((rc = encode_2d(ctx, &tmO, io.out, L.Cout, M, static_cast<uint64_t>(io.out_ld) * 2, kSlab, kBM)) != FRB_OK) return rc;
+    if (io.out_mode == OUT_HEAD_SCATTER) {
+      a.head_loc = io.loc; a.head_conf = io.conf; a.head_landm = io.landm;
+      a.head_P_total = io.P_total; a.head_P_off = io.P_off; a.head_hw = Ho * Wo;
+      tmO = tmA;                                   // never used: the head epilogue stores from registers
+    } else if ((rc = encode_2d(ctx, &tmO, io.out, L.Cout, M, static_cast<uint64_t>(io.out_ld) * 2, kSlab, kBM)) != FRB_OK) return rc;
     tmR = tmO;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_2d(ctx, &tmR, io.res, L.Cout, M, static_cast<uint64_t>(io.res_ld) * 2, kSlab, kBM)) != FRB_OK)
@@ -502,6 +509,7 @@ int frb_destroy(frb_ctx* ctx) {
   if (ctx == nullptr) return FRB_ERR_INVALID;
   for (auto& kv : ctx->nets) destroy_net(kv.second);
   ctx->nets.clear();
+  if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
   if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
   for (cudaEvent_t e : ctx->lt_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)

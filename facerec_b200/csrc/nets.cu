@@ -829,9 +829,11 @@ static int run_plan_graphed(frb_ctx* ctx, Net* net, Plan& plan, const ExecPtrs& 
   if (plan.graph == nullptr) {
     const long long l0 = ctx->launches;
     cudaGraph_t g = nullptr;
-    FRB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    const int rc = run_plan(ctx, net, plan, gp, st);
-    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    // captured on a stream of our own: the caller's may be the legacy default stream, which cannot be captured
+    if (ctx->capture_stream == nullptr) FRB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+    FRB_CUDA(ctx, cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = run_plan(ctx, net, plan, gp, ctx->capture_stream);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->capture_stream, &g);
     if (rc != FRB_OK) {
       if (g) cudaGraphDestroy(g);
       return rc;
