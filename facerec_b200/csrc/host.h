@@ -44,7 +44,7 @@ struct frb_ctx {
   int trace_mode = 0;          // FRB_OPT_TRACE: per-CTA stall counters of the conv_tma roles
   long long* trace_dev = nullptr;  // FRB_OPT_TRACE: device buffer for conv_tma timeline records
   cudaStream_t capture_stream = nullptr;   // graph capture of short forwards happens here, replay on the caller's stream
-  int graphs = 1;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
+  int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)

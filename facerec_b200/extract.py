@@ -155,6 +155,20 @@ class PreloadedSource:
         pass
 
 
+_RING_CACHE = {}
+
+
+def _pinned_ring(n_slots: int, shape, pin: bool):
+    """Batch buffers the decoder threads fill.  Page-locking host memory costs ~0.25 s per GB (3.6 GB for nine 64 x 1080p
+    slots), so the ring of a given shape is allocated once per process and reused by later shards / files."""
+    import torch
+    key = (tuple(shape), bool(pin))
+    ring = _RING_CACHE.setdefault(key, [])
+    while len(ring) < n_slots:
+        ring.append(torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=pin))
+    return ring[:n_slots]
+
+
 class BatchReader:
     """T decoder threads filling a ring of batch buffers in order.  Thread t decodes batches t, t + T, ... (each with its
     own handle on the source when T > 1, seeking to the batch's first frame); `next()` hands the batches out in order as
@@ -427,17 +441,21 @@ class Extractor:
         # facerec/extract.py:233) and decodes straight INTO the batch's ring slot (no np.stack, no pin_memory copy: both
         # were a full extra pass over 400 MB per 64 x 1080p batch).  One thread decodes 1080p mp4v at ~180 frames/s, far
         # below what the GPU path consumes, hence --decode-threads.
+        from time import perf_counter
+        t_setup0 = perf_counter()
         pin = device.type == "cuda"
         n_to_read = end_overlap - beg
         reopen = getattr(src, "reopen", None)
         n_threads = max(1, int(getattr(self, "decode_threads", 1))) if reopen is not None else 1
         # slots: T being filled + 1 ready + two in flight on the GPU + one walked by the host + one still referenced by
         # the min_trajectory-delayed frames of the batch before it
-        ring = [torch.empty((self.batch, d_height, d_width, 3), dtype=torch.uint8, pin_memory=pin) for _ in range(n_threads + 5)]
+        ring = _pinned_ring(n_threads + 5, (self.batch, d_height, d_width, 3), pin)
         reader = BatchReader(src, ring, self.batch, beg, n_to_read, n_threads)
         from collections import deque
         from time import perf_counter
-        tm = self.timing = {"wait_reader": 0.0, "launch": 0.0, "wait_detect": 0.0, "host_loop": 0.0, "wait_embed_write": 0.0}
+        tm = self.timing = {"wait_reader": 0.0, "launch": 0.0, "wait_detect": 0.0, "host_loop": 0.0, "wait_embed_write": 0.0,
+                            "setup": perf_counter() - t_setup0, "loop": 0.0}
+        t_loop0 = perf_counter()
         staged_embedder = hasattr(self.embedder, "embed_boxes_launch")
         staged_detector = hasattr(self.detector, "detect_batch_launch")
         inflight = deque()            # batches whose detection (and scene statistics) are running on the GPU
@@ -523,6 +541,7 @@ class Extractor:
         for trk in tracker.pop_expired(expiry_age=0):
             dump_line(trajectory_record(trk, d_width, d_height), trajectories_file)
             counts["traj"] += 1
+        tm["loop"] = perf_counter() - t_loop0
         with open(f"{dirs['scene_changes']}/scene_changes_{suffix}.json", "w") as fh:
             json.dump({"frame_indices": [c for c in scene_changes if beg <= c < end]}, fh, indent=None, separators=(",", ":"))
         features_file.close()

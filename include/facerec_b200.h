@@ -64,8 +64,10 @@ enum frb_option {
                            /* shared memory where the slice fits and the grid can be a multiple of the N tiles)      */
   FRB_OPT_MPAIR = 12,      /* halo-mode convs with streamed weights work on two 8 x 16 patches per weight stage:     */
                            /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
-  FRB_OPT_GRAPHS = 13      /* 0: every forward launches its kernels one by one (default 1: short forwards - InceptionResnetV1, */
-                           /* RetinaFace-MobileNet0.25 up to 64 x 360p - are captured once per shape into a CUDA graph)        */
+  FRB_OPT_GRAPHS = 13      /* 1: short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 up to 64 x 360p) are captured once per  */
+                           /* shape into a CUDA graph and replayed.  Default 0: measured SLOWER than stream launches with         */
+                           /* programmatic dependent launch (the kernels are GPU-bound at 10-35 us, and a replayed graph loses    */
+                           /* the set-up overlap: 1.49 vs 1.23 ms at 64 faces, profiles/r02_stages_v1.json)                        */
   /* values 2, 4, 7, 8 are timing / tracing experiments that only a debug build of the library honours:
      include/facerec_b200_debug.h */
 };

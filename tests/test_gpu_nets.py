@@ -126,8 +126,8 @@ def test_dependent_launch_policy_does_not_change_results(ctx, pdl):
 
 
 def test_graph_replay_equals_eager_launches(ctx):
-    """FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 at 360p) are captured into a CUDA graph
-    on their second call and replayed through net-owned staging buffers; results are the bits of the eager launches, for
+    """FRB_OPT_GRAPHS = 1 (opt-in): short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 at 360p) are captured into a CUDA
+    graph on their second call and replayed through net-owned staging buffers; results are the bits of the eager launches, for
     changing input / output pointers and interleaved batch sizes (one graph per shape)."""
     from facerec_b200 import ops, weights, _lib
     rng = np.random.RandomState(8)
@@ -139,6 +139,7 @@ def test_graph_replay_equals_eager_launches(ctx):
         faces[n][..., :3] = torch.randn(n, 160, 160, 3, generator=gen) * 0.5
     fr = [torch.from_numpy(_frames(rng, 4, 360, 640)).cuda() for _ in range(2)]
     eager = _lib.Context(0)
+    ctx.set_option(_lib.FRB_OPT_GRAPHS, 1)
     try:
         eager.set_option(_lib.FRB_OPT_GRAPHS, 0)
         want = {}
@@ -158,4 +159,5 @@ def test_graph_replay_equals_eager_launches(ctx):
                 assert all(torch.equal(a, b) for a, b in zip(got, w)), rep
         assert ctx.launch_count() - l0 > 4 * 2 * 100   # replays are counted with the kernels they contain
     finally:
+        ctx.set_option(_lib.FRB_OPT_GRAPHS, 0)
         eager.close()

@@ -87,15 +87,16 @@ def main():
     for rep in range(2):
         pre.seek(0)
         dt, counts, tm = run(pre, 1, os.path.join(a.work, "pre"))
-    res["preloaded"] = {"frames": pre.n_frames, "frames_per_s": pre.n_frames / dt, **counts, "main_thread_seconds": tm}
+    res["preloaded"] = {"n_frames": pre.n_frames, "frames_per_s": pre.n_frames / dt, "frames_per_s_steady": pre.n_frames / tm["loop"],
+                        **counts, "main_thread_seconds": tm}
     del pre
 
     best = (0.0, 1)
     for t in a.threads:
         dt, counts, tm = run(clip, t, os.path.join(a.work, f"t{t}"))
         fps = a.frames / dt
-        res[f"file_threads{t}"] = {"frames_per_s": fps, "seconds": dt, **counts, "main_thread_seconds": tm,
-                                   "decode_share_of_wall": round(tm["wait_reader"] / dt, 3)}
+        res[f"file_threads{t}"] = {"frames_per_s": fps, "seconds": dt, "frames_per_s_steady": a.frames / tm["loop"], **counts,
+                                   "main_thread_seconds": tm, "decode_wait_share_of_loop": round(tm["wait_reader"] / tm["loop"], 3)}
         best = max(best, (fps, t))
     # outputs must not depend on the number of decoder threads
     ref_dir = os.path.join(a.work, f"t{a.threads[0]}", "100001-data")
