@@ -319,9 +319,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (shared::cluster address from mapa_shared)
+// arrive on a barrier that may live in the peer CTA (shared::cluster address from mapa_shared).  Default semantics
+// (release at CTA scope): what is handed over are TMEM accumulators, ordered by tcgen05.wait::ld + tcgen05.fence before the
+// arrive, not generic-proxy memory; an explicit .release.cluster costs a MEMBAR per arrival (first on the stall list of
+// the kNN epilogue, profiles/r02_ncu_dist_gemm.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)

@@ -33,6 +33,13 @@
 // Weight slice (FRB_OPT_WEIGHT_SLICE): when the grid is a multiple of the number of N tiles, tile % n_tiles is the
 // same for every tile of a CTA, and a slice of up to 48 KB is loaded once like the small matrices above.
 //
+// CTA pairs (FRB_OPT_CTA2, per-tap / linear path with streamed weights): two CTAs on the SMs of one TPC (cluster of 2,
+// cta_group::2) work on two M tiles of the SAME N tile with ONE tcgen05.mma of M = 256: each CTA loads its own A blocks
+// and residual slabs and HALF of every weight block (BN/2 rows), the leader CTA (cluster rank 0) issues the MMAs, commits
+// are multicast to both CTAs' barriers, the epilogues hand the accumulators back on the leader's barrier.  The layers that
+// take this path (1x1 convs of layer3/4 and the FPN, strided convs) stream 94 B/clk of operands per SM at BN = 256
+// against ~53 B/clk an SM can pull through L2 beside a busy tensor pipe; half the weight bytes is 62 B/clk.
+//
 // Programmatic dependent launch (FRB_OPT_PDL, short launches only): barrier init, TMEM allocation, descriptor
 // prefetch and the resident-weight loads run before griddepcontrol.wait, i.e. under the previous kernel's tail.
 //
@@ -95,6 +102,7 @@ struct ConvTmaArgs {
   int dual_issue;        // 1: two MMA issuer warps take tiles alternately where the rings allow it (FRB_OPT_DUAL_ISSUE)
   int mpair;             // 1: halo mode, a tile is two 8-wide patches side by side under one halo tile and one weight stream
   int pdl;               // 1: launched with programmatic stream serialization (FRB_OPT_PDL)
+  int cta2;              // 1: CTA pairs (cluster of 2): M = 256 MMAs, weights split over the pair (tmB / tmI boxes are half size)
   int skip_loads;        // debug build, stall variants only (FRB_OPT_SKIP_LOADS): the producer only arrives on the full barriers
   long long* stall;      // debug: per-CTA stall-cycle counters of the three roles (16 words per CTA), or null
   // fused RetinaFace heads (1x1, 32 columns = cls 4 | box 8 | ldm 20 per pixel): fp32 rows written straight from the
@@ -144,11 +152,16 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int b_stage_bytes = p.BN * 128;
+  const bool cta2 = p.cta2 != 0;
+  const uint32_t crank = cta2 ? cluster_ctarank() : 0u;          // rank in the CTA pair (leader = 0)
+  const int tile_unit = cta2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // who walks the tile list
+  const int grid_units = cta2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int b_rows = cta2 ? p.BN / 2 : p.BN;                     // weight rows this CTA holds per k-block
+  const int b_stage_bytes = b_rows * 128;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + (p.halo ? p.a_stages * p.halo_bytes : p.stages * p.kbps * kAStageBytes);   // ring (or resident matrix)
   const int res_nts = p.b_resident == 2 ? 1 : p.n_tiles;                                // resident N tiles and the first of them
-  const int res_nt0 = p.b_resident == 2 ? static_cast<int>(blockIdx.x) % p.n_tiles : 0;
+  const int res_nt0 = p.b_resident == 2 ? tile_unit % p.n_tiles : 0;
   uint8_t* smem_o = smem_b + (p.b_resident ? res_nts * p.num_kb : p.stages * (p.halo ? p.brow : p.kbps)) * b_stage_bytes;
   uint8_t* smem_i = smem_o + kOutBufs * kSlabBytes;                                    // 64 x 64 identity (kRes = 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_i + (kRes == 1 ? kIdentBytes : 0));
@@ -196,7 +209,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       }
       for (int b = 0; b < kMaxAcc; ++b) {
         mbar_init(&tfull_bar[b], 1);
-        mbar_init(&tempty_bar[b], 4 * nslab);          // every warp of the nslab groups that read the buffer
+        mbar_init(&tempty_bar[b], 4 * nslab * (cta2 ? 2 : 1));   // every warp of the nslab groups that read the buffer (both CTAs of a pair)
       }
       mbar_init(bres_bar, 1);
       mbar_init(&turn_bar[0], 1);
@@ -208,11 +221,17 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc_dyn(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (cta2) {
+      tmem_alloc_2cta(tmem_slot, tmem_cols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc_dyn(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (cta2) cluster_sync_all();       // barriers initialised and TMEM allocated in both CTAs before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
@@ -222,8 +241,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
 
   // tile -> coordinates of its first pixel
   auto decode = [&](int tile, int& n_tile, int& c1, int& c2, int& c3) {
-    const int m_tile = fastdiv(tile, p.fd_n);
+    int m_tile = fastdiv(tile, p.fd_n);
     n_tile = tile - m_tile * p.n_tiles;
+    if (cta2) m_tile = 2 * m_tile + static_cast<int>(crank);   // the pair's two M tiles (one past the end: all loads and stores clip)
     if (p.patch) {
       const int t = fastdiv(m_tile, p.fd_w);
       const int tb = fastdiv(t, p.fd_h);
@@ -257,8 +277,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     float* const g_bias = s_bias + grp * kSlab;
     float* const g_slope = s_slope + grp * kSlab;
     // (a paired tile is two accumulators = two "tiles" of this role: the same slabs, the second 8 pixels to the right)
-    const int my_tiles = ((p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x))
-                         << (p.mpair ? 1 : 0);
+    const int my_tiles = ((p.total_tiles - tile_unit + grid_units - 1) / grid_units) << (p.mpair ? 1 : 0);
+    const uint32_t tempty_leader = cta2 ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
     const int my_slabs = my_tiles * nslab;
     StallClock<kStall> sc{kStall && p.stall != nullptr && threadIdx.x == 0, 0};
     long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
@@ -269,7 +289,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     auto slab_at = [&](int ti, int s2) {
       Slab sl;
       int nt;
-      decode(blockIdx.x + (p.mpair ? ti >> 1 : ti) * gridDim.x, nt, sl.c1, sl.c2, sl.c3);
+      decode(tile_unit + (p.mpair ? ti >> 1 : ti) * grid_units, nt, sl.c1, sl.c2, sl.c3);
       if (p.mpair) sl.c1 += (ti & 1) * 8;
       sl.tile_iter = ti;
       sl.s = s2;
@@ -387,7 +407,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           for (int c = 0; c < 16; ++c) y[16 + c] = __uint_as_float(v1[c]) + g_bias[16 + c];
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) {
+            if (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);
+            else mbar_arrive(&tempty_bar[buf]);
+          }
           const int m = cur.c1 + row;
           if (m < p.M) {
             const int hb = m / p.head_hw;
@@ -432,7 +455,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       // this warp's part of the accumulator slab is in registers / staged: hand the TMEM buffer back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);   // the leader's issuer owns the MMAs
+        else mbar_arrive(&tempty_bar[buf]);
+      }
       // global reads of the group's next slab
       s_in += kEpiGroups;
       while (s_in >= nslab) { s_in -= nslab; ++ti; }
@@ -464,7 +490,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     // instructions sit under the elected lane.  (Measured before this rewrite: ~600 cycles of dependent
     // single-warp instructions per k-block in both this loop and the producer's, i.e. the pipeline could not
     // deliver a k-block faster than that whatever the tile shape — 4 MMAs are 225-512 cycles of tensor time.)
-    const uint32_t idesc = make_idesc_f16(kBM, p.BN, kBF16 ? 1 : 0);
+    const uint32_t idesc = make_idesc_f16(cta2 ? 2 * kBM : kBM, p.BN, kBF16 ? 1 : 0);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
     const uint32_t a_step = kAStageBytes >> 4, b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
     const uint32_t halo_step = static_cast<uint32_t>(p.halo_bytes) >> 4;
@@ -502,10 +528,20 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     StallClock<kStall> sc{kStall && p.stall != nullptr && iw == 0, 0};
     long long st_tempty = 0, st_full = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
-    if (p.b_resident || kRes == 1) mbar_wait(bres_bar, 0, p.watchdog, 250);
+    const bool issues = !cta2 || crank == 0;          // in a pair only the leader's issuer warps have work
+    if (issues && (p.b_resident || kRes == 1)) mbar_wait(bres_bar, 0, p.watchdog, 250);
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
-    for (int tile = dual ? blockIdx.x + iw * gridDim.x : (iw == solo ? static_cast<int>(blockIdx.x) : p.total_tiles);
-         tile < p.total_tiles; tile += tstep * gridDim.x, tile_iter += tstep) {
+    // the pair's MMAs and commits (per-tap / linear path only; the halo paths never run as pairs)
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+      if (cta2) tc_mma_f16_2cta(d, a, b, id, acc);
+      else tc_mma_f16(d, a, b, id, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (cta2) tc_commit_2cta(bar, 3);
+      else tc_commit_a(bar);
+    };
+    for (int tile = !issues ? p.total_tiles : (dual ? tile_unit + iw * grid_units : (iw == solo ? tile_unit : p.total_tiles));
+         tile < p.total_tiles; tile += tstep * grid_units, tile_iter += tstep) {
       const int acc_iter = p.mpair ? 2 * tile_iter : tile_iter;          // a paired tile fills two accumulator buffers
       const int buf = acc_iter & (nacc - 1);
       const uint32_t tphase = static_cast<uint32_t>(acc_iter >> nacc_shift) & 1u;
@@ -687,31 +723,31 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               const bool two = p.kbps == 2 && kb0 + 1 < p.num_kb;          // this stage carries two k-blocks
               if (!p.b_resident) b_cur = b_ring;
               if (elect_one()) {
-                tc_mma_f16(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, j != 0 ? 1u : 0u);
-                tc_mma_f16(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
-                tc_mma_f16(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
-                tc_mma_f16(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
+                mma(d_tmem, pack_desc(a_ring, hi1024), pack_desc(b_cur, hi1024), idesc, j != 0 ? 1u : 0u);
+                mma(d_tmem, pack_desc(a_ring + 2, hi1024), pack_desc(b_cur + 2, hi1024), idesc, 1u);
+                mma(d_tmem, pack_desc(a_ring + 4, hi1024), pack_desc(b_cur + 4, hi1024), idesc, 1u);
+                mma(d_tmem, pack_desc(a_ring + 6, hi1024), pack_desc(b_cur + 6, hi1024), idesc, 1u);
                 if (two) {
                   const uint32_t a2 = a_ring + a_step, b2 = b_cur + b_step;
-                  tc_mma_f16(d_tmem, pack_desc(a2, hi1024), pack_desc(b2, hi1024), idesc, 1u);
-                  tc_mma_f16(d_tmem, pack_desc(a2 + 2, hi1024), pack_desc(b2 + 2, hi1024), idesc, 1u);
-                  tc_mma_f16(d_tmem, pack_desc(a2 + 4, hi1024), pack_desc(b2 + 4, hi1024), idesc, 1u);
-                  tc_mma_f16(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
+                  mma(d_tmem, pack_desc(a2, hi1024), pack_desc(b2, hi1024), idesc, 1u);
+                  mma(d_tmem, pack_desc(a2 + 2, hi1024), pack_desc(b2 + 2, hi1024), idesc, 1u);
+                  mma(d_tmem, pack_desc(a2 + 4, hi1024), pack_desc(b2 + 4, hi1024), idesc, 1u);
+                  mma(d_tmem, pack_desc(a2 + 6, hi1024), pack_desc(b2 + 6, hi1024), idesc, 1u);
                 }
-                tc_commit_a(empty0 + stage * 8);
-                if (last_mine) tc_commit_a(tfull0 + buf * 8);
+                commit(empty0 + stage * 8);
+                if (last_mine) commit(tfull0 + buf * 8);
               }
             } else {
               const int rs = j - n_k;
-              const uint32_t idesc_r = make_idesc_f16(kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
+              const uint32_t idesc_r = make_idesc_f16(cta2 ? 2 * kBM : kBM, min(kSlab, p.BN - rs * kSlab), kBF16 ? 1 : 0);
               const uint32_t d_r = d_tmem + static_cast<uint32_t>(rs * kSlab);
               if (elect_one()) {
-                tc_mma_f16(d_r, pack_desc(a_ring, hi1024), pack_desc(ident_lo, hi1024), idesc_r, 1u);
-                tc_mma_f16(d_r, pack_desc(a_ring + 2, hi1024), pack_desc(ident_lo + 2, hi1024), idesc_r, 1u);
-                tc_mma_f16(d_r, pack_desc(a_ring + 4, hi1024), pack_desc(ident_lo + 4, hi1024), idesc_r, 1u);
-                tc_mma_f16(d_r, pack_desc(a_ring + 6, hi1024), pack_desc(ident_lo + 6, hi1024), idesc_r, 1u);
-                tc_commit_a(empty0 + stage * 8);
-                if (last_mine) tc_commit_a(tfull0 + buf * 8);
+                mma(d_r, pack_desc(a_ring, hi1024), pack_desc(ident_lo, hi1024), idesc_r, 1u);
+                mma(d_r, pack_desc(a_ring + 2, hi1024), pack_desc(ident_lo + 2, hi1024), idesc_r, 1u);
+                mma(d_r, pack_desc(a_ring + 4, hi1024), pack_desc(ident_lo + 4, hi1024), idesc_r, 1u);
+                mma(d_r, pack_desc(a_ring + 6, hi1024), pack_desc(ident_lo + 6, hi1024), idesc_r, 1u);
+                commit(empty0 + stage * 8);
+                if (last_mine) commit(tfull0 + buf * 8);
               }
             }
             __syncwarp();
@@ -748,22 +784,30 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     StallClock<kStall> sc{kStall && p.stall != nullptr, 0};
     long long st_empty = 0, st_rempty = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
+    // pair: completion bytes of both CTAs' loads are signalled on the LEADER's barriers (its issuer waits on them)
+    const uint32_t full_dst0 = cta2 ? mapa_shared(full0, 0) : full0;
     if ((p.b_resident || kRes == 1) && lane == 0) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? res_nts * p.num_kb * b_stage_bytes : 0) +
-                                                            (kRes == 1 ? kIdentBytes : 0)));
-      if (p.b_resident)
-        for (int nt = 0; nt < res_nts; ++nt)
-          for (int kb = 0; kb < p.num_kb; ++kb)
-            tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, (res_nt0 + nt) * p.BN);
-      if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
+      if (cta2) {
+        // (resident weights never run as pairs) each CTA holds half of the identity's rows: 32 x 64
+        if (crank == 0) mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(kIdentBytes));
+        if (kRes == 1) tma_load_2d_2cta(smem_u32(smem_i), &tmI, mapa_shared(smem_u32(bres_bar), 0), 0, static_cast<int>(crank) * 32);
+      } else {
+        mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? res_nts * p.num_kb * b_stage_bytes : 0) +
+                                                              (kRes == 1 ? kIdentBytes : 0)));
+        if (p.b_resident)
+          for (int nt = 0; nt < res_nts; ++nt)
+            for (int kb = 0; kb < p.num_kb; ++kb)
+              tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, (res_nt0 + nt) * p.BN);
+        if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
+      }
     }
     griddep_wait();                      // weights and identity are constants; activations are the previous kernel's
     const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
     const uint32_t halo_tx = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = tile_unit; tile < p.total_tiles; tile += grid_units, ++tile_iter) {
       int n_tile, c1, c2, c3;
       decode(tile, n_tile, c1, c2, c3);
-      const int n_coord = n_tile * p.BN;
+      const int n_coord = n_tile * p.BN + static_cast<int>(crank) * b_rows;      // pair: this CTA's half of the weight rows
       if (kStall && lane == 0 && p.watchdog) p.watchdog[16 + 8 * blockIdx.x + 2] = tile_iter;
       if (p.halo) {
         const int taps = p.kh * p.kw;
@@ -823,13 +867,21 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           if (kStall && p.skip_loads) {
             if (elect_one()) mbar_arrive(&full_bar[stage]);
           } else if (elect_one()) {
-            mbar_expect_tx_a(full0 + stage * 8, tx_bytes * static_cast<uint32_t>(nk));
+            if (!cta2) mbar_expect_tx_a(full0 + stage * 8, tx_bytes * static_cast<uint32_t>(nk));
+            else if (crank == 0) mbar_expect_tx_a(full0 + stage * 8, 2u * tx_bytes * static_cast<uint32_t>(nk));
           }
           for (int j = 0; j < nk; ++j) {
             if (!(kStall && p.skip_loads) && elect_one()) {
-              if (!p.b_resident) tma_load_2d_a(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, full0 + stage * 8, kcoord, n_coord);
-              if (p.patch) tma_load_4d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, cb * kBK, aw + tap_s, ah + tap_r, c3);
-              else tma_load_2d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, full0 + stage * 8, kcoord, c1);
+              const uint32_t fb = full_dst0 + static_cast<uint32_t>(stage) * 8u;
+              if (cta2) {
+                tma_load_2d_2cta(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, fb, kcoord, n_coord);
+                if (p.patch) tma_load_4d_2cta(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, cb * kBK, aw + tap_s, ah + tap_r, c3);
+                else tma_load_2d_2cta(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, kcoord, c1);
+              } else {
+                if (!p.b_resident) tma_load_2d_a(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, fb, kcoord, n_coord);
+                if (p.patch) tma_load_4d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, cb * kBK, aw + tap_s, ah + tap_r, c3);
+                else tma_load_2d_a(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, kcoord, c1);
+              }
             }
             kcoord += kBK;
             if (++cb == p.cin_blocks) {
@@ -850,9 +902,18 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
           sc.stop(st_empty);
           if (elect_one()) {
-            mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(p.a_bytes));
-            if (p.patch) tma_load_4d_a(a_dst, &tmR, full0 + stage * 8, n_coord + rs * kSlab, c1, c2, c3);
-            else tma_load_2d_a(a_dst, &tmR, full0 + stage * 8, n_coord + rs * kSlab, c1);
+            // (the residual's channel coordinate is the FULL N tile's, not this CTA's half of the weight rows)
+            const int r_coord = n_tile * p.BN + rs * kSlab;
+            const uint32_t fb = full_dst0 + static_cast<uint32_t>(stage) * 8u;
+            if (cta2) {
+              if (crank == 0) mbar_expect_tx_a(full0 + stage * 8, 2u * static_cast<uint32_t>(p.a_bytes));
+              if (p.patch) tma_load_4d_2cta(a_dst, &tmR, fb, r_coord, c1, c2, c3);
+              else tma_load_2d_2cta(a_dst, &tmR, fb, r_coord, c1);
+            } else {
+              mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(p.a_bytes));
+              if (p.patch) tma_load_4d_a(a_dst, &tmR, fb, r_coord, c1, c2, c3);
+              else tma_load_2d_a(a_dst, &tmR, fb, r_coord, c1);
+            }
           }
           __syncwarp();
           a_dst += kAStageBytes;
@@ -871,9 +932,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   // -------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (cta2) cluster_sync_all();        // the peer may still read this CTA's weight halves or arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc_dyn(tmem_base, tmem_cols);
+    if (cta2) tmem_dealloc_2cta(tmem_base, tmem_cols);
+    else tmem_dealloc_dyn(tmem_base, tmem_cols);
   }
 }
 

@@ -16,11 +16,18 @@ static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, c
   cfg.blockDim = dim3(kTmaThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = a.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (a.cta2) {                          // CTA pairs: clusters of two, one per TPC
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, a, tmA, tmB, tmO, tmR, tmI);
 }
 

@@ -131,6 +131,12 @@ int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bi
   FRB_CUDA(ctx, cudaMemcpy(L.d_w, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
   FRB_CUDA(ctx, cudaMemcpy(L.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
   FRB_CUDA(ctx, cudaMemcpy(L.d_slope, slope.data(), slope.size() * 4, cudaMemcpyHostToDevice));
+  L.has_tmB2 = 0;
+  if (L.BN % 16 == 0 && L.BN >= 32) {
+    int rc2 = encode_2d(ctx, &L.tmB2, L.d_w, L.K_pad, L.Cout_pad, static_cast<uint64_t>(L.K_pad) * 2, kBK, L.BN / 2);
+    if (rc2 != FRB_OK) return rc2;
+    L.has_tmB2 = 1;
+  }
   return encode_2d(ctx, &L.tmB, L.d_w, L.K_pad, L.Cout_pad, static_cast<uint64_t>(L.K_pad) * 2, kBK, L.BN);
 }
 
@@ -363,6 +369,13 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (!a.b_resident && !a.halo && ctx->weight_slice && L.n_tiles > 1 && slice_bytes <= kResidentSliceBytes &&
       a.total_tiles >= 4 * ctx->num_sms && L.n_tiles <= ctx->num_sms / 4)
     a.b_resident = 2;
+  // CTA pairs: per-tap / linear path with streamed weights.  Two M tiles per pair and N tile; results are the same bits
+  // (a tile's k-blocks accumulate in the same order), so the choice may depend on the amount of work.
+  a.cta2 = (ctx->cta2 && !a.halo && !a.b_resident && L.has_tmB2 && m_tiles >= 2 &&
+            (io.res_mode != RES_PRE_ACT || (L.BN % kSlab) == 0) && io.out_mode != OUT_HEAD_SCATTER &&
+            ((m_tiles + 1) / 2) * L.n_tiles >= ctx->num_sms / 2) ? 1 : 0;
+  if (a.cta2) a.total_tiles = static_cast<int>(((m_tiles + 1) / 2) * L.n_tiles);
+  const int b_rows = a.cta2 ? L.BN / 2 : L.BN;
   const int res_bytes = a.b_resident == 2 ? slice_bytes : w_bytes;
   const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? res_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
                          (4 * kMaxStages + 20) * 8 + 2048 + 1024;
@@ -372,7 +385,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   // halo mode with streamed weights: a whole filter row of taps per B stage when two such stages and two halo tiles fit
   a.brow = 1;
   if (a.halo && !a.b_resident && L.kw > 1 && 2 * L.kw * L.BN * 128 + 2 * a.halo_bytes <= total_budget) a.brow = L.kw;
-  int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? a.brow : a.kbps) * L.BN * 128);
+  int stage_bytes = (a.halo ? 0 : a.kbps * kAStageBytes) + (a.b_resident ? 0 : (a.halo ? a.brow : a.kbps) * b_rows * 128);
   if (a.kbps == 2 && total_budget / stage_bytes < ctx->kbps2_min_stages) {   // too few double stages to cover the TMA latency
     a.kbps = 1;
     stage_bytes /= 2;
@@ -391,14 +404,21 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (smem > 227 * 1024) return set_err(ctx, FRB_ERR_INVALID, "conv: shared-memory plan does not fit (%zu bytes)", smem);
   int grid = std::min(a.total_tiles, ctx->num_sms);
   if (a.b_resident == 2) grid = grid / L.n_tiles * L.n_tiles;
+  if (a.cta2) grid = 2 * std::min(a.total_tiles, ctx->num_sms / 2);
+  if (a.cta2 && io.res_mode == RES_PRE_ACT) {
+    // each CTA of a pair holds half of the identity's rows
+    void* ident = ctx->d_ident[ctx->use_bf16 ? 1 : 0];
+    if ((rc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 32)) != FRB_OK) return rc;
+  }
+  const CUtensorMap& tmBsel = a.cta2 ? L.tmB2 : L.tmB;
   const int act = io.res_mode == RES_POST_ACT_UPSAMPLE ? 0 : L.act_kind;
   cudaError_t le;
 #ifdef FRB_DEBUG_BUILD
-  if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
   else
 #endif
-  if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
-  else le = conv_tma_launch_f16(io.res_mode, act, grid, smem, stream, a, tmA, L.tmB, tmO, tmR, tmI);
+  if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
+  else le = conv_tma_launch_f16(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
   FRB_CUDA(ctx, le);
   ctx->launches++;
   return check_last(ctx, "conv_tma_kernel launch");
@@ -542,6 +562,7 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_MPAIR: ctx->mpair = value; return FRB_OK;
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
 #ifndef FRB_DEBUG_BUILD
     case FRB_OPT_FORCE_GATHER:
     case FRB_OPT_SKIP_LOADS:

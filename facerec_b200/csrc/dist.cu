@@ -280,16 +280,18 @@ dist_gemm_kernel(const __grid_constant__ DistArgs p, const __grid_constant__ CUt
         else rowoff = static_cast<long long>(gi) * p.N - (static_cast<long long>(gi) * (gi + 1)) / 2 - gi - 1;
       }
       const int row_first = (ir.m_pair * 2 + static_cast<int>(rank)) * kGM + quarter * 32;   // first row of this warp
+      // |x|^2 of the warp's 128 columns of a tile: one coalesced 512-byte load, fetched one tile ahead
+      float4 nb_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ir.n_end > ir.n_begin) nb_next = __ldg(reinterpret_cast<const float4*>(p.nb + ir.n_begin * kGN + half * 128) + lane);
 
       for (int n_tile = ir.n_begin; n_tile < ir.n_end; ++n_tile, ++tile_iter) {
         const int buf = tile_iter & 1;
         const uint32_t tphase = (tile_iter >> 1) & 1;
         const int n_base = n_tile * kGN + half * 128;                   // first database row of this warp's columns
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kGN + half * 128);
-        // |x|^2 of the warp's 128 columns: one coalesced 512-byte load, broadcast reads below
-        const float4 nb4 = __ldg(reinterpret_cast<const float4*>(p.nb + n_base) + lane);
         __syncwarp();                                                   // the previous tile's readers are done
-        reinterpret_cast<float4*>(mynb)[lane] = nb4;
+        reinterpret_cast<float4*>(mynb)[lane] = nb_next;                // broadcast reads below
+        if (n_tile + 1 < ir.n_end) nb_next = __ldg(reinterpret_cast<const float4*>(p.nb + n_base + kGN) + lane);
         __syncwarp();
         mbar_wait(&tfull_bar[buf], tphase, p.watchdog, 100 + buf);
         tc_fence_after();

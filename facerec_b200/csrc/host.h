@@ -44,6 +44,7 @@ struct frb_ctx {
   int trace_mode = 0;          // FRB_OPT_TRACE: per-CTA stall counters of the conv_tma roles
   long long* trace_dev = nullptr;  // FRB_OPT_TRACE: device buffer for conv_tma timeline records
   cudaStream_t capture_stream = nullptr;   // graph capture of short forwards happens here, replay on the caller's stream
+  int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
@@ -83,6 +84,8 @@ struct ConvLayer {
   float* d_bias = nullptr;   // [Cout_pad]
   float* d_slope = nullptr;  // [Cout_pad] negative slope per output channel (1 linear, 0 relu)
   CUtensorMap tmB;
+  CUtensorMap tmB2;          // the same matrix with a box of BN / 2 rows: one CTA's half of a weight block in pair mode
+  int has_tmB2 = 0;
 };
 
 struct ConvIO {

@@ -55,8 +55,16 @@ CASES = [
     (4, 68, 120, 128, 512, 1, 1, (1, 1), (0, 0), 1, 1, False),   # ResNet conv3 + skip with a resident weight slice per CTA
     (4, 68, 120, 128, 576, 1, 1, (1, 1), (0, 0), 2, 0, False),   # no skip: two k-blocks per stage, three 192-wide N tiles, 147 CTAs
     (4, 68, 120, 128, 576, 1, 1, (1, 1), (0, 0), 1, 1, False),   # nine 64-wide N tiles: grid of 144 CTAs
+    # CTA pairs (cta_group::2): per-tap / linear path, streamed weights, >= 74 (M pair, N tile) units
+    (3, 68, 120, 1024, 256, 1, 1, (1, 1), (0, 0), 1, 0, False),  # layer3 conv1: 16 k-blocks, two per stage, BN = 256 split 128 + 128
+    (3, 68, 120, 256, 1024, 1, 1, (1, 1), (0, 0), 1, 1, False),  # layer3 conv3 + skip: residual slabs x identity halves, 8 N tiles
+    (4, 135, 240, 128, 128, 3, 3, (2, 2), (1, 1), 1, 0, False),  # layer2.0 conv2: strided 3x3, patch boxes, 9 taps x 2 blocks
+    (2, 135, 240, 256, 512, 1, 1, (2, 2), (0, 0), 0, 0, False),  # layer2.0 downsample: strided 1x1, two N tiles
+    (3, 67, 119, 512, 256, 1, 1, (1, 1), (0, 0), 2, 2, False),   # FPN lateral + upsampled top-down, ODD number of M tiles
+    (5, 33, 59, 192, 320, 3, 3, (2, 2), (1, 1), 1, 0, False),    # ragged strided patches, 160-wide N tiles (80 + 80), odd M tiles
 ]
-SLICE_CASES = CASES[-3:]
+SLICE_CASES = CASES[-9:-6]
+PAIR_CASES = CASES[-6:]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
@@ -153,3 +161,31 @@ def test_conv2d_rejects_bad_shapes(ctx):
     x = torch.zeros(1, 8, 8, 12, dtype=torch.float16, device="cuda")   # Cin not a multiple of 8
     with pytest.raises(_lib.FrbError):
         ops.conv2d(ctx, x, np.zeros((16, 1, 1, 12), np.float32), None)
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: f"{c[1]}x{c[2]}x{c[3]}x{c[4]}")
+def test_conv2d_cta_pairs_give_the_same_bits(ctx, case):
+    """FRB_OPT_CTA2: two CTAs of a TPC share one M = 256 tcgen05.mma and split the weight block; the k-blocks of a tile
+    still accumulate in the same order, so the output is bit-identical to the single-CTA launch."""
+    from facerec_b200 import ops, _lib
+    B, H, W, Cin, Cout, kh, kw, stride, pad, act, res_mode, out_fp32 = case
+    g = torch.Generator().manual_seed(77 + Cin + Cout)
+    x16 = torch.randn(B, H, W, Cin, generator=g).half().cuda()
+    w = (torch.randn(Cout, kh, kw, Cin, generator=g) / np.sqrt(kh * kw * Cin)).numpy().astype(np.float32)
+    b = (torch.randn(Cout, generator=g) * 0.1).numpy().astype(np.float32)
+    Ho = (H + 2 * pad[0] - kh) // stride[0] + 1
+    Wo = (W + 2 * pad[1] - kw) // stride[1] + 1
+    res16 = None
+    if res_mode == 1:
+        res16 = torch.randn(B, Ho, Wo, Cout, generator=g).half().cuda()
+    elif res_mode == 2:
+        res16 = torch.randn(B, (Ho + 1) // 2, (Wo + 1) // 2, Cout, generator=g).half().cuda()
+    single = _lib.Context(0)
+    try:
+        single.set_option(_lib.FRB_OPT_CTA2, 0)
+        a, _ = ops.conv2d(single, x16, w, b, stride, pad, act, 0.1, res16, res_mode, out_fp32)
+        c, _ = ops.conv2d(ctx, x16, w, b, stride, pad, act, 0.1, res16, res_mode, out_fp32)
+        torch.cuda.synchronize()
+        assert torch.equal(a, c)
+    finally:
+        single.close()
