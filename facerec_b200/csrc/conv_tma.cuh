@@ -121,6 +121,12 @@ cudaError_t conv_tma_launch_f16(int res, int act, int grid, size_t smem, cudaStr
 cudaError_t conv_tma_launch_bf16(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
                                  const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
     const CUtensorMap& tmI);
+cudaError_t conv_tma_launch_f16_pair(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                     const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+    const CUtensorMap& tmI);
+cudaError_t conv_tma_launch_bf16_pair(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
+                                      const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+    const CUtensorMap& tmI);
 cudaError_t conv_tma_launch_stall(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
                                   const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
     const CUtensorMap& tmI);
@@ -142,7 +148,7 @@ __device__ __forceinline__ int fastdiv(int n, const uint32_t* fd) {
 
 // kRes: 0 no residual, 1 residual added before the activation (ResNet / Inception skip), 2 nearest-upsampled
 // residual added after it (FPN top-down).  kAct: 0 per-channel slope, 1 ReLU everywhere, 2 linear everywhere.
-template <bool kBF16, bool kStall, int kRes, int kAct>
+template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ CUtensorMap tmA,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -152,8 +158,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const bool cta2 = p.cta2 != 0;
-  const uint32_t crank = cta2 ? cluster_ctarank() : 0u;          // rank in the CTA pair (leader = 0)
+  // CTA pairs are a separate instantiation: every tcgen05 instruction of a kernel must carry the same cta_group, and a
+  // kernel that uses cta_group::2 can only be launched as clusters of two
+  constexpr bool cta2 = kPair;
+  uint32_t crank = 0u;                                            // rank in the CTA pair (leader = 0)
+  if constexpr (cta2) crank = cluster_ctarank();
   const int tile_unit = cta2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // who walks the tile list
   const int grid_units = cta2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int b_rows = cta2 ? p.BN / 2 : p.BN;                     // weight rows this CTA holds per k-block
@@ -221,7 +230,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       fence_mbar_init();
     }
     __syncwarp();
-    if (cta2) {
+    if constexpr (cta2) {
       tmem_alloc_2cta(tmem_slot, tmem_cols);
       tmem_relinquish_2cta();
     } else {
@@ -231,7 +240,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  if (cta2) cluster_sync_all();       // barriers initialised and TMEM allocated in both CTAs before anything crosses the pair
+  if constexpr (cta2) cluster_sync_all();       // barriers initialised and TMEM allocated in both CTAs before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
@@ -278,7 +287,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     float* const g_slope = s_slope + grp * kSlab;
     // (a paired tile is two accumulators = two "tiles" of this role: the same slabs, the second 8 pixels to the right)
     const int my_tiles = ((p.total_tiles - tile_unit + grid_units - 1) / grid_units) << (p.mpair ? 1 : 0);
-    const uint32_t tempty_leader = cta2 ? mapa_shared(smem_u32(tempty_bar), 0) : 0u;
+    uint32_t tempty_leader = 0u;
+    if constexpr (cta2) tempty_leader = mapa_shared(smem_u32(tempty_bar), 0);
     const int my_slabs = my_tiles * nslab;
     StallClock<kStall> sc{kStall && p.stall != nullptr && threadIdx.x == 0, 0};
     long long st_tfull = 0, st_res = 0, st_slab = 0, st_bar = 0;
@@ -408,7 +418,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);
+            if constexpr (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);
             else mbar_arrive(&tempty_bar[buf]);
           }
           const int m = cur.c1 + row;
@@ -456,7 +466,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);   // the leader's issuer owns the MMAs
+        if constexpr (cta2) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(buf) * 8u);   // the leader's issuer owns the MMAs
         else mbar_arrive(&tempty_bar[buf]);
       }
       // global reads of the group's next slab
@@ -533,11 +543,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     const uint32_t ident_lo = desc_lo(smem_u32(smem_i));
     // the pair's MMAs and commits (per-tap / linear path only; the halo paths never run as pairs)
     auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-      if (cta2) tc_mma_f16_2cta(d, a, b, id, acc);
+      if constexpr (cta2) tc_mma_f16_2cta(d, a, b, id, acc);
       else tc_mma_f16(d, a, b, id, acc);
     };
     auto commit = [&](uint32_t bar) {
-      if (cta2) tc_commit_2cta(bar, 3);
+      if constexpr (cta2) tc_commit_2cta(bar, 3);
       else tc_commit_a(bar);
     };
     for (int tile = !issues ? p.total_tiles : (dual ? tile_unit + iw * grid_units : (iw == solo ? tile_unit : p.total_tiles));
@@ -576,6 +586,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         if (p.mpair) tc_commit_a(tfull0 + (buf + 1) * 8);
       };
       const uint32_t row_a = static_cast<uint32_t>(p.halo_w) * 8u;             // next halo row (descriptor units of 16 B)
+      bool halo_done = false;
+      if constexpr (!cta2) {       // (pairs never take the halo paths: these branches hold cta_group::1 instructions)
+      halo_done = p.halo != 0;
       if (p.halo && p.b_resident) {
         // Resident weights: nothing but the halo tile has to arrive, so ALL taps of a channel block go out under one
         // barrier wait, back to back (an mbarrier wait costs the pipe ~140 cycles, tools/umma_issue_probe.cu; the
@@ -702,7 +715,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           }
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
         }
-      } else {
+      }
+      }
+      if (!halo_done) {
         // One walk over the tile's ring stages: n_k weight stages (one or two k-blocks each), then for kRes = 1 the
         // residual slabs (accumulator columns [rs * 64, rs * 64 + ncols) += residual slab x identity).
         // (Splitting the stages of a tile between the two issuers was tried: 2-4 % on the long tiles, but the order in
@@ -785,9 +800,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     long long st_empty = 0, st_rempty = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
     // pair: completion bytes of both CTAs' loads are signalled on the LEADER's barriers (its issuer waits on them)
-    const uint32_t full_dst0 = cta2 ? mapa_shared(full0, 0) : full0;
+    uint32_t full_dst0 = full0;
+    if constexpr (cta2) full_dst0 = mapa_shared(full0, 0);
     if ((p.b_resident || kRes == 1) && lane == 0) {
-      if (cta2) {
+      if constexpr (cta2) {
         // (resident weights never run as pairs) each CTA holds half of the identity's rows: 32 x 64
         if (crank == 0) mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(kIdentBytes));
         if (kRes == 1) tma_load_2d_2cta(smem_u32(smem_i), &tmI, mapa_shared(smem_u32(bres_bar), 0), 0, static_cast<int>(crank) * 32);
@@ -873,7 +889,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           for (int j = 0; j < nk; ++j) {
             if (!(kStall && p.skip_loads) && elect_one()) {
               const uint32_t fb = full_dst0 + static_cast<uint32_t>(stage) * 8u;
-              if (cta2) {
+              if constexpr (cta2) {
                 tma_load_2d_2cta(b_dst + static_cast<uint32_t>(j * b_stage_bytes), &tmB, fb, kcoord, n_coord);
                 if (p.patch) tma_load_4d_2cta(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, cb * kBK, aw + tap_s, ah + tap_r, c3);
                 else tma_load_2d_2cta(a_dst + static_cast<uint32_t>(j * kAStageBytes), &tmA, fb, kcoord, c1);
@@ -905,7 +921,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
             // (the residual's channel coordinate is the FULL N tile's, not this CTA's half of the weight rows)
             const int r_coord = n_tile * p.BN + rs * kSlab;
             const uint32_t fb = full_dst0 + static_cast<uint32_t>(stage) * 8u;
-            if (cta2) {
+            if constexpr (cta2) {
               if (crank == 0) mbar_expect_tx_a(full0 + stage * 8, 2u * static_cast<uint32_t>(p.a_bytes));
               if (p.patch) tma_load_4d_2cta(a_dst, &tmR, fb, r_coord, c1, c2, c3);
               else tma_load_2d_2cta(a_dst, &tmR, fb, r_coord, c1);
@@ -932,10 +948,10 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
   // -------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (cta2) cluster_sync_all();        // the peer may still read this CTA's weight halves or arrive on its barriers
+  if constexpr (cta2) cluster_sync_all();   // the peer may still read this CTA's weight halves or arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
-    if (cta2) tmem_dealloc_2cta(tmem_base, tmem_cols);
+    if constexpr (cta2) tmem_dealloc_2cta(tmem_base, tmem_cols);
     else tmem_dealloc_dyn(tmem_base, tmem_cols);
   }
 }

@@ -5,7 +5,7 @@ namespace frb {
 
 cudaError_t conv_tma_launch_bf16(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
                                const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
-  return conv_tma_dispatch<true, false>(res, act, grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  return conv_tma_dispatch<true, false, false>(res, act, grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
 }
 
 }  // namespace frb

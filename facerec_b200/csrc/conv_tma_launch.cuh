@@ -5,10 +5,10 @@
 
 namespace frb {
 
-template <bool kBF16, bool kStall, int kRes, int kAct>
+template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair>
 static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a, const CUtensorMap& tmA,
                                        const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
-  auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct>;
+  auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct, kPair>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -32,18 +32,18 @@ static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, c
 }
 
 // res: ConvRes of the launch; act: 0 per-channel slope, 1 ReLU, 2 linear (an upsampled residual always takes 0)
-template <bool kBF16, bool kStall>
+template <bool kBF16, bool kStall, bool kPair>
 static cudaError_t conv_tma_dispatch(int res, int act, int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a,
                                      const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
-  if (res == RES_POST_ACT_UPSAMPLE) return conv_tma_launch_one<kBF16, kStall, 2, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  if (res == RES_POST_ACT_UPSAMPLE) return conv_tma_launch_one<kBF16, kStall, 2, 0, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   if (res == RES_PRE_ACT) {
-    if (act == 1) return conv_tma_launch_one<kBF16, kStall, 1, 1>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
-    if (act == 2) return conv_tma_launch_one<kBF16, kStall, 1, 2>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
-    return conv_tma_launch_one<kBF16, kStall, 1, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+    if (act == 1) return conv_tma_launch_one<kBF16, kStall, 1, 1, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+    if (act == 2) return conv_tma_launch_one<kBF16, kStall, 1, 2, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+    return conv_tma_launch_one<kBF16, kStall, 1, 0, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   }
-  if (act == 1) return conv_tma_launch_one<kBF16, kStall, 0, 1>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
-  if (act == 2) return conv_tma_launch_one<kBF16, kStall, 0, 2>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
-  return conv_tma_launch_one<kBF16, kStall, 0, 0>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  if (act == 1) return conv_tma_launch_one<kBF16, kStall, 0, 1, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  if (act == 2) return conv_tma_launch_one<kBF16, kStall, 0, 2, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
+  return conv_tma_launch_one<kBF16, kStall, 0, 0, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
 }
 
 }  // namespace frb

@@ -371,7 +371,7 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     a.b_resident = 2;
   // CTA pairs: per-tap / linear path with streamed weights.  Two M tiles per pair and N tile; results are the same bits
   // (a tile's k-blocks accumulate in the same order), so the choice may depend on the amount of work.
-  a.cta2 = (ctx->cta2 && !a.halo && !a.b_resident && L.has_tmB2 && m_tiles >= 2 &&
+  a.cta2 = (ctx->cta2 && a.stall == nullptr && !a.halo && !a.b_resident && L.has_tmB2 && m_tiles >= 2 &&
             (io.res_mode != RES_PRE_ACT || (L.BN % kSlab) == 0) && io.out_mode != OUT_HEAD_SCATTER &&
             ((m_tiles + 1) / 2) * L.n_tiles >= ctx->num_sms / 2) ? 1 : 0;
   if (a.cta2) a.total_tiles = static_cast<int>(((m_tiles + 1) / 2) * L.n_tiles);
@@ -417,7 +417,9 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (a.stall != nullptr && !ctx->use_bf16) le = conv_tma_launch_stall(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
   else
 #endif
-  if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
+  if (a.cta2) le = ctx->use_bf16 ? conv_tma_launch_bf16_pair(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI)
+                                 : conv_tma_launch_f16_pair(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
+  else if (ctx->use_bf16) le = conv_tma_launch_bf16(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
   else le = conv_tma_launch_f16(io.res_mode, act, grid, smem, stream, a, tmA, tmBsel, tmO, tmR, tmI);
   FRB_CUDA(ctx, le);
   ctx->launches++;
