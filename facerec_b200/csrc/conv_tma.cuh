@@ -33,7 +33,7 @@
 // Weight slice (FRB_OPT_WEIGHT_SLICE): when the grid is a multiple of the number of N tiles, tile % n_tiles is the
 // same for every tile of a CTA, and a slice of up to 48 KB is loaded once like the small matrices above.
 //
-// CTA pairs (FRB_OPT_CTA2, per-tap / linear path with streamed weights): two CTAs on the SMs of one TPC (cluster of 2,
+// CTA pairs (FRB_OPT_CTA2; every path except 1x1 layers with resident weights / weight slices, which are HBM-bound): two CTAs on the SMs of one TPC (cluster of 2,
 // cta_group::2) work on two M tiles of the SAME N tile with ONE tcgen05.mma of M = 256: each CTA loads its own A blocks
 // and residual slabs and HALF of every weight block (BN/2 rows), the leader CTA (cluster rank 0) issues the MMAs, commits
 // are multicast to both CTAs' barriers, the epilogues hand the accumulators back on the leader's barrier.  The layers that
@@ -569,26 +569,25 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.BN);
       const uint32_t b_res = b_lo0 + static_cast<uint32_t>((n_tile - res_nt0) * p.num_kb) * b_step;   // resident weights of this N tile
       auto mma4 = [&](uint32_t a, uint32_t b, uint32_t acc0) {          // one 64-channel tap out of a halo tile
-        tc_mma_f16(d_tmem, pack_desc(a, hi_halo), pack_desc(b, hi1024), idesc, acc0);
-        tc_mma_f16(d_tmem, pack_desc(a + 2, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
-        tc_mma_f16(d_tmem, pack_desc(a + 4, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
-        tc_mma_f16(d_tmem, pack_desc(a + 6, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
+        mma(d_tmem, pack_desc(a, hi_halo), pack_desc(b, hi1024), idesc, acc0);
+        mma(d_tmem, pack_desc(a + 2, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
+        mma(d_tmem, pack_desc(a + 4, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
+        mma(d_tmem, pack_desc(a + 6, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
         if (p.mpair) {                                                   // the patch 8 pixels (8 x 128 B) to the right
           const uint32_t d2 = d_tmem + static_cast<uint32_t>(p.BN);
-          tc_mma_f16(d2, pack_desc(a + 64, hi_halo), pack_desc(b, hi1024), idesc, acc0);
-          tc_mma_f16(d2, pack_desc(a + 66, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
-          tc_mma_f16(d2, pack_desc(a + 68, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
-          tc_mma_f16(d2, pack_desc(a + 70, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
+          mma(d2, pack_desc(a + 64, hi_halo), pack_desc(b, hi1024), idesc, acc0);
+          mma(d2, pack_desc(a + 66, hi_halo), pack_desc(b + 2, hi1024), idesc, 1u);
+          mma(d2, pack_desc(a + 68, hi_halo), pack_desc(b + 4, hi1024), idesc, 1u);
+          mma(d2, pack_desc(a + 70, hi_halo), pack_desc(b + 6, hi1024), idesc, 1u);
         }
       };
       auto commit_tile = [&]() {                                         // accumulator(s) complete -> epilogue
-        tc_commit_a(tfull0 + buf * 8);
-        if (p.mpair) tc_commit_a(tfull0 + (buf + 1) * 8);
+        commit(tfull0 + buf * 8);
+        if (p.mpair) commit(tfull0 + (buf + 1) * 8);
       };
       const uint32_t row_a = static_cast<uint32_t>(p.halo_w) * 8u;             // next halo row (descriptor units of 16 B)
-      bool halo_done = false;
-      if constexpr (!cta2) {       // (pairs never take the halo paths: these branches hold cta_group::1 instructions)
-      halo_done = p.halo != 0;
+      const bool halo_done = p.halo != 0;
+      {
       if (p.halo && p.b_resident) {
         // Resident weights: nothing but the halo tile has to arrive, so ALL taps of a channel block go out under one
         // barrier wait, back to back (an mbarrier wait costs the pipe ~140 cycles, tools/umma_issue_probe.cu; the
@@ -624,7 +623,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
                 }
               }
             }
-            tc_commit_a(aempty0 + astage * 8);
+            commit(aempty0 + astage * 8);
             if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
           }
           __syncwarp();
@@ -656,9 +655,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
                   acc_t = 1u;
                 }
               }
-              tc_commit_a(empty0 + stage * 8);
+              commit(empty0 + stage * 8);
               if (tr == p.kh - 1) {
-                tc_commit_a(aempty0 + astage * 8);
+                commit(aempty0 + astage * 8);
                 if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
               }
             }
@@ -695,9 +694,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               const bool last_tap = tr == p.kh - 1 && ts == p.kw - 1;
               if (elect_one()) {
                 mma4(a_tap, b_tap, acc);
-                if (!p.b_resident) tc_commit_a(empty0 + stage * 8);
+                if (!p.b_resident) commit(empty0 + stage * 8);
                 if (last_tap) {
-                  tc_commit_a(aempty0 + astage * 8);
+                  commit(aempty0 + astage * 8);
                   if (kRes != 1 && cb == p.cin_blocks - 1) commit_tile();
                 }
               }
@@ -800,22 +799,37 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
     long long st_empty = 0, st_rempty = 0;
     const long long st_begin = kStall && sc.on ? clock64() : 0;
     // pair: completion bytes of both CTAs' loads are signalled on the LEADER's barriers (its issuer waits on them)
-    uint32_t full_dst0 = full0;
-    if constexpr (cta2) full_dst0 = mapa_shared(full0, 0);
-    if ((p.b_resident || kRes == 1) && lane == 0) {
+    // pair: completion bytes of BOTH CTAs' loads are signalled on the LEADER's barriers (its issuer waits on them); the
+    // leader announces the sum.  `lead` turns a local barrier address into the leader's (same offset in its window).
+    uint32_t lead = 0u;
+    if constexpr (cta2) lead = mapa_shared(full0, 0) - full0;
+    const uint32_t full_dst0 = full0 + lead;
+    auto expect = [&](uint32_t bar, uint32_t bytes) {
       if constexpr (cta2) {
-        // (resident weights never run as pairs) each CTA holds half of the identity's rows: 32 x 64
-        if (crank == 0) mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(kIdentBytes));
-        if (kRes == 1) tma_load_2d_2cta(smem_u32(smem_i), &tmI, mapa_shared(smem_u32(bres_bar), 0), 0, static_cast<int>(crank) * 32);
+        if (crank == 0) mbar_expect_tx_a(bar, 2u * bytes);
       } else {
-        mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>((p.b_resident ? res_nts * p.num_kb * b_stage_bytes : 0) +
-                                                              (kRes == 1 ? kIdentBytes : 0)));
-        if (p.b_resident)
-          for (int nt = 0; nt < res_nts; ++nt)
-            for (int kb = 0; kb < p.num_kb; ++kb)
-              tma_load_2d(smem_b + (nt * p.num_kb + kb) * b_stage_bytes, &tmB, bres_bar, kb * kBK, (res_nt0 + nt) * p.BN);
-        if (kRes == 1) tma_load_2d(smem_i, &tmI, bres_bar, 0, 0);
+        mbar_expect_tx_a(bar, bytes);
       }
+    };
+    auto ld2 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {
+      if constexpr (cta2) tma_load_2d_2cta(dst, m, bar + lead, x, y);
+      else tma_load_2d_a(dst, m, bar, x, y);
+    };
+    auto ld4 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1_, int c2_, int c3_) {
+      if constexpr (cta2) tma_load_4d_2cta(dst, m, bar + lead, c0, c1_, c2_, c3_);
+      else tma_load_4d_a(dst, m, bar, c0, c1_, c2_, c3_);
+    };
+    if ((p.b_resident || kRes == 1) && lane == 0) {
+      // a pair holds half of every resident weight block (b_rows rows) and half of the identity (32 rows) per CTA
+      const uint32_t bres = smem_u32(bres_bar);
+      expect(bres, static_cast<uint32_t>((p.b_resident ? res_nts * p.num_kb * b_stage_bytes : 0) +
+                                          (kRes == 1 ? (cta2 ? kIdentBytes / 2 : kIdentBytes) : 0)));
+      if (p.b_resident)
+        for (int nt = 0; nt < res_nts; ++nt)
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            ld2(smem_u32(smem_b) + static_cast<uint32_t>((nt * p.num_kb + kb) * b_stage_bytes), &tmB, bres, kb * kBK,
+                (res_nt0 + nt) * p.BN + static_cast<int>(crank) * b_rows);
+      if (kRes == 1) ld2(smem_u32(smem_i), &tmI, bres, 0, static_cast<int>(crank) * 32);
     }
     griddep_wait();                      // weights and identity are constants; activations are the previous kernel's
     const uint32_t tx_bytes = static_cast<uint32_t>((p.b_resident ? 0 : b_stage_bytes) + p.a_bytes);
@@ -832,9 +846,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
           mbar_wait_a(aempty0 + astage * 8, aphase ^ 1, p.watchdog, 320 + astage);
           sc.stop(st_empty);
           if (elect_one()) {
-            mbar_expect_tx_a(afull0 + astage * 8, halo_tx);
-            tma_load_4d_a(a_s0 + static_cast<uint32_t>(astage * p.halo_bytes), &tmA, afull0 + astage * 8, hb * kBK, c1 - p.pw,
-                          c2 - p.ph, c3);
+            expect(afull0 + astage * 8, halo_tx);
+            ld4(a_s0 + static_cast<uint32_t>(astage * p.halo_bytes), &tmA, afull0 + astage * 8, hb * kBK, c1 - p.pw, c2 - p.ph, c3);
           }
           __syncwarp();
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
@@ -845,10 +858,9 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
               sc.stop(st_empty);
               if (elect_one()) {
-                mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(p.brow * b_stage_bytes));
+                expect(full0 + stage * 8, static_cast<uint32_t>(p.brow * b_stage_bytes));
                 for (int ts = 0; ts < p.brow; ++ts)
-                  tma_load_2d_a(b_dst + static_cast<uint32_t>(ts * b_stage_bytes), &tmB, full0 + stage * 8,
-                                kcoord + ts * p.cin_blocks * kBK, n_coord);
+                  ld2(b_dst + static_cast<uint32_t>(ts * b_stage_bytes), &tmB, full0 + stage * 8, kcoord + ts * p.cin_blocks * kBK, n_coord);
               }
               __syncwarp();
               kcoord += p.brow * p.cin_blocks * kBK;
@@ -862,8 +874,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
               mbar_wait_a(empty0 + stage * 8, phase ^ 1, p.watchdog, 300 + stage);
               sc.stop(st_empty);
               if (elect_one()) {
-                mbar_expect_tx_a(full0 + stage * 8, static_cast<uint32_t>(b_stage_bytes));
-                tma_load_2d_a(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
+                expect(full0 + stage * 8, static_cast<uint32_t>(b_stage_bytes));
+                ld2(b_dst, &tmB, full0 + stage * 8, kcoord, n_coord);
               }
               __syncwarp();
               kcoord += p.cin_blocks * kBK;

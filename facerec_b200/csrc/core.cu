@@ -369,14 +369,15 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   if (!a.b_resident && !a.halo && ctx->weight_slice && L.n_tiles > 1 && slice_bytes <= kResidentSliceBytes &&
       a.total_tiles >= 4 * ctx->num_sms && L.n_tiles <= ctx->num_sms / 4)
     a.b_resident = 2;
-  // CTA pairs: per-tap / linear path with streamed weights.  Two M tiles per pair and N tile; results are the same bits
+  // CTA pairs: every path but the HBM-bound 1x1 layers with resident weights or weight slices.  Two M tiles per pair and
+  // N tile, half of each weight block (streamed or resident) per CTA; results are the same bits
   // (a tile's k-blocks accumulate in the same order), so the choice may depend on the amount of work.
-  a.cta2 = (ctx->cta2 && a.stall == nullptr && !a.halo && !a.b_resident && L.has_tmB2 && m_tiles >= 2 &&
+  a.cta2 = (ctx->cta2 && a.stall == nullptr && a.b_resident != 2 && (a.halo || !a.b_resident) && L.has_tmB2 && m_tiles >= 2 &&
             (io.res_mode != RES_PRE_ACT || (L.BN % kSlab) == 0) && io.out_mode != OUT_HEAD_SCATTER &&
             ((m_tiles + 1) / 2) * L.n_tiles >= ctx->num_sms / 2) ? 1 : 0;
   if (a.cta2) a.total_tiles = static_cast<int>(((m_tiles + 1) / 2) * L.n_tiles);
   const int b_rows = a.cta2 ? L.BN / 2 : L.BN;
-  const int res_bytes = a.b_resident == 2 ? slice_bytes : w_bytes;
+  const int res_bytes = (a.b_resident == 2 ? slice_bytes : w_bytes) / (a.cta2 ? 2 : 1);
   const int base_fixed = kOutBufs * kSlabBytes + (a.b_resident ? res_bytes : 0) + (io.res_mode == RES_PRE_ACT ? kIdentBytes : 0) +
                          (4 * kMaxStages + 20) * 8 + 2048 + 1024;
   const int total_budget = 226 * 1024 - base_fixed;

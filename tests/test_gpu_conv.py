@@ -62,9 +62,12 @@ CASES = [
     (2, 135, 240, 256, 512, 1, 1, (2, 2), (0, 0), 0, 0, False),  # layer2.0 downsample: strided 1x1, two N tiles
     (3, 67, 119, 512, 256, 1, 1, (1, 1), (0, 0), 2, 2, False),   # FPN lateral + upsampled top-down, ODD number of M tiles
     (5, 33, 59, 192, 320, 3, 3, (2, 2), (1, 1), 1, 0, False),    # ragged strided patches, 160-wide N tiles (80 + 80), odd M tiles
+    (3, 135, 240, 128, 128, 3, 3, (1, 1), (1, 1), 1, 0, False),  # pairs on halo tiles, a filter row of streamed weights per stage
+    (2, 135, 240, 256, 256, 3, 3, (1, 1), (1, 1), 1, 0, False),  # pairs on PAIRED halo tiles (FPN merge1): 4 patches per weight stage
+    (2, 133, 239, 64, 64, 3, 3, (1, 1), (1, 1), 1, 0, False),    # pairs on halo tiles with resident weights (32 rows per CTA), ragged
 ]
-SLICE_CASES = CASES[-9:-6]
-PAIR_CASES = CASES[-6:]
+SLICE_CASES = CASES[-12:-9]
+PAIR_CASES = CASES[-9:]
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
