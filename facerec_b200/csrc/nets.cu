@@ -12,6 +12,7 @@
 // A forward for a given (batch, H, W) is planned once: tensors get arena offsets by liveness
 // (greedy interval placement), ops are replayed on the caller's stream.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <stdexcept>
@@ -207,7 +208,10 @@ static void add_dw(Net* net, const WeightBlob& blob, const std::string& name, in
 }
 
 // Layers whose epilogue adds a residual tile stage two 64-column slabs of it in shared memory.
-static const int kResBnCap = 128;
+// N tile cap of the layers that add a residual: 256 where K is long enough to pay for the wider tile (every N tile of an
+// M tile re-reads the A blocks: layer3 / layer4 conv3 + skip went 0.62 -> 0.55 and 0.53 -> 0.36 ms per launch), 128 for
+// the short-K ones, which keep a resident weight slice per CTA instead (layer2 conv3, Block35).
+static int res_bn_cap(int cin) { return cin >= 256 ? 256 : 128; }
 
 // ------------------------------------------------------------------------------------ architecture tables
 static const int kMnetStride[13] = {1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1};
@@ -268,7 +272,7 @@ static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
         const std::string p = sfmt("layer%d.%d", l + 1, i);
         add_plain(net, blob, p + ".conv1", 0.f, 1, 1, 0, 0);
         add_plain(net, blob, p + ".conv2", 0.f, s, s, 1, 1);
-        add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0, 0, 1.f, kResBnCap);   // ReLU after the residual add
+        add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0, 0, 1.f, res_bn_cap(kR50Planes[l]));   // ReLU after the residual add
         if (i == 0) add_plain(net, blob, p + ".down", 1.f, s, s, 0, 0);
       }
   } else {
@@ -353,7 +357,7 @@ static void load_irv1(Net* net, const WeightBlob& blob) {
     place(u, blob, p + ".conv2d", 0, 0, 0.f, 0.17f, 0, 32);
     place(u, blob, p + ".conv2d", 0, 32, 0.f, 0.17f, 64, 32);
     place(u, blob, p + ".conv2d", 0, 64, 0.f, 0.17f, 32, 32);
-    add_conv(net, p + ".up", u, 1, 1, 0, 0, kResBnCap);
+    add_conv(net, p + ".up", u, 1, 1, 0, 0, res_bn_cap(96));
   }
   add_plain(net, blob, "mixed_6a.branch0", 0.f, 2, 2, 0, 0);
   add_plain(net, blob, "mixed_6a.branch1.0", 0.f, 1, 1, 0, 0);
@@ -372,7 +376,7 @@ static void load_irv1(Net* net, const WeightBlob& blob) {
       add_plain(net, blob, p + ".branch1.1", 0.f, 1, 1, 0, 1);   // 1x3
       add_plain(net, blob, p + ".branch1.2", 0.f, 1, 1, 1, 0);   // 3x1
     }
-    add_plain(net, blob, p + ".conv2d", out_slope, 1, 1, 0, 0, 0, scale, kResBnCap);   // input order (b0, b1.2) == source order
+    add_plain(net, blob, p + ".conv2d", out_slope, 1, 1, 0, 0, 0, scale, res_bn_cap(2 * cb));   // input order (b0, b1.2) == source order
     net->conv_idx[p + ".up"] = net->conv_idx[p + ".conv2d"];
   };
   for (int i = 0; i < 10; ++i) add_block_17_8(sfmt("repeat_2.%d", i), 896, 128, 0.10f, 0.f, true);
