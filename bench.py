@@ -18,11 +18,13 @@ all_gather of the embeddings) and configs[4] (50k queries x 1M actor embeddings,
 device-timed rate, end-to-end rate and roofline, so that the driver's 1/2/4/8-GPU runs exercise the path's only collective.
 
 `value`  : frames/s with the batch already resident in HBM when the timed region starts.
-`e2e`    : the same through the host-facing call (FacePipeline.detect_embed) with pinned HOST frames:
-           H2D of the batch and D2H of detections + embeddings inside the timed region.
+`e2e`    : the same from pinned HOST frames: every step copies its own 64 frames host -> device (a copy stream prefetches
+           step k+1 under step k, as the extractor does) into FacePipeline.step_device and reads detections + embeddings
+           back (D2H) inside the timed region.
 `roofline`: the RetinaFace-R50 forward (70 launches of conv_tma_kernel after layer fusion + 1 max-pool), timed with
            CUDA events on the launching stream inside the timed region; algorithmic work
-           449.71 GFLOP/frame x 64 frames per launch of the forward.
+           449.71 GFLOP/frame x 64 frames per launch of the forward.  `traffic` is not measured by this
+           script: it is the dram__bytes sum of the committed ncu launch list of the same forward (profiles/r02_fwd_traffic.json).
 """
 from __future__ import annotations
 
@@ -138,6 +140,19 @@ def load_peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
     return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+
+
+def cited_traffic(backbone, B, H, W):
+    """DRAM bytes of one forward from the committed ncu launch list (tools/summarize_launches.py): a CITED constant,
+    bench.py does not run under a profiler."""
+    p = os.path.join(ROOT, "profiles", "r02_fwd_traffic.json")
+    if (backbone, B, H, W) != ("r50", 64, 1080, 1920) or not os.path.exists(p):
+        return {"traffic": None}
+    d = json.load(open(p))
+    return {"traffic": d["dram_bytes"],
+            "traffic_unit": f"bytes per forward, CITED from the ncu launch list {d['source']} ({d['dram_read_bytes'] / 1e9:.1f} GB read + "
+                            f"{d['dram_write_bytes'] / 1e9:.1f} GB written over {d['launches']} launches; algorithmic minimum 2.60 GB/frame x 64 = 166 GB; "
+                            f"L2 -> SM {d['l2_bytes'] / 1e9:.0f} GB; time-weighted tensor-pipe active {d['tensor_pipe_active_pct_time_weighted']:.1f} %)"}
 
 
 def make_batch(seed, first, B, H, W):
@@ -626,11 +641,8 @@ def run_b200(a):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": fwd_tflops / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum over the 71 launches of one forward (64 x 1080p,
-                         # R50), ncu metrics pass of tools/forward_once.py: profiles/r01_ncu_conv_tma_v5.md
-                         "traffic": 157.5e9 if (a.backbone, B, H, W) == ("r50", 64, 1080, 1920) else None,
-                         "traffic_unit": "bytes per forward, ncu dram__bytes of the 71 launches (94.9 GB read + 62.6 GB written, profiles/r01_fwd_launches_v15.csv; algorithmic minimum 2.60 GB/frame x 64 = 166 GB)",
-                         "kernel": f"conv_tma_kernel x{fwd_launches - 1} (+1 maxpool) = one frb_retina_forward over {B} frames",
+                         **cited_traffic(a.backbone, B, H, W),
+                         "kernel": f"conv_tma_kernel x{fwd_launches - 1} (single-CTA and CTA-pair instantiations, heads included) + 1 maxpool = one frb_retina_forward over {B} frames",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
         if dist_recs:
