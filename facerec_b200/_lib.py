@@ -70,6 +70,8 @@ SIGNATURES = {
     "frb_linkage_complete": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "frb_knn_topk": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "frb_knn_redo_count": (_i, [_vp]),
+    "frb_knn_fit": (_i, [_vp, _vp, _i, _i, _vp]),
+    "frb_workspace_bytes": (C.c_longlong, [_vp, _i, _i, _i, _i]),
     "frb_knn_vote": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "frb_format_f32_json": (C.c_longlong, [_vp, _i, _vp, C.c_longlong]),
     "frb_sort_create": (_vp, [_i, _i, C.c_double]),

@@ -155,6 +155,20 @@ int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   return run_knn_topk(ctx, d_Q, Q, d_DB, M, D, k, d_idx, d_dist, static_cast<cudaStream_t>(stream));
 }
 
+long long frb_workspace_bytes(frb_ctx* ctx, int model_id, int B, int H, int W) {
+  if (ctx == nullptr) return -1;
+  Net* net = find_net(ctx, model_id);
+  if (net == nullptr || B <= 0) return -1;
+  if (model_id == FRB_IRV1) { H = 160; W = 160; }
+  return net_workspace_bytes(net, B, H, W);
+}
+
+int frb_knn_fit(frb_ctx* ctx, const float* d_DB, int M, int D, void* stream) {
+  FRB_ENTER(ctx);
+  FRB_NEED(ctx, d_DB != nullptr, "frb_knn_fit: null pointer");
+  return run_knn_fit(ctx, d_DB, M, D, static_cast<cudaStream_t>(stream));
+}
+
 int frb_knn_redo_count(frb_ctx* ctx) { return ctx ? ctx->knn_redo_last : -1; }
 
 int frb_knn_vote(frb_ctx* ctx, const int32_t* d_idx, const int32_t* d_label_idx, int Q, int k, int n_classes,

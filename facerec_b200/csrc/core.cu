@@ -42,7 +42,7 @@ int check_cuda(frb_ctx* ctx, cudaError_t e, const char* what) {
 int check_last(frb_ctx* ctx, const char* what) { return check_cuda(ctx, cudaGetLastError(), what); }
 
 int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out) {
-  if (slot < 0 || slot >= 8) return set_err(ctx, FRB_ERR_INVALID, "bad scratch slot %d", slot);
+  if (slot < 0 || slot >= frb_ctx::kScratchSlots) return set_err(ctx, FRB_ERR_INVALID, "bad scratch slot %d", slot);
   if (ctx->scratch_bytes[slot] < bytes) {
     if (ctx->scratch[slot]) {
       FRB_CUDA(ctx, cudaDeviceSynchronize());   // the old buffer may still be in use by queued work
@@ -538,7 +538,7 @@ int frb_destroy(frb_ctx* ctx) {
   for (int i = 0; i < 2; ++i)
     if (ctx->d_ident[i]) cudaFree(ctx->d_ident[i]);
   if (ctx->trace_dev) cudaFree(ctx->trace_dev);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < frb_ctx::kScratchSlots; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   delete ctx;
   return FRB_OK;

@@ -781,6 +781,28 @@ static void knn_chunks(frb_ctx* ctx, DistArgs& a) {
   a.items = a.m_pairs * a.chunks;
 }
 
+// KNeighborsClassifier.fit: the database's scaled fp16 planes, |x|^2 (+inf padded), max |x|^2 and scale exponent, kept
+// in scratch slots of their own until the next fit
+int run_knn_fit(frb_ctx* ctx, const float* d_DB, int M, int D, cudaStream_t st) {
+  if (M <= 0 || D <= 0) return set_err(ctx, FRB_ERR_INVALID, "knn_fit: bad shape");
+  const int Dp = round_up(D, kGK);
+  const int m_pad = round_up(M, kGN);
+  void *ds = nullptr, *dn = nullptr, *fm = nullptr;
+  int rc;
+  ctx->knn_fit_db = nullptr;
+  if ((rc = ctx_scratch(ctx, 8, static_cast<size_t>(M) * 2 * Dp * 2, &ds)) != FRB_OK) return rc;
+  if ((rc = ctx_scratch(ctx, 9, static_cast<size_t>(m_pad) * 4, &dn)) != FRB_OK) return rc;
+  if ((rc = ctx_scratch(ctx, 10, 64, &fm)) != FRB_OK) return rc;
+  FRB_CUDA(ctx, cudaMemsetAsync(fm, 0, 64, st));
+  unsigned int* bits = static_cast<unsigned int*>(fm);          // [0] max |x|^2, [1] max |x_ij|, [2] exponent
+  if ((rc = max_abs(ctx, d_DB, static_cast<size_t>(M) * D, bits + 1, st)) != FRB_OK) return rc;
+  if ((rc = split_rows(ctx, d_DB, M, D, Dp, 1.f, bits + 1, ds, static_cast<float*>(dn), m_pad, INFINITY, bits, reinterpret_cast<int*>(bits + 2), st)) != FRB_OK) return rc;
+  ctx->knn_fit_db = d_DB;
+  ctx->knn_fit_m = M;
+  ctx->knn_fit_d = D;
+  return FRB_OK;
+}
+
 int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k, int32_t* d_idx,
                  float* d_dist, cudaStream_t st) {
   if (Q < 0 || M <= 0 || D <= 0 || k <= 0 || k > kTopK) return set_err(ctx, FRB_ERR_INVALID, "knn_topk: bad shape (k must be 1..%d)", kTopK);
@@ -789,19 +811,25 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   const int m_pad = round_up(M, kGN);
   void *qs = nullptr, *qn = nullptr, *ds = nullptr, *dn = nullptr, *pd = nullptr, *pi = nullptr, *misc = nullptr;
   int rc;
-  if ((rc = ctx_scratch(ctx, 0, static_cast<size_t>(M) * 2 * Dp * 2, &ds)) != FRB_OK) return rc;
-  if ((rc = ctx_scratch(ctx, 1, static_cast<size_t>(m_pad) * 4, &dn)) != FRB_OK) return rc;
+  const bool fitted = ctx->knn_fit_db == d_DB && ctx->knn_fit_m == M && ctx->knn_fit_d == D && ctx->scratch[8] != nullptr;
+  if (fitted) {
+    ds = ctx->scratch[8];
+    dn = ctx->scratch[9];
+  } else {
+    if ((rc = ctx_scratch(ctx, 0, static_cast<size_t>(M) * 2 * Dp * 2, &ds)) != FRB_OK) return rc;
+    if ((rc = ctx_scratch(ctx, 1, static_cast<size_t>(m_pad) * 4, &dn)) != FRB_OK) return rc;
+  }
   if ((rc = ctx_scratch(ctx, 2, static_cast<size_t>(Q) * 2 * Dp * 2, &qs)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 3, static_cast<size_t>(Q) * 4, &qn)) != FRB_OK) return rc;
   // misc (32-bit words): [0] max |x|^2 bits, [1] redo count, [2] max|q| bits, [3] max|x| bits, [4] exp(Q), [5] exp(DB),
   //                      [8, 8+Q) redo list, [8+Q, 8+2Q) published thresholds, [8+2Q, 8+3Q) thresholds of the exact pass
   if ((rc = ctx_scratch(ctx, 6, (static_cast<size_t>(Q) * 3 + 8) * 4, &misc)) != FRB_OK) return rc;
-  unsigned int* d_max_bits = static_cast<unsigned int*>(misc);
+  unsigned int* d_max_bits = fitted ? static_cast<unsigned int*>(ctx->scratch[10]) : static_cast<unsigned int*>(misc);
   int32_t* d_redo_count = static_cast<int32_t*>(misc) + 1;
   unsigned int* d_maxabs_q = static_cast<unsigned int*>(misc) + 2;
   unsigned int* d_maxabs_db = static_cast<unsigned int*>(misc) + 3;
   int* d_exp_q = static_cast<int*>(misc) + 4;
-  int* d_exp_db = static_cast<int*>(misc) + 5;
+  int* d_exp_db = fitted ? static_cast<int*>(ctx->scratch[10]) + 2 : static_cast<int*>(misc) + 5;
   int32_t* d_redo_list = static_cast<int32_t*>(misc) + 8;
   unsigned int* d_thr = static_cast<unsigned int*>(misc) + 8 + Q;
   unsigned int* d_thr2 = d_thr + Q;
@@ -822,9 +850,11 @@ int run_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M
   if ((rc = ctx_scratch(ctx, 4, part * 4, &pd)) != FRB_OK) return rc;
   if ((rc = ctx_scratch(ctx, 5, part * 4, &pi)) != FRB_OK) return rc;
   // database: plain split, |x|^2 padded with +inf; queries: split scaled by -2 (accumulator = -2 q.x in scaled units)
-  if ((rc = max_abs(ctx, d_DB, static_cast<size_t>(M) * D, d_maxabs_db, st)) != FRB_OK) return rc;
+  if (!fitted) {
+    if ((rc = max_abs(ctx, d_DB, static_cast<size_t>(M) * D, d_maxabs_db, st)) != FRB_OK) return rc;
+    if ((rc = split_rows(ctx, d_DB, M, D, Dp, 1.f, d_maxabs_db, ds, static_cast<float*>(dn), m_pad, INFINITY, d_max_bits, d_exp_db, st)) != FRB_OK) return rc;
+  }
   if ((rc = max_abs(ctx, d_Q, static_cast<size_t>(Q) * D, d_maxabs_q, st)) != FRB_OK) return rc;
-  if ((rc = split_rows(ctx, d_DB, M, D, Dp, 1.f, d_maxabs_db, ds, static_cast<float*>(dn), m_pad, INFINITY, d_max_bits, d_exp_db, st)) != FRB_OK) return rc;
   if ((rc = split_rows(ctx, d_Q, Q, D, Dp, -2.f, d_maxabs_q, qs, static_cast<float*>(qn), Q, 0.f, nullptr, d_exp_q, st)) != FRB_OK) return rc;
   CUtensorMap tmA, tmB;
   if ((rc = encode_f16_rows(ctx, &tmA, qs, Q, Dp)) != FRB_OK) return rc;

@@ -55,9 +55,15 @@ struct frb_ctx {
   long long launches = 0;      // kernels launched through this context (bench bookkeeping)
   bool attr_nms = false;       // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: tracked per context
   bool attr_dist = false;
+  // frb_knn_fit: the database whose split planes / norms are kept in scratch slots 0 / 1 (and its max |x|^2, scale exponent)
+  const float* knn_fit_db = nullptr;
+  int knn_fit_m = 0, knn_fit_d = 0;
+  unsigned int knn_fit_max_norm_bits = 0;
+  int knn_fit_exp = 0;
   int knn_redo_last = 0;       // queries of the last frb_knn_topk call that needed the exact three-segment pass
-  void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  static constexpr int kScratchSlots = 12;   // 0-7 per-call scratch of the distance stage, 8-10 the fitted kNN database
+  void* scratch[kScratchSlots] = {};
+  size_t scratch_bytes[kScratchSlots] = {};
 };
 
 namespace frb {
@@ -143,6 +149,7 @@ int launch_crop_resize(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, c
 int run_pdist(frb_ctx*, const float* d_X, int N, int D, int row0, int rows, int layout, void* d_out, cudaStream_t);
 int run_knn_topk(frb_ctx*, const float* d_Q, int Q, const float* d_DB, int M, int D, int k, int32_t* d_idx, float* d_dist,
                  cudaStream_t);
+int run_knn_fit(frb_ctx*, const float* d_DB, int M, int D, cudaStream_t);
 int run_knn_vote(frb_ctx*, const int32_t* d_idx, const int32_t* d_label_idx, int Q, int k, int n_classes, float* d_proba,
                  cudaStream_t);
 int run_segment_mean(frb_ctx*, const float* d_X, const int32_t* d_offsets, int S, int D, float* d_out, cudaStream_t);
@@ -161,5 +168,6 @@ int net_forward_retina(frb_ctx* ctx, Net* net, const void* d_in, int B, int H, i
                        float* d_landm, cudaStream_t stream);
 int net_forward_irv1(frb_ctx* ctx, Net* net, const void* d_in, int F, float* d_emb, cudaStream_t stream);
 void destroy_net(Net* net);
+long long net_workspace_bytes(Net* net, int B, int H, int W);
 
 }  // namespace frb

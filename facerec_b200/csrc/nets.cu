@@ -676,6 +676,21 @@ static Plan* get_plan(Net* net, int B, int H, int W) {
   return &res.first->second;
 }
 
+// Bytes of the activation arena a forward of this shape needs (the arena is allocated, and only ever grows, on the first
+// forward of a shape; a caller that wants no allocation on its hot path runs one warm-up forward per shape it uses).
+long long net_workspace_bytes(Net* net, int B, int H, int W) {
+  try {
+    Plan plan;
+    plan.B = B; plan.H = H; plan.W = W;
+    if (net->model == FRB_IRV1) plan_irv1(net, plan);
+    else plan_retina(net, plan, net->model == FRB_RETINA_R50);
+    assign_arena(plan);
+    return static_cast<long long>(plan.arena_bytes);
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
+
 // ------------------------------------------------------------------------------------ execution
 struct ExecPtrs {
   const void* in = nullptr;

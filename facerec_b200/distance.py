@@ -117,6 +117,7 @@ class B200KNeighborsClassifier:
         self.classes_, inv = np.unique(y, return_inverse=True)
         self._db = torch.from_numpy(X).to(self.device)
         self._labels = torch.from_numpy(inv.astype(np.int32)).to(self.device)
+        ops.knn_fit(self.ctx, self._db)        # the database's fp16 planes and norms are prepared once, not per query batch
         return self
 
     def kneighbors(self, V, n_neighbors: Optional[int] = None):

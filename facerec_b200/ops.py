@@ -200,6 +200,16 @@ def knn_topk(ctx: Context, Q: torch.Tensor, DB: torch.Tensor, k: int):
     return idx, dist
 
 
+def knn_fit(ctx: Context, DB: torch.Tensor) -> None:
+    """Prepare the database once (KNeighborsClassifier.fit); later knn_topk calls with the SAME tensor reuse it."""
+    _need_cuda(DB, "DB", torch.float32)
+    ctx.check(ctx.lib.frb_knn_fit(ctx.handle, ptr(DB), DB.shape[0], DB.shape[1], current_stream()), "frb_knn_fit")
+
+
+def workspace_bytes(ctx: Context, model_id: int, B: int, H: int = 160, W: int = 160) -> int:
+    return int(ctx.lib.frb_workspace_bytes(ctx.handle, model_id, B, H, W))
+
+
 def knn_redo_count(ctx: Context) -> int:
     """Queries of the last knn_topk call that went through the exact split-bf16 pass (diagnostics)."""
     return int(ctx.lib.frb_knn_redo_count(ctx.handle))

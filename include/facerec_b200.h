@@ -91,6 +91,11 @@ int frb_debug_layer_times(frb_ctx* ctx, double* h_rows, int max_rows);
  * Replaces: model construction at facerec/extract.py:392 and facerec/detector.py:64. */
 int frb_load_model(frb_ctx* ctx, int model_id, const void* h_blob, size_t bytes);
 
+/* Bytes of the activation arena a forward of `model_id` needs for B frames of H x W (B faces for FRB_IRV1; H, W ignored
+ * there), or -1 if the model is not loaded.  The library allocates the arena itself on the first forward of a shape and only
+ * ever grows it: one warm-up forward per shape leaves the hot path free of allocations. */
+long long frb_workspace_bytes(frb_ctx* ctx, int model_id, int B, int H, int W);
+
 /* ---- per-frame path ----------------------------------------------------------------------- */
 
 /* Layout of the 16-bit network input produced by K1. */
@@ -198,6 +203,12 @@ int frb_linkage_complete(frb_ctx* ctx, float* d_D /*[N,N]*/, int N, int32_t* d_m
  * Replaces KNeighborsClassifier.fit/kneighbors (facerec/classify_knn.py:212,227). */
 int frb_knn_topk(frb_ctx* ctx, const float* d_Q, int Q, const float* d_DB, int M, int D, int k,
                  int32_t* d_idx /*[Q,k] ascending distance*/, float* d_dist /*[Q,k]*/, void* stream);
+
+/* The `fit` half of KNeighborsClassifier.fit / predict_proba (facerec/classify_knn.py:212): prepares the database once
+ * (power-of-two scaling, fp16 hi / lo planes, |x|^2) and keeps it inside ctx; later frb_knn_topk calls that pass the SAME
+ * d_DB, M, D reuse it instead of preparing the database on every call (0.65 ms per 10^6 rows).  The caller must not change
+ * the database in place without calling frb_knn_fit again.  Optional: frb_knn_topk works without it. */
+int frb_knn_fit(frb_ctx* ctx, const float* d_DB, int M, int D, void* stream);
 
 /* Diagnostics: how many queries of the LAST frb_knn_topk call on ctx could not be proven from the one-pass bf16 scan
  * and went through the exact split-bf16 pass (results are exact either way; this only costs time). */

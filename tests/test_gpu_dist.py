@@ -121,6 +121,31 @@ def test_knn_tight_clusters_take_the_exact_pass(ctx):
     assert ops.knn_redo_count(ctx) < 60
 
 
+def test_knn_fit_reuses_the_prepared_database(ctx):
+    """frb_knn_fit (KNeighborsClassifier.fit): later frb_knn_topk calls with the same database tensor skip its preparation
+    and give the same bits; another database, or the same one after a new fit, is never confused with it."""
+    from facerec_b200 import ops
+    rng = np.random.RandomState(21)
+    db = torch.from_numpy(_mixture(rng, 7000, centres=60)).cuda()
+    db2 = torch.from_numpy(_mixture(rng, 7000, centres=60)).cuda()
+    q = torch.from_numpy(_mixture(rng, 400, centres=60)).cuda()
+    plain = [t.clone() for t in ops.knn_topk(ctx, q, db, 10)]
+    plain2 = [t.clone() for t in ops.knn_topk(ctx, q, db2, 10)]
+    l0 = ctx.launch_count()
+    ops.knn_topk(ctx, q, db, 10)
+    unfitted = ctx.launch_count() - l0
+    ops.knn_fit(ctx, db)
+    ops.pdist(ctx, db[:300].contiguous())                       # other distance calls must not disturb the fitted planes
+    l0 = ctx.launch_count()
+    fitted = ops.knn_topk(ctx, q, db, 10)
+    assert ctx.launch_count() - l0 == unfitted - 2              # no max-abs / split pass over the database
+    assert all(torch.equal(a, b) for a, b in zip(plain, fitted))
+    other = ops.knn_topk(ctx, q, db2, 10)                       # a different tensor: prepared per call as before
+    assert all(torch.equal(a, b) for a, b in zip(plain2, other))
+    from facerec_b200 import weights as W
+    assert ops.workspace_bytes(ctx, W.MODEL_IDS["irv1"], 8) in (-1,) or ops.workspace_bytes(ctx, W.MODEL_IDS["irv1"], 8) > 0
+
+
 def test_knn_vote_matches_sklearn_predict_proba(ctx):
     from sklearn.neighbors import KNeighborsClassifier
     from facerec_b200 import ops
@@ -151,7 +176,8 @@ def test_segment_mean_matches_numpy(ctx):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("n,d,dup", [(2, 8, False), (37, 16, False), (700, 512, False), (1500, 512, False), (400, 4, True)])
+@pytest.mark.parametrize("n,d,dup", [(2, 8, False), (37, 16, False), (700, 512, False), (1500, 512, False), (400, 4, True),
+                                     (4000, 512, False), (3000, 3, True)])
 def test_gpu_linkage_equals_scipy_on_same_distances(ctx, n, d, dup):
     """frb_linkage_complete + host relabelling == scipy linkage(method='complete') fed the SAME fp32 distances
     (bit-identical Z, ties included: `dup` plants duplicate points and a coarse grid so many distances tie)."""
