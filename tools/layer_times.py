@@ -19,7 +19,7 @@ def main():
     model = sys.argv[1] if len(sys.argv) > 1 else "retina_r50"
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
-    H, Wd = 1080, 1920
+    H, Wd = int(os.environ.get("FRB_H", "1080")), int(os.environ.get("FRB_W", "1920"))
     ctx = _lib.Context(0)
     if os.environ.get("FRB_DUAL"):
         ctx.set_option(_lib.FRB_OPT_DUAL_ISSUE, int(os.environ["FRB_DUAL"]))
