@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfacerec_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "conv_tma_f16_pair.cu", "conv_tma_bf16_pair.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
+SOURCES = ["core.cu", "conv_tma_f16.cu", "conv_tma_bf16.cu", "conv_tma_f16_pair.cu", "conv_tma_bf16_pair.cu", "conv_tail.cu", "glue.cu", "nets.cu", "dist.cu", "scene.cu",
            "linkage.cu", "sort.cu", "jsonfmt.cu", "api.cu"]
 # FRB_DEBUG_BUILD=1: the tuning experiments of include/facerec_b200_debug.h (stall-accounting kernel variants, skipped loads)
 DEBUG_BUILD = os.environ.get("FRB_DEBUG_BUILD", "0") not in ("", "0")

@@ -1,0 +1,379 @@
+// K2t — the tail of a ResNet bottleneck fused with the head of the next one (layer1 of RetinaFace-R50):
+//
+//   y  = relu(conv3_1x1(a) + skip)          [M, 256]   (what conv_tma_kernel<res = 1, act = 1> writes)
+//   y1 = relu(conv1_1x1_next(y))            [M, N2]    (what the next block's conv_tma_kernel<0, 1> writes)
+//
+// Both layers are HBM-bound at 1080p (profiles/r02_layer_times_r50_ab_pairs_res256.txt: conv3 + skip 1.59 ms at 6.0 TB/s,
+// the next conv1 0.77 ms at 6.9 TB/s of which 4.25 GB is re-reading y), so the only way to make them faster is not to read
+// y again: the staged output slabs of y — which the epilogue packs into the 128-byte-swizzled K-major layout for their TMA
+// store anyway — are at the same time the A operand of the second GEMM.  Per 128-pixel tile:
+//
+//   producer   A block(s) of a and the four 64-channel skip slabs -> stage ring (16 KB boxes)
+//   issuer     G1: acc1[buf] (256 TMEM columns)  = a x W3   (N = 256 MMAs), then += skip slab x I (N = 64 MMAs on the slab's
+//                  columns: the skip is added by the tensor core exactly as in conv_tma_kernel, same order, same bits)
+//   epilogue   e1: per 64-column slab: TMEM -> +bias -> 16-bit -> ReLU -> slab slot (swizzled) -> TMA store into y,
+//                  and "slab written" to the issuer
+//   issuer     M2: acc2 (columns [0, N2) of the SAME buffer, drained by then) (+)= slab x W1n block, slabs in channel
+//                  order (the accumulation order of the unfused conv1: its output bits do not change either)
+//   epilogue   e2: TMEM -> +bias2 -> 16-bit -> ReLU -> slab slot -> TMA store into y1; buffer back to the issuer
+//
+// Weights of both layers and the identity stay resident in shared memory.  Epilogue items (4 e1 slabs + N2/64 e2 slabs per
+// tile) are dealt round-robin to three independent 4-warp groups; a slab slot is reused when its TMA store has finished
+// reading it and (e1) the M2 MMAs on it have retired.  The issuer runs G1 one tile ahead of M2, so the epilogue of tile t
+// overlaps G1 of tile t + 1; every wait in here depends only on earlier items, so the pipeline cannot deadlock.
+// Linear M tiling (1x1, stride 1, no padding); ragged last tile: loads zero-fill, stores clip.
+#include <algorithm>
+#include <string.h>
+
+#include "conv_igemm.cuh"
+#include "host.h"
+
+namespace frb {
+
+constexpr int kTailEpiWarps = 12;
+constexpr int kTailGroups = kTailEpiWarps / 4;
+constexpr int kTailThreads = (kTailEpiWarps + 2) * 32;     // + MMA issuer + TMA producer
+constexpr int kTailN1 = 256;                               // conv3 output channels = one MMA N
+constexpr int kTailSlab = 64;
+constexpr int kTailSlabBytes = kBM * kTailSlab * 2;        // 16 KB: one A box, one skip slab, one output slab
+constexpr int kTailMaxRing = 8, kTailMaxSlots = 8;
+constexpr int kTailIdentBytes = 64 * 128;
+
+struct ConvTailArgs {
+  int M, m_tiles;
+  int kb1;               // 64-channel blocks of conv3's input (1 or 2)
+  int N2;                // output channels of the next conv1: 64 or 128
+  int ring, slots;
+  const float* bias1;    // [256]
+  const float* bias2;    // [N2]
+  int* watchdog;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kTailThreads, 1)
+conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO1,
+                 const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmW3,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmI) {
+  using E = Elem16<kBF16>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int w1_block = p.N2 * 128;                                   // one 64-wide k-block of the next conv1's weights
+  uint8_t* smem_w3 = smem;                                           // [kb1][256 x 64]
+  uint8_t* smem_w1 = smem_w3 + p.kb1 * (kTailN1 * 128);              // [4][N2 x 64]
+  uint8_t* smem_i = smem_w1 + 4 * w1_block;                          // 64 x 64 identity
+  uint8_t* smem_ring = smem_i + kTailIdentBytes;
+  uint8_t* smem_slot = smem_ring + p.ring * kTailSlabBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slot + p.slots * kTailSlabBytes);
+  uint64_t* full_bar = bars;                          // [8] ring slot filled by TMA
+  uint64_t* empty_bar = bars + 8;                     // [8] ring slot consumed by the MMAs
+  uint64_t* slabw_bar = bars + 16;                    // [8] slab slot written by its epilogue group (e1)
+  uint64_t* sfree_bar = bars + 24;                    // [8] slab slot free again: 2 arrivals (store drained, M2 retired)
+  uint64_t* acc1_bar = bars + 32;                     // [2] G1 + skip complete
+  uint64_t* acc2_bar = bars + 34;                     // [2] M2 complete
+  uint64_t* afree_bar = bars + 36;                    // [2] e2 has drained the buffer
+  uint64_t* bres_bar = bars + 38;                     // resident operands have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 39);
+  float* s_bias1 = reinterpret_cast<float*>(bars + 40);   // [256]
+  float* s_bias2 = s_bias1 + kTailN1;                     // [128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kMmaWarp = kTailEpiWarps, kTmaWarp = kTailEpiWarps + 1;
+  const int ns2 = p.N2 / kTailSlab;
+  const int ipt = 4 + ns2;                                           // epilogue items per tile
+  const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO1); tma_prefetch_desc(&tmO2);
+    tma_prefetch_desc(&tmW3); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmI);
+  }
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < 8; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+        mbar_init(&slabw_bar[s], 1);
+        mbar_init(&sfree_bar[s], 2);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&acc1_bar[b], 1);
+        mbar_init(&acc2_bar[b], 1);
+        mbar_init(&afree_bar[b], 4 * ns2);
+      }
+      mbar_init(bres_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < kTailN1) s_bias1[threadIdx.x] = __ldg(p.bias1 + threadIdx.x);
+  else if (threadIdx.x < kTailN1 + p.N2) s_bias2[threadIdx.x - kTailN1] = __ldg(p.bias2 + threadIdx.x - kTailN1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kTailEpiWarps) {
+    // ================================================================ epilogue groups
+    const int quarter = warp & 3;
+    const int grp = warp >> 2;
+    const int gtid = threadIdx.x & 127;
+    const bool leader = gtid == 0;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw7 = static_cast<uint32_t>(row & 7);
+    const int my_items = my_tiles * ipt;
+    int t = grp / ipt, j = grp - t * ipt;                            // tile iteration, item inside the tile
+    int slot = grp % p.slots, use = grp / p.slots;                   // slab slot of the item, how often it has been used
+    int prev_slot = -1;
+    for (int q = grp; q < my_items; q += kTailGroups) {
+      const int buf = t & 1;
+      const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
+      const bool second = j >= 4;                                    // e2 item
+      const int s = second ? j - 4 : j;
+      const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
+      if (leader && prev_slot >= 0) {
+        // the group's previous store has finished reading its slot: first of the slot's two "free" arrivals (for an e2
+        // slot, which no MMA reads, the second one too)
+        tma_store_wait_read<0>();
+        mbar_arrive(&sfree_bar[prev_slot & 15]);
+        if (prev_slot & 16) mbar_arrive(&sfree_bar[prev_slot & 15]);
+      }
+      mbar_wait(&sfree_bar[slot], (static_cast<uint32_t>(use) & 1u) ^ 1u, p.watchdog, 100 + slot);
+      mbar_wait(second ? &acc2_bar[buf] : &acc1_bar[buf], aph, p.watchdog, second ? 120 + buf : 110 + buf);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTailN1 + s * kTailSlab);
+      const float* bias = second ? s_bias2 + s * kTailSlab : s_bias1 + s * kTailSlab;
+      uint8_t* const orow = smem_slot + slot * kTailSlabBytes + static_cast<uint32_t>(row) * 128u;
+      uint32_t v0[16], v1[16];
+      auto finish16 = [&](const uint32_t* v, int cbase) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int cc = cbase + c * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + cc);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + cc + 4);
+          uint4 o;
+          o.x = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y));
+          o.y = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w));
+          o.z = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y));
+          o.w = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(cc >> 3) ^ sw7) << 4)) = o;
+        }
+      };
+      tmem_ld16(taddr, v0);
+      tc_wait_ld16(v0);
+      tmem_ld16(taddr + 16, v1);
+      finish16(v0, 0);
+      tc_wait_ld16(v1);
+      tmem_ld16(taddr + 32, v0);
+      finish16(v1, 16);
+      tc_wait_ld16(v0);
+      tmem_ld16(taddr + 48, v1);
+      finish16(v0, 32);
+      tc_wait_ld16(v1);
+      tc_fence_before();                       // the accumulator columns of this warp are in registers
+      if (second) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afree_bar[buf]);
+      }
+      finish16(v1, 48);
+      fence_proxy_async_smem();                // the slab is read by TMA (store) and by the tensor core (M2)
+      named_bar_sync(1 + grp, 128);
+      if (leader) {
+        if (!second) {
+          mbar_arrive(&slabw_bar[slot]);
+          tma_store_2d(&tmO1, smem_slot + slot * kTailSlabBytes, s * kTailSlab, m0);
+        } else {
+          tma_store_2d(&tmO2, smem_slot + slot * kTailSlabBytes, s * kTailSlab, m0);
+        }
+        tma_store_commit();
+        prev_slot = slot | (second ? 16 : 0);
+      }
+      j += kTailGroups;
+      while (j >= ipt) { j -= ipt; ++t; }
+      slot += kTailGroups;
+      while (slot >= p.slots) { slot -= p.slots; ++use; }
+    }
+    if (leader) {
+      tma_store_wait<0>();                     // stores must land before the CTA (and its smem) goes away
+      // (nobody waits for the last slots any more: no arrival needed)
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc1 = make_idesc_f16(kBM, kTailN1, kBF16 ? 1 : 0);
+    const uint32_t idesc_r = make_idesc_f16(kBM, kTailSlab, kBF16 ? 1 : 0);
+    const uint32_t idesc2 = make_idesc_f16(kBM, p.N2, kBF16 ? 1 : 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t ring_lo = desc_lo(smem_u32(smem_ring)), slot_lo = desc_lo(smem_u32(smem_slot));
+    const uint32_t w3_lo = desc_lo(smem_u32(smem_w3)), w1_lo = desc_lo(smem_u32(smem_w1)), id_lo = desc_lo(smem_u32(smem_i));
+    const uint32_t step = kTailSlabBytes >> 4;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), slabw0 = smem_u32(slabw_bar),
+                   sfree0 = smem_u32(sfree_bar), acc10 = smem_u32(acc1_bar), acc20 = smem_u32(acc2_bar), afree0 = smem_u32(afree_bar);
+    int stage = 0;
+    uint32_t phase = 0;
+    mbar_wait(bres_bar, 0, p.watchdog, 250);
+    auto mma4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc0) {
+      tc_mma_f16(d, pack_desc(a, hi), pack_desc(b, hi), idesc, acc0);
+      tc_mma_f16(d, pack_desc(a + 2, hi), pack_desc(b + 2, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 4, hi), pack_desc(b + 4, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 6, hi), pack_desc(b + 6, hi), idesc, 1u);
+    };
+    auto issue_g1 = [&](int t) {
+      const int buf = t & 1;
+      const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTailN1);
+      mbar_wait_a(afree0 + buf * 8, (static_cast<uint32_t>(t >> 1) & 1u) ^ 1u, p.watchdog, 200 + buf);
+      tc_fence_after();
+      for (int kb = 0; kb < p.kb1; ++kb) {
+        mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+        tc_fence_after();
+        if (elect_one()) {
+          mma4(d, ring_lo + static_cast<uint32_t>(stage) * step, w3_lo + static_cast<uint32_t>(kb) * ((kTailN1 * 128) >> 4), idesc1,
+               kb != 0 ? 1u : 0u);
+          tc_commit_a(empty0 + stage * 8);
+        }
+        __syncwarp();
+        if (++stage == p.ring) { stage = 0; phase ^= 1; }
+      }
+      for (int rs = 0; rs < 4; ++rs) {
+        mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+        tc_fence_after();
+        if (elect_one()) {
+          mma4(d + static_cast<uint32_t>(rs * kTailSlab), ring_lo + static_cast<uint32_t>(stage) * step, id_lo, idesc_r, 1u);
+          tc_commit_a(empty0 + stage * 8);
+          if (rs == 3) tc_commit_a(acc10 + buf * 8);
+        }
+        __syncwarp();
+        if (++stage == p.ring) { stage = 0; phase ^= 1; }
+      }
+    };
+    int slot = 0, use = 0;                    // slab slot of the next e1 item M2 consumes
+    auto issue_m2 = [&](int t) {
+      const int buf = t & 1;
+      const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTailN1);
+      for (int s = 0; s < 4; ++s) {
+        mbar_wait_a(slabw0 + slot * 8, static_cast<uint32_t>(use) & 1u, p.watchdog, 230 + slot);
+        if (s == 0 && ns2 == 2) {
+          // acc2 of a 128-wide conv1 covers the columns of slabs 0 AND 1: both must have left TMEM
+          int s1 = slot + 1, u1 = use;
+          if (s1 == p.slots) { s1 = 0; ++u1; }
+          mbar_wait_a(slabw0 + s1 * 8, static_cast<uint32_t>(u1) & 1u, p.watchdog, 240 + s1);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          mma4(d, slot_lo + static_cast<uint32_t>(slot) * step, w1_lo + static_cast<uint32_t>(s) * (static_cast<uint32_t>(w1_block) >> 4),
+               idesc2, s != 0 ? 1u : 0u);
+          tc_commit_a(sfree0 + slot * 8);
+          if (s == 3) tc_commit_a(acc20 + buf * 8);
+        }
+        __syncwarp();
+        if (++slot == p.slots) { slot = 0; ++use; }
+      }
+      // the tile's e2 items take the next ns2 slots
+      for (int e = 0; e < ns2; ++e)
+        if (++slot == p.slots) { slot = 0; ++use; }
+    };
+    if (my_tiles > 0) issue_g1(0);
+    for (int t = 0; t < my_tiles; ++t) {
+      if (t + 1 < my_tiles) issue_g1(t + 1);
+      issue_m2(t);
+    }
+  } else {
+    // ================================================================ TMA producer
+    const uint32_t ring0 = smem_u32(smem_ring);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    if (lane == 0) {
+      const uint32_t bres = smem_u32(bres_bar);
+      mbar_expect_tx_a(bres, static_cast<uint32_t>(p.kb1 * kTailN1 * 128 + 4 * w1_block + kTailIdentBytes));
+      for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d_a(smem_u32(smem_w3) + static_cast<uint32_t>(kb * kTailN1 * 128), &tmW3, bres, kb * kBK, 0);
+      for (int s = 0; s < 4; ++s) tma_load_2d_a(smem_u32(smem_w1) + static_cast<uint32_t>(s * w1_block), &tmW1, bres, s * kBK, 0);
+      tma_load_2d_a(smem_u32(smem_i), &tmI, bres, 0, 0);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
+      for (int i = 0; i < p.kb1 + 4; ++i) {
+        mbar_wait_a(empty0 + stage * 8, phase ^ 1u, p.watchdog, 300 + stage);
+        if (elect_one()) {
+          mbar_expect_tx_a(full0 + stage * 8, kTailSlabBytes);
+          if (i < p.kb1) tma_load_2d_a(ring0 + static_cast<uint32_t>(stage * kTailSlabBytes), &tmA, full0 + stage * 8, i * kBK, m0);
+          else tma_load_2d_a(ring0 + static_cast<uint32_t>(stage * kTailSlabBytes), &tmR, full0 + stage * 8, (i - p.kb1) * kTailSlab, m0);
+        }
+        __syncwarp();
+        if (++stage == p.ring) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  // -------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_base, 512);
+  }
+}
+
+// Which pairs of layers the fused kernel takes: conv3 (1x1, Cin 64 or 128 -> 256, ReLU after the skip) followed by the next
+// block's conv1 (1x1, 256 -> 64 or 128, ReLU), both with every channel on ReLU.
+bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1) {
+  auto lin = [](const ConvLayer& L) { return L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0 && !L.special; };
+  return lin(L3) && lin(L1) && L3.Cout == kTailN1 && L3.Cout_pad == kTailN1 && (L3.Cin == 64 || L3.Cin == 128) && L3.K_pad == L3.Cin &&
+         L1.Cin == kTailN1 && L1.K_pad == kTailN1 && L1.Cout == 64 && L1.Cout_pad == L1.Cout && L3.act_kind == 1 &&
+         L1.act_kind == 1;
+}
+
+int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
+                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream) {
+  if (!conv_tail_applicable(L3, L1)) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: layer pair not supported");
+  if (M <= 0 || M > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: bad problem size");
+  const void* ptrs[4] = {in, res, out1, out2};
+  const int lds[4] = {in_ld, res_ld, out1_ld, out2_ld};
+  for (int i = 0; i < 4; ++i)
+    if ((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) != 0 || (lds[i] % 8) != 0)
+      return set_err(ctx, FRB_ERR_INVALID, "conv_tail: operands must be 16-byte aligned with a pixel stride that is a multiple of 8");
+  ConvTailArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = static_cast<int>(M);
+  a.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  a.kb1 = L3.Cin / kBK;
+  a.N2 = L1.Cout;
+  a.bias1 = L3.d_bias;
+  a.bias2 = L1.d_bias;
+  a.watchdog = ctx->wd_dev;
+  const int fixed = a.kb1 * kTailN1 * 128 + 4 * a.N2 * 128 + kTailIdentBytes + 40 * 8 + (kTailN1 + 128) * 4 + 1024;
+  const int units = (227 * 1024 - fixed) / kTailSlabBytes;               // 16 KB buffers left for the ring and the slab slots
+  // skip slabs spend one TMA latency in the ring, output slabs an epilogue pass plus a store drain in their slot
+  a.ring = std::min(kTailMaxRing, std::max(3, units - units * 5 / 9));
+  a.slots = std::min(kTailMaxSlots, units - a.ring);
+  if (a.slots < 3) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: shared-memory plan does not fit");
+  const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.ring + a.slots) * kTailSlabBytes;
+
+  void* ident = nullptr;
+  int rc = ctx_identity(ctx, &ident);
+  if (rc != FRB_OK) return rc;
+  CUtensorMap tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI;
+  if ((rc = encode_2d(ctx, &tmA, in, L3.Cin, M, static_cast<uint64_t>(in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmR, res, kTailN1, M, static_cast<uint64_t>(res_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmO1, out1, kTailN1, M, static_cast<uint64_t>(out1_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmO2, out2, a.N2, M, static_cast<uint64_t>(out2_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmW3, L3.d_w, L3.K_pad, L3.Cout_pad, static_cast<uint64_t>(L3.K_pad) * 2, kBK, kTailN1)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmW1, L1.d_w, L1.K_pad, L1.Cout_pad, static_cast<uint64_t>(L1.K_pad) * 2, kBK, a.N2)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64)) != FRB_OK) return rc;
+
+  const int grid = std::min(a.m_tiles, ctx->num_sms);
+  if (ctx->use_bf16) {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_tail_kernel<true><<<grid, kTailThreads, smem, stream>>>(a, tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI);
+  } else {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_tail_kernel<false><<<grid, kTailThreads, smem, stream>>>(a, tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI);
+  }
+  ctx->launches++;
+  return check_last(ctx, "conv_tail_kernel launch");
+}
+
+}  // namespace frb

@@ -58,6 +58,19 @@ int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out) {
   return FRB_OK;
 }
 
+// 64 x 64 identity in the activation type: B operand of the MMAs that add a residual slab into the accumulator
+int ctx_identity(frb_ctx* ctx, void** out) {
+  void*& ident = ctx->d_ident[ctx->use_bf16 ? 1 : 0];
+  if (ident == nullptr) {
+    std::vector<uint16_t> h(64 * 64, 0);
+    for (int i = 0; i < 64; ++i) h[i * 64 + i] = ctx->use_bf16 ? 0x3F80 : 0x3C00;   // 1.0
+    FRB_CUDA(ctx, cudaMalloc(&ident, h.size() * 2));
+    FRB_CUDA(ctx, cudaMemcpy(ident, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  }
+  *out = ident;
+  return FRB_OK;
+}
+
 // ----------------------------------------------------------------------------- conv host side
 static int pick_bn(int cout_pad16, int cap) {
   cap = std::max(16, std::min(256, cap)) & ~15;
@@ -258,14 +271,9 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   memset(&tmI, 0, sizeof(tmI));
   if (io.res_mode == RES_PRE_ACT) {
     // 64 x 64 identity in the activation type: B operand of the MMAs that add the residual into the accumulator
-    void*& ident = ctx->d_ident[ctx->use_bf16 ? 1 : 0];
-    if (ident == nullptr) {
-      std::vector<uint16_t> h(64 * 64, 0);
-      for (int i = 0; i < 64; ++i) h[i * 64 + i] = ctx->use_bf16 ? 0x3F80 : 0x3C00;   // 1.0
-      FRB_CUDA(ctx, cudaMalloc(&ident, h.size() * 2));
-      FRB_CUDA(ctx, cudaMemcpy(ident, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    }
-    int irc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64);
+    void* ident = nullptr;
+    int irc = ctx_identity(ctx, &ident);
+    if (irc == FRB_OK) irc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64);
     if (irc != FRB_OK) return irc;
   }
   int rc;
@@ -566,6 +574,12 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_FUSE_TAIL:
+      if (ctx->fuse_tail != (value ? 1 : 0)) {
+        ctx->fuse_tail = value ? 1 : 0;
+        for (auto& kv : ctx->nets) net_drop_plans(kv.second);     // the op list of a forward changes
+      }
+      return FRB_OK;
 #ifndef FRB_DEBUG_BUILD
     case FRB_OPT_FORCE_GATHER:
     case FRB_OPT_SKIP_LOADS:

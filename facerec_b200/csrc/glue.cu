@@ -187,6 +187,86 @@ int launch_preprocess_s2d(frb_ctx* ctx, const uint8_t* d_frames, int B, int H, i
   return check_last(ctx, "preprocess_s2d_kernel");
 }
 
+// ------------------------------------------------------------------------------------------ K3
+// First convolution of a network: 3x3 over the 3 real channels of the NHWC8 input (RetinaFace-MobileNet0.25 body.0,
+// InceptionResnetV1 conv2d_1a).  K = 27 is no work for a tensor core (the implicit-GEMM fallback spent 0.54 of a 1.7 ms
+// MobileNet forward here, 10x its HBM time): one thread computes 8 output channels of one pixel on the CUDA cores, fp32
+// accumulation over (r, s, c) in that order, 16-bit weights from the layer's prepared matrix staged in shared memory.
+template <bool kBF16>
+__global__ void __launch_bounds__(256) conv3x3_c3_direct_kernel(const uint4* __restrict__ in, int B, int H, int W, int stride, int pad, int Ho,
+                                                                 int Wo, const uint16_t* __restrict__ w16, int K_pad, int Cout,
+                                                                 const float* __restrict__ bias, const float* __restrict__ slope,
+                                                                 uint4* __restrict__ out, int out_c8) {
+  extern __shared__ float s_w[];                      // [Cout][27] (r, s, c)
+  for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
+    const int n = i / 27, t = i - n * 27, tap = t / 3, c = t - tap * 3;
+    const uint16_t u = w16[static_cast<size_t>(n) * K_pad + tap * 8 + c];
+    float f;
+    if (kBF16) f = __uint_as_float(static_cast<uint32_t>(u) << 16);
+    else f = __half2float(*reinterpret_cast<const __half*>(&u));
+    s_w[i] = f;
+  }
+  __syncthreads();
+  const int cg = Cout >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    long long t = i / cg;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * stride - pad + r;
+      if (static_cast<unsigned>(ih) >= static_cast<unsigned>(H)) continue;
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int iw = ow * stride - pad + sx;
+        if (static_cast<unsigned>(iw) >= static_cast<unsigned>(W)) continue;
+        const uint4 v = __ldg(in + (static_cast<long long>(b) * H + ih) * W + iw);
+        const float2 x01 = H16<kBF16>::up(v.x);
+        const float x2 = H16<kBF16>::up(v.y).x;
+        const float* wt = s_w + (g * 8) * 27 + (r * 3 + sx) * 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = fmaf(x01.x, wt[j * 27 + 0], acc[j]);
+          acc[j] = fmaf(x01.y, wt[j * 27 + 1], acc[j]);
+          acc[j] = fmaf(x2, wt[j * 27 + 2], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = acc[j] + __ldg(bias + g * 8 + j);
+      acc[j] = fmaf(__ldg(slope + g * 8 + j), fminf(y, 0.f), fmaxf(y, 0.f));     // leaky: slope 0 = ReLU, 1 = linear
+    }
+    out[((static_cast<long long>(b) * Ho + oh) * Wo + ow) * out_c8 + g] = pack8<kBF16>(acc);
+  }
+}
+
+int launch_conv3x3_c3_direct(frb_ctx* ctx, const void* in, int B, int H, int W, int stride, int pad, const void* d_w16, int K_pad,
+                             int Cout, const float* d_bias, const float* d_slope, void* out, int out_ld, cudaStream_t st) {
+  if (Cout % 8 || out_ld % 8 || Cout > 64) return set_err(ctx, FRB_ERR_INVALID, "direct conv: Cout must be a multiple of 8, at most 64");
+  const int Ho = conv_out_dim(H, 3, stride, pad), Wo = conv_out_dim(W, 3, stride, pad);
+  const long long total = static_cast<long long>(B) * Ho * Wo * (Cout / 8);
+  const int grid = grid_for(total, 256, ctx->num_sms);
+  const size_t smem = static_cast<size_t>(Cout) * 27 * 4;
+  if (ctx->use_bf16)
+    conv3x3_c3_direct_kernel<true><<<grid, 256, smem, st>>>(static_cast<const uint4*>(in), B, H, W, stride, pad, Ho, Wo,
+                                                            static_cast<const uint16_t*>(d_w16), K_pad, Cout, d_bias, d_slope,
+                                                            static_cast<uint4*>(out), out_ld / 8);
+  else
+    conv3x3_c3_direct_kernel<false><<<grid, 256, smem, st>>>(static_cast<const uint4*>(in), B, H, W, stride, pad, Ho, Wo,
+                                                             static_cast<const uint16_t*>(d_w16), K_pad, Cout, d_bias, d_slope,
+                                                             static_cast<uint4*>(out), out_ld / 8);
+  ctx->launches++;
+  return check_last(ctx, "conv3x3_c3_direct_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ K4
 // Depthwise 3x3 (pad 1, stride 1|2) + bias + activation, NHWC, 8 channels per thread.
 // w: [9][C] fp32 (tap-major), bias [C] fp32.

@@ -46,6 +46,7 @@ struct frb_ctx {
   cudaStream_t capture_stream = nullptr;   // graph capture of short forwards happens here, replay on the caller's stream
   int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
+  int fuse_tail = 1;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
@@ -85,6 +86,7 @@ struct ConvLayer {
   int K = 0, K_pad = 0, BN = 0, Cout_pad = 0, n_tiles = 0;
   int act_kind = 0;          // 0 per-channel slope, 1 ReLU on every channel, 2 linear on every channel
   int special = 0;           // 1: ResNet stem over the space-to-depth input (window conv, see nets.cu)
+  int direct3 = 0;           // 1: first conv of a network (3 real input channels of NHWC8, 3x3): CUDA-core kernel K3
   int bn_cap = 0;            // per-layer cap on the N tile (0 = context default); residual layers use 128
   void* d_w = nullptr;       // [Cout_pad, K_pad] 16-bit, K-major, K ordered (r, s, c)
   float* d_bias = nullptr;   // [Cout_pad]
@@ -116,6 +118,8 @@ inline int conv_out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) /
 // 2D tiled tensor map over a row-major 16-bit matrix [outer, inner], 128-byte swizzle.
 int encode_2d(frb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
               uint32_t box_inner, uint32_t box_outer);
+// 64 x 64 identity matrix in the context's activation type (device memory owned by the context)
+int ctx_identity(frb_ctx* ctx, void** out);
 // Grow-only device scratch owned by the context (slot = independent buffer).
 int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out);
 
@@ -124,11 +128,17 @@ int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out);
 int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bias, const float* h_slope);
 void conv_release(ConvLayer& L);
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
+// conv_tail.cu: y = relu(conv3(in) + res) [M, 256] and y1 = relu(conv1_next(y)) [M, L1.Cout] in one launch (K2t)
+bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1);
+int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
+                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream);
 
 // ------------------------------------------------------------------ glue kernels (glue.cu)
 int launch_preprocess_s2d(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out, cudaStream_t);
 int launch_preprocess(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, int out_c, void* d_out,
                       cudaStream_t);
+int launch_conv3x3_c3_direct(frb_ctx*, const void* in, int B, int H, int W, int stride, int pad, const void* d_w16, int K_pad,
+                             int Cout, const float* d_bias, const float* d_slope, void* out, int out_ld, cudaStream_t);
 int launch_dwconv3x3(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_w9c,
                      const float* d_bias, int act, float slope, void* out, cudaStream_t);
 int launch_maxpool3x3s2(frb_ctx*, const void* in, int in_ld, int B, int H, int W, int C, int pad, void* out, int out_ld,
@@ -168,6 +178,7 @@ int net_forward_retina(frb_ctx* ctx, Net* net, const void* d_in, int B, int H, i
                        float* d_landm, cudaStream_t stream);
 int net_forward_irv1(frb_ctx* ctx, Net* net, const void* d_in, int F, float* d_emb, cudaStream_t stream);
 void destroy_net(Net* net);
+void net_drop_plans(Net* net);
 long long net_workspace_bytes(Net* net, int B, int H, int W);
 
 }  // namespace frb

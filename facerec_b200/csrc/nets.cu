@@ -128,10 +128,11 @@ struct TensorInfo {
 struct View {
   int t = -1, coff = 0;
 };
-enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4 };
+// OP_CONV_TAIL: conv3 + skip (layer) and the next block's conv1 (layer2) in one launch (conv_tail.cu); out2 = conv1's output
+enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4, OP_CONV_TAIL = 5 };
 struct Op {
-  int kind = 0, layer = -1;
-  View in, out, res;
+  int kind = 0, layer = -1, layer2 = -1;
+  View in, out, res, out2;
   int res_mode = 0, out_mode = 0, pad = 0, C = 0, P_off = 0;
 };
 struct Plan {
@@ -277,6 +278,7 @@ static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
       }
   } else {
     add_plain(net, blob, "body.0", 0.1f, 2, 2, 1, 1, 8);
+    net->convs.back().direct3 = 1;      // K = 27: CUDA cores (glue.cu K3)
     for (int i = 1; i <= 13; ++i) {
       add_dw(net, blob, sfmt("body.%d.dw", i), kMnetStride[i - 1], 0.1f);
       add_plain(net, blob, sfmt("body.%d.pw", i), 0.1f, 1, 1, 0, 0);
@@ -322,7 +324,7 @@ static void load_irv1(Net* net, const WeightBlob& blob) {
   {
     HostConv c1(64, 3, 3, 8);
     place(c1, blob, "conv2d_1a", 0, 0, 0.f);
-    add_conv(net, "conv2d_1a", c1, 2, 2, 0, 0);
+    add_conv(net, "conv2d_1a", c1, 2, 2, 0, 0);       // (K3's direct kernel measured slower here: 64 output channels, 0.38 vs 0.14 ms at 128 faces)
     HostConv c2(64, 3, 3, 64);
     place(c2, blob, "conv2d_2a", 0, 0, 0.f);
     add_conv(net, "conv2d_2a", c2, 1, 1, 0, 0);
@@ -436,6 +438,13 @@ struct Builder {
     touch(in); touch(out); touch(res);
     plan->ops.push_back(op);
   }
+  void conv_tail(const std::string& name3, const std::string& name1, View in, View res, View out, View out2) {
+    Op op;
+    op.kind = OP_CONV_TAIL; op.layer = layer(name3); op.layer2 = layer(name1); op.in = in; op.res = res; op.out = out; op.out2 = out2;
+    op.res_mode = RES_PRE_ACT;
+    touch(in); touch(res); touch(out); touch(out2);
+    plan->ops.push_back(op);
+  }
   void dw(int idx, View in, View out) {
     Op op;
     op.kind = OP_DW; op.layer = idx; op.in = in; op.out = out;
@@ -482,14 +491,19 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
     int h = conv_out_dim(H1, 3, 2, 1), w = conv_out_dim(W1, 3, 2, 1);
     int x = b.tensor(h, w, 64);
     b.maxpool(V(t1), V(x), 64, 1);
+    int y1_fused = -1;
     for (int l = 0; l < 4; ++l) {
       const int planes = kR50Planes[l];
       for (int i = 0; i < kR50Blocks[l]; ++i) {
         const int s = (i == 0 && l > 0) ? 2 : 1;
         const std::string p = sfmt("layer%d.%d", l + 1, i);
         const int ho = conv_out_dim(h, 3, s, 1), wo = conv_out_dim(w, 3, s, 1);
-        const int y1 = b.tensor(h, w, planes);
-        b.conv(p + ".conv1", V(x), V(y1));
+        int y1 = y1_fused;                       // already written by the previous block's fused tail
+        if (y1 < 0) {
+          y1 = b.tensor(h, w, planes);
+          b.conv(p + ".conv1", V(x), V(y1));
+        }
+        y1_fused = -1;
         const int y2 = b.tensor(ho, wo, planes);
         b.conv(p + ".conv2", V(y1), V(y2));
         int idn = x;
@@ -498,7 +512,15 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
           b.conv(p + ".down", V(x), V(idn));
         }
         const int y = b.tensor(ho, wo, planes * 4);
-        b.conv(p + ".conv3", V(y2), V(y), RES_PRE_ACT, V(idn));
+        // conv3 + skip together with the next block's conv1 (same layer: stride 1, same planes) where K2t takes the pair
+        const std::string pn = sfmt("layer%d.%d", l + 1, i + 1);
+        if (net->ctx->fuse_tail && i + 1 < kR50Blocks[l] &&
+            conv_tail_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")])) {
+          y1_fused = b.tensor(ho, wo, planes);
+          b.conv_tail(p + ".conv3", pn + ".conv1", V(y2), V(idn), V(y), V(y1_fused));
+        } else {
+          b.conv(p + ".conv3", V(y2), V(y), RES_PRE_ACT, V(idn));
+        }
         x = y; h = ho; w = wo;
       }
       if (l >= 1) c[l - 1] = x;
@@ -736,7 +758,21 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
           io.res = base(op.res); io.res_ld = tr.C; io.rH = tr.H; io.rW = tr.W;
         }
         io.loc = ep.loc; io.conf = ep.conf; io.landm = ep.landm; io.P_total = plan.P_total; io.P_off = op.P_off;
-        rc = conv_launch(ctx, net->convs[op.layer], io, st);
+        {
+          const ConvLayer& L = net->convs[op.layer];
+          if (L.direct3 && io.out_mode == OUT_16BIT && io.res_mode == RES_NONE && ti.C == 8 && op.in.coff == 0)
+            rc = launch_conv3x3_c3_direct(ctx, io.in, plan.B, ti.H, ti.W, L.sh, L.ph, L.d_w, L.K_pad, L.Cout, L.d_bias, L.d_slope,
+                                          io.out, io.out_ld, st);
+          else
+            rc = conv_launch(ctx, L, io, st);
+        }
+        break;
+      }
+      case OP_CONV_TAIL: {
+        const TensorInfo& tr = plan.tensors[op.res.t];
+        rc = conv_tail_launch(ctx, net->convs[op.layer], net->convs[op.layer2], base(op.in), ti.C,
+                              static_cast<long long>(plan.B) * ti.H * ti.W, base(op.res), tr.C, base(op.out),
+                              plan.tensors[op.out.t].C, base(op.out2), plan.tensors[op.out2.t].C, st);
         break;
       }
       case OP_DW: {
@@ -764,11 +800,18 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
                       : static_cast<double>(plan.B) * conv_out_dim(ti.H, L.kh, L.sh, L.ph) * conv_out_dim(ti.W, L.kw, L.sw, L.pw);
         N = L.Cout;
         K = static_cast<double>(L.kh) * L.kw * L.Cin;
+      } else if (op.kind == OP_CONV_TAIL) {
+        // reported as one conv row: M pixels, N = both outputs, flop of both GEMMs
+        const ConvLayer& L3 = net->convs[op.layer];
+        const ConvLayer& L1 = net->convs[op.layer2];
+        M = static_cast<double>(plan.B) * ti.H * ti.W;
+        N = L3.Cout + L1.Cout;
+        K = (static_cast<double>(L3.Cout) * L3.Cin + static_cast<double>(L1.Cout) * L1.Cin) / N;
       } else {
         M = static_cast<double>(plan.B) * ti.H * ti.W;
         N = ti.C;
       }
-      const double row[6] = {static_cast<double>(op.kind), M, N, K, 2.0 * M * N * K, 0.0};
+      const double row[6] = {static_cast<double>(op.kind == OP_CONV_TAIL ? OP_CONV : op.kind), M, N, K, 2.0 * M * N * K, 0.0};
       ctx->lt_info.insert(ctx->lt_info.end(), row, row + 6);
       mark();
     }
@@ -877,6 +920,14 @@ static int run_plan_graphed(frb_ctx* ctx, Net* net, Plan& plan, const ExecPtrs& 
     FRB_CUDA(ctx, cudaMemcpyAsync(ep.landm, io + l.off[3], l.out_bytes[2], cudaMemcpyDeviceToDevice, st));
   }
   return FRB_OK;
+}
+
+// An option that changes which ops a forward consists of (FRB_OPT_FUSE_TAIL) invalidates the cached plans.
+void net_drop_plans(Net* net) {
+  if (net == nullptr) return;
+  cudaDeviceSynchronize();
+  drop_graphs(net);
+  net->plans.clear();
 }
 
 Net* build_net(frb_ctx* ctx, int model_id, const void* blob, size_t bytes) {

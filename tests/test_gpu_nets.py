@@ -161,3 +161,30 @@ def test_graph_replay_equals_eager_launches(ctx):
     finally:
         ctx.set_option(_lib.FRB_OPT_GRAPHS, 0)
         eager.close()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 270, 480), (3, 135, 97), (1, 64, 64)])
+def test_fused_bottleneck_tail_does_not_change_results(ctx, B, H, W):
+    """FRB_OPT_FUSE_TAIL: layer1's conv3 + skip and the next block's conv1 as one launch (conv_tail.cu) accumulate in the
+    same order as the two separate launches: heads identical bit for bit, also on ragged last tiles (M % 128 != 0),
+    toggled back and forth on ONE context (the cached plans are rebuilt)."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(11)
+    fr = torch.from_numpy(_frames(rng, B, H, W)).cuda()
+    mid = weights.MODEL_IDS["retina_r50"]
+    c = _lib.Context(0)
+    try:
+        ops.load_model(c, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+        x16 = ops.preprocess_u8(c, fr, True, ops.input_layout(mid))
+        outs = []
+        for fuse in (1, 0, 1):
+            c.set_option(_lib.FRB_OPT_FUSE_TAIL, fuse)
+            n0 = c.launch_count()
+            outs.append([t.clone() for t in ops.retina_forward(c, mid, x16, H, W)])
+            outs[-1].append(c.launch_count() - n0)
+    finally:
+        c.close()
+    assert outs[0][3] == outs[2][3] == outs[1][3] - 2          # two launches fewer per forward
+    for k in range(3):
+        assert torch.isfinite(outs[0][k]).all()
+        assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k])
