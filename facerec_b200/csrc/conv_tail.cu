@@ -16,13 +16,16 @@
 //   issuer     M2: acc2 (columns [0, N2) of the SAME buffer, drained by then) (+)= slab x W1n block, slabs in channel
 //                  order (the accumulation order of the unfused conv1: its output bits do not change either)
 //   epilogue   e2: TMEM -> +bias2 -> 16-bit -> ReLU -> slab slot -> TMA store into y1; buffer back to the issuer
+//   store warp sends the staged slabs (e1 and e2, in order) and hands a slot back once its store has drained
 //
 // Weights of both layers and the identity stay resident in shared memory.  Epilogue items (4 e1 slabs + N2/64 e2 slabs per
-// tile) are dealt round-robin to three independent 4-warp groups; a slab slot is reused when its TMA store has finished
-// reading it and (e1) the M2 MMAs on it have retired.  The issuer runs G1 one tile ahead of M2, so the epilogue of tile t
-// overlaps G1 of tile t + 1; every wait in here depends only on earlier items, so the pipeline cannot deadlock.
+// tile) are dealt round-robin to three independent 4-warp groups that take the slab slots in item order; a slot is reused when its TMA
+// store has finished reading it and (e1) the M2 MMAs on it have retired.  The issuer runs G1 one tile ahead of M2, so the epilogue of tile t
+// overlaps G1 of tile t + 1; every wait in here depends only on earlier items, so the pipeline cannot deadlock
+// (tools/conv_tail_protocol_sim.py replays the barrier protocol under random interleavings and checks every parity wait).
 // Linear M tiling (1x1, stride 1, no padding); ragged last tile: loads zero-fill, stores clip.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_igemm.cuh"
@@ -32,7 +35,7 @@ namespace frb {
 
 constexpr int kTailEpiWarps = 12;
 constexpr int kTailGroups = kTailEpiWarps / 4;
-constexpr int kTailThreads = (kTailEpiWarps + 2) * 32;     // + MMA issuer + TMA producer
+constexpr int kTailThreads = (kTailEpiWarps + 3) * 32;     // + MMA issuer + TMA producer + store warp
 constexpr int kTailN1 = 256;                               // conv3 output channels = one MMA N
 constexpr int kTailSlab = 64;
 constexpr int kTailSlabBytes = kBM * kTailSlab * 2;        // 16 KB: one A box, one skip slab, one output slab
@@ -44,7 +47,9 @@ struct ConvTailArgs {
   int kb1;               // 64-channel blocks of conv3's input (1 or 2)
   int N2;                // output channels of the next conv1: 64 or 128
   int ring, slots;
-  const float* bias1;    // [256]
+  int kbx;               // 0: the skip is a tensor (four 64-channel slabs per tile, added through the identity); > 0: the skip is
+                         // a 1x1 conv of x computed right here, kbx 64-channel blocks of x per tile (tmR = x, tmI = its weights)
+  const float* bias1;    // [256] (skip conv: conv3's bias + the skip conv's)
   const float* bias2;    // [N2]
   int* watchdog;
 };
@@ -63,8 +68,8 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
   const int w1_block = p.N2 * 128;                                   // one 64-wide k-block of the next conv1's weights
   uint8_t* smem_w3 = smem;                                           // [kb1][256 x 64]
   uint8_t* smem_w1 = smem_w3 + p.kb1 * (kTailN1 * 128);              // [4][N2 x 64]
-  uint8_t* smem_i = smem_w1 + 4 * w1_block;                          // 64 x 64 identity
-  uint8_t* smem_ring = smem_i + kTailIdentBytes;
+  uint8_t* smem_i = smem_w1 + 4 * w1_block;                          // 64 x 64 identity, or [kbx][256 x 64] skip-conv weights
+  uint8_t* smem_ring = smem_i + (p.kbx ? p.kbx * (kTailN1 * 128) : kTailIdentBytes);
   uint8_t* smem_slot = smem_ring + p.ring * kTailSlabBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slot + p.slots * kTailSlabBytes);
   uint64_t* full_bar = bars;                          // [8] ring slot filled by TMA
@@ -75,13 +80,15 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
   uint64_t* acc2_bar = bars + 34;                     // [2] M2 complete
   uint64_t* afree_bar = bars + 36;                    // [2] e2 has drained the buffer
   uint64_t* bres_bar = bars + 38;                     // resident operands have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 39);
-  float* s_bias1 = reinterpret_cast<float*>(bars + 40);   // [256]
+  uint64_t* turn_bar = bars + 39;                     // [3] group g has taken the slab slot of its current item
+  uint64_t* staged_bar = bars + 42;                   // [8] slab slot staged (e1 and e2): the store warp may send it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
+  float* s_bias1 = reinterpret_cast<float*>(bars + 52);   // [256]
   float* s_bias2 = s_bias1 + kTailN1;                     // [128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = kTailEpiWarps, kTmaWarp = kTailEpiWarps + 1;
+  constexpr int kMmaWarp = kTailEpiWarps, kTmaWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2;
   const int ns2 = p.N2 / kTailSlab;
   const int ipt = 4 + ns2;                                           // epilogue items per tile
   const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -97,6 +104,7 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
         mbar_init(&empty_bar[s], 1);
         mbar_init(&slabw_bar[s], 1);
         mbar_init(&sfree_bar[s], 2);
+        mbar_init(&staged_bar[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&acc1_bar[b], 1);
@@ -104,6 +112,7 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
         mbar_init(&afree_bar[b], 4 * ns2);
       }
       mbar_init(bres_bar, 1);
+      for (int g = 0; g < kTailGroups; ++g) mbar_init(&turn_bar[g], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -128,21 +137,22 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
     const int my_items = my_tiles * ipt;
     int t = grp / ipt, j = grp - t * ipt;                            // tile iteration, item inside the tile
     int slot = grp % p.slots, use = grp / p.slots;                   // slab slot of the item, how often it has been used
-    int prev_slot = -1;
     for (int q = grp; q < my_items; q += kTailGroups) {
       const int buf = t & 1;
       const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
       const bool second = j >= 4;                                    // e2 item
       const int s = second ? j - 4 : j;
-      const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
-      if (leader && prev_slot >= 0) {
-        // the group's previous store has finished reading its slot: first of the slot's two "free" arrivals (for an e2
-        // slot, which no MMA reads, the second one too)
-        tma_store_wait_read<0>();
-        mbar_arrive(&sfree_bar[prev_slot & 15]);
-        if (prev_slot & 16) mbar_arrive(&sfree_bar[prev_slot & 15]);
+      if (leader) {
+        // Slots are taken in item order (item q after item q - 1, whichever groups they belong to): barrier phases are told
+        // apart by parity only, and a group that ran two uses of a slot ahead of another group would take the slot's
+        // phase before last for its own (tools/conv_tail_protocol_sim.py finds that interleaving when groups take slots
+        // independently).  One thread waits for the group: the turn barrier below may be a phase further on by the
+        // time a slower thread would look at it.
+        if (q > 0) mbar_wait(&turn_bar[(grp + kTailGroups - 1) % kTailGroups], static_cast<uint32_t>((q - 1) / kTailGroups) & 1u, p.watchdog, 130 + grp);
+        mbar_wait(&sfree_bar[slot], (static_cast<uint32_t>(use) & 1u) ^ 1u, p.watchdog, 100 + slot);
+        mbar_arrive(&turn_bar[grp]);
       }
-      mbar_wait(&sfree_bar[slot], (static_cast<uint32_t>(use) & 1u) ^ 1u, p.watchdog, 100 + slot);
+      named_bar_sync(1 + grp, 128);
       mbar_wait(second ? &acc2_bar[buf] : &acc1_bar[buf], aph, p.watchdog, second ? 120 + buf : 110 + buf);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTailN1 + s * kTailSlab);
@@ -183,23 +193,52 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
       fence_proxy_async_smem();                // the slab is read by TMA (store) and by the tensor core (M2)
       named_bar_sync(1 + grp, 128);
       if (leader) {
-        if (!second) {
-          mbar_arrive(&slabw_bar[slot]);
-          tma_store_2d(&tmO1, smem_slot + slot * kTailSlabBytes, s * kTailSlab, m0);
-        } else {
-          tma_store_2d(&tmO2, smem_slot + slot * kTailSlabBytes, s * kTailSlab, m0);
-        }
-        tma_store_commit();
-        prev_slot = slot | (second ? 16 : 0);
+        if (!second) mbar_arrive(&slabw_bar[slot]);          // -> M2
+        mbar_arrive(&staged_bar[slot]);                      // -> the store warp
       }
       j += kTailGroups;
       while (j >= ipt) { j -= ipt; ++t; }
       slot += kTailGroups;
       while (slot >= p.slots) { slot -= p.slots; ++use; }
     }
-    if (leader) {
+  } else if (warp == kStoreWarp) {
+    // ================================================================ store warp
+    // One thread sends every staged slab (items in order) and gives the slot back once the store has finished READING it, one
+    // store behind: the epilogue groups never wait for a store to drain (as leaders of their own stores they spent a
+    // store-read latency per item: 1.57 -> ... ms per launch, profiles/r02_layer_times_r50_fuse_ab.txt).
+    if (lane == 0) {
+      const int my_items = my_tiles * ipt;
+      int t = 0, j = 0, slot = 0;
+      uint32_t par = 0;                        // per slot: parity of its uses so far
+      int pend_slot = -1;                      // the store before the last one: slot | 16 for an e2 slot
+      int last_slot = -1;
+      auto give_back = [&](int ps) {
+        // a slot's two "free" arrivals: store drained, M2 retired (an e2 slot is read by no MMA: both from here)
+        mbar_arrive(&sfree_bar[ps & 15]);
+        if (ps & 16) mbar_arrive(&sfree_bar[ps & 15]);
+      };
+      for (int q = 0; q < my_items; ++q) {
+        const bool second = j >= 4;
+        const int s = second ? j - 4 : j;
+        const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
+        mbar_wait(&staged_bar[slot], (par >> slot) & 1u, p.watchdog, 400 + slot);
+        par ^= 1u << slot;
+        tma_store_2d(second ? &tmO2 : &tmO1, smem_slot + slot * kTailSlabBytes, s * kTailSlab, m0);
+        tma_store_commit();
+        pend_slot = last_slot;
+        last_slot = slot | (second ? 16 : 0);
+        if (pend_slot >= 0) {
+          tma_store_wait_read<1>();            // everything but the store just committed has been read
+          give_back(pend_slot);
+        }
+        if (++j == ipt) { j = 0; ++t; }
+        if (++slot == p.slots) slot = 0;
+      }
+      if (last_slot >= 0) {
+        tma_store_wait_read<0>();
+        give_back(last_slot);
+      }
       tma_store_wait<0>();                     // stores must land before the CTA (and its smem) goes away
-      // (nobody waits for the last slots any more: no arrival needed)
     }
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
@@ -237,6 +276,21 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
         __syncwarp();
         if (++stage == p.ring) { stage = 0; phase ^= 1; }
       }
+      if (p.kbx) {
+        // the skip is a 1x1 conv of x: more k-blocks into the same accumulator (fp32, not rounded to 16 bits in between)
+        for (int kb = 0; kb < p.kbx; ++kb) {
+          mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
+          tc_fence_after();
+          if (elect_one()) {
+            mma4(d, ring_lo + static_cast<uint32_t>(stage) * step, id_lo + static_cast<uint32_t>(kb) * ((kTailN1 * 128) >> 4), idesc1, 1u);
+            tc_commit_a(empty0 + stage * 8);
+            if (kb == p.kbx - 1) tc_commit_a(acc10 + buf * 8);
+          }
+          __syncwarp();
+          if (++stage == p.ring) { stage = 0; phase ^= 1; }
+        }
+        return;
+      }
       for (int rs = 0; rs < 4; ++rs) {
         mbar_wait_a(full0 + stage * 8, phase, p.watchdog, 210 + stage);
         tc_fence_after();
@@ -249,17 +303,18 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
         if (++stage == p.ring) { stage = 0; phase ^= 1; }
       }
     };
-    int slot = 0, use = 0;                    // slab slot of the next e1 item M2 consumes
+    int slot = 0;                             // slab slot of the next e1 item M2 consumes
+    uint32_t e1par = 0;                       // per slot: parity of the number of e1 slabs consumed from it ("written" phases
+                                              // count e1 items only; e2 items share the slots but never arrive there)
     auto issue_m2 = [&](int t) {
       const int buf = t & 1;
       const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTailN1);
       for (int s = 0; s < 4; ++s) {
-        mbar_wait_a(slabw0 + slot * 8, static_cast<uint32_t>(use) & 1u, p.watchdog, 230 + slot);
+        mbar_wait_a(slabw0 + slot * 8, (e1par >> slot) & 1u, p.watchdog, 230 + slot);
         if (s == 0 && ns2 == 2) {
           // acc2 of a 128-wide conv1 covers the columns of slabs 0 AND 1: both must have left TMEM
-          int s1 = slot + 1, u1 = use;
-          if (s1 == p.slots) { s1 = 0; ++u1; }
-          mbar_wait_a(slabw0 + s1 * 8, static_cast<uint32_t>(u1) & 1u, p.watchdog, 240 + s1);
+          const int s1 = slot + 1 == p.slots ? 0 : slot + 1;
+          mbar_wait_a(slabw0 + s1 * 8, (e1par >> s1) & 1u, p.watchdog, 240 + s1);
         }
         tc_fence_after();
         if (elect_one()) {
@@ -269,11 +324,12 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
           if (s == 3) tc_commit_a(acc20 + buf * 8);
         }
         __syncwarp();
-        if (++slot == p.slots) { slot = 0; ++use; }
+        e1par ^= 1u << slot;
+        if (++slot == p.slots) slot = 0;
       }
       // the tile's e2 items take the next ns2 slots
       for (int e = 0; e < ns2; ++e)
-        if (++slot == p.slots) { slot = 0; ++use; }
+        if (++slot == p.slots) slot = 0;
     };
     if (my_tiles > 0) issue_g1(0);
     for (int t = 0; t < my_tiles; ++t) {
@@ -286,16 +342,18 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     if (lane == 0) {
       const uint32_t bres = smem_u32(bres_bar);
-      mbar_expect_tx_a(bres, static_cast<uint32_t>(p.kb1 * kTailN1 * 128 + 4 * w1_block + kTailIdentBytes));
+      mbar_expect_tx_a(bres, static_cast<uint32_t>(p.kb1 * kTailN1 * 128 + 4 * w1_block + (p.kbx ? p.kbx * kTailN1 * 128 : kTailIdentBytes)));
       for (int kb = 0; kb < p.kb1; ++kb) tma_load_2d_a(smem_u32(smem_w3) + static_cast<uint32_t>(kb * kTailN1 * 128), &tmW3, bres, kb * kBK, 0);
       for (int s = 0; s < 4; ++s) tma_load_2d_a(smem_u32(smem_w1) + static_cast<uint32_t>(s * w1_block), &tmW1, bres, s * kBK, 0);
-      tma_load_2d_a(smem_u32(smem_i), &tmI, bres, 0, 0);
+      if (p.kbx == 0) tma_load_2d_a(smem_u32(smem_i), &tmI, bres, 0, 0);
+      for (int kb = 0; kb < p.kbx; ++kb) tma_load_2d_a(smem_u32(smem_i) + static_cast<uint32_t>(kb * kTailN1 * 128), &tmI, bres, kb * kBK, 0);
     }
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
-      for (int i = 0; i < p.kb1 + 4; ++i) {
+      const int n_skip = p.kbx ? p.kbx : 4;                          // x blocks, or the four slabs of the skip tensor
+      for (int i = 0; i < p.kb1 + n_skip; ++i) {
         mbar_wait_a(empty0 + stage * 8, phase ^ 1u, p.watchdog, 300 + stage);
         if (elect_one()) {
           mbar_expect_tx_a(full0 + stage * 8, kTailSlabBytes);
@@ -322,13 +380,23 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
 bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1) {
   auto lin = [](const ConvLayer& L) { return L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0 && !L.special; };
   return lin(L3) && lin(L1) && L3.Cout == kTailN1 && L3.Cout_pad == kTailN1 && (L3.Cin == 64 || L3.Cin == 128) && L3.K_pad == L3.Cin &&
-         L1.Cin == kTailN1 && L1.K_pad == kTailN1 && L1.Cout == 64 && L1.Cout_pad == L1.Cout && L3.act_kind == 1 &&
+         L1.Cin == kTailN1 && L1.K_pad == kTailN1 && (L1.Cout == 64 || L1.Cout == 128) && L1.Cout_pad == L1.Cout && L3.act_kind == 1 &&
          L1.act_kind == 1;
 }
 
+// A skip conv that K2t can compute itself: 1x1 / stride 1, 64 or 128 -> 256 channels, linear (the bottleneck's ReLU comes
+// after the add).  Its output then never exists in memory, nor in 16 bits: one rounding fewer than the separate launches.
+bool conv_tail_skip_applicable(const ConvLayer& Ld) {
+  return Ld.kh == 1 && Ld.kw == 1 && Ld.sh == 1 && Ld.sw == 1 && Ld.ph == 0 && Ld.pw == 0 && !Ld.special && Ld.Cout == kTailN1 &&
+         Ld.Cout_pad == kTailN1 && Ld.Cin == 64 && Ld.K_pad == Ld.Cin && Ld.act_kind == 2;
+}
+
+// res: the skip tensor [M, 256], or with Ld != null the INPUT x [M, Ld->Cin] of the skip conv Ld (bias1 = conv3's bias + Ld's)
 int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
-                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream) {
-  if (!conv_tail_applicable(L3, L1)) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: layer pair not supported");
+                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, const ConvLayer* Ld,
+                     const float* bias1, cudaStream_t stream) {
+  if (!conv_tail_applicable(L3, L1) || (Ld != nullptr && (!conv_tail_skip_applicable(*Ld) || bias1 == nullptr)))
+    return set_err(ctx, FRB_ERR_INVALID, "conv_tail: layer pair not supported");
   if (M <= 0 || M > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: bad problem size");
   const void* ptrs[4] = {in, res, out1, out2};
   const int lds[4] = {in_ld, res_ld, out1_ld, out2_ld};
@@ -341,15 +409,22 @@ int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, con
   a.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
   a.kb1 = L3.Cin / kBK;
   a.N2 = L1.Cout;
-  a.bias1 = L3.d_bias;
+  a.kbx = Ld != nullptr ? Ld->Cin / kBK : 0;
+  a.bias1 = Ld != nullptr ? bias1 : L3.d_bias;
   a.bias2 = L1.d_bias;
   a.watchdog = ctx->wd_dev;
-  const int fixed = a.kb1 * kTailN1 * 128 + 4 * a.N2 * 128 + kTailIdentBytes + 40 * 8 + (kTailN1 + 128) * 4 + 1024;
+  const int fixed = a.kb1 * kTailN1 * 128 + 4 * a.N2 * 128 + (a.kbx ? a.kbx * kTailN1 * 128 : kTailIdentBytes) + 52 * 8 +
+                    (kTailN1 + 128) * 4 + 1024;
   const int units = (227 * 1024 - fixed) / kTailSlabBytes;               // 16 KB buffers left for the ring and the slab slots
-  // skip slabs spend one TMA latency in the ring, output slabs an epilogue pass plus a store drain in their slot
-  a.ring = std::min(kTailMaxRing, std::max(3, units - units * 5 / 9));
-  a.slots = std::min(kTailMaxSlots, units - a.ring);
-  if (a.slots < 3) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: shared-memory plan does not fit");
+  // The ring is what hides the HBM latency (a tile's loads: conv3's input and the four skip slabs); the output slabs need
+  // a slot for an epilogue pass plus a store drain.  Measured on one box (profiles/r02_layer_times_r50_fuse_ab.txt), 9 units:
+  // ring 4 / 5 / 6 / 7 = 1.72 / 1.66 / 1.65 / 1.91 ms per launch; 7 units (N2 = 128): ring 3 / 4 / 5 = 2.42 / 2.23 / 2.19 ms.
+  a.slots = units >= 9 ? 4 : 3;
+  if (a.kbx) a.slots = units - 4;                                        // two loads per tile: a short ring is enough
+  a.ring = std::min(kTailMaxRing, units - a.slots);
+  if (const char* e = getenv("FRB_TAIL_RING")) { a.ring = std::max(2, std::min(units - 2, atoi(e))); a.slots = units - a.ring; }   // tuning experiment
+  a.slots = std::min(kTailMaxSlots, a.slots);
+  if (a.ring < 2 || a.slots < 2) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: shared-memory plan does not fit");
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.ring + a.slots) * kTailSlabBytes;
 
   void* ident = nullptr;
@@ -357,12 +432,14 @@ int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, con
   if (rc != FRB_OK) return rc;
   CUtensorMap tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI;
   if ((rc = encode_2d(ctx, &tmA, in, L3.Cin, M, static_cast<uint64_t>(in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
-  if ((rc = encode_2d(ctx, &tmR, res, kTailN1, M, static_cast<uint64_t>(res_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmR, res, Ld != nullptr ? Ld->Cin : kTailN1, M, static_cast<uint64_t>(res_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
   if ((rc = encode_2d(ctx, &tmO1, out1, kTailN1, M, static_cast<uint64_t>(out1_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
   if ((rc = encode_2d(ctx, &tmO2, out2, a.N2, M, static_cast<uint64_t>(out2_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
   if ((rc = encode_2d(ctx, &tmW3, L3.d_w, L3.K_pad, L3.Cout_pad, static_cast<uint64_t>(L3.K_pad) * 2, kBK, kTailN1)) != FRB_OK) return rc;
   if ((rc = encode_2d(ctx, &tmW1, L1.d_w, L1.K_pad, L1.Cout_pad, static_cast<uint64_t>(L1.K_pad) * 2, kBK, a.N2)) != FRB_OK) return rc;
-  if ((rc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64)) != FRB_OK) return rc;
+  if (Ld != nullptr) rc = encode_2d(ctx, &tmI, Ld->d_w, Ld->K_pad, Ld->Cout_pad, static_cast<uint64_t>(Ld->K_pad) * 2, kBK, kTailN1);
+  else rc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64);
+  if (rc != FRB_OK) return rc;
 
   const int grid = std::min(a.m_tiles, ctx->num_sms);
   if (ctx->use_bf16) {

@@ -157,6 +157,8 @@ void conv_release(ConvLayer& L) {
   if (L.d_w) cudaFree(L.d_w);
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_slope) cudaFree(L.d_slope);
+  if (L.d_bias_skip) cudaFree(L.d_bias_skip);
+  L.d_bias_skip = nullptr;
   L.d_w = nullptr;
   L.d_bias = nullptr;
   L.d_slope = nullptr;
@@ -575,8 +577,9 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_FUSE_TAIL:
-      if (ctx->fuse_tail != (value ? 1 : 0)) {
-        ctx->fuse_tail = value ? 1 : 0;
+      if (value < 0 || value > 3) return set_err(ctx, FRB_ERR_INVALID, "fuse_tail must be 0..3");
+      if (ctx->fuse_tail != value) {
+        ctx->fuse_tail = value;
         for (auto& kv : ctx->nets) net_drop_plans(kv.second);     // the op list of a forward changes
       }
       return FRB_OK;

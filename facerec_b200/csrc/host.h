@@ -46,7 +46,7 @@ struct frb_ctx {
   cudaStream_t capture_stream = nullptr;   // graph capture of short forwards happens here, replay on the caller's stream
   int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
-  int fuse_tail = 1;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
+  int fuse_tail = 3;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
@@ -91,6 +91,7 @@ struct ConvLayer {
   void* d_w = nullptr;       // [Cout_pad, K_pad] 16-bit, K-major, K ordered (r, s, c)
   float* d_bias = nullptr;   // [Cout_pad]
   float* d_slope = nullptr;  // [Cout_pad] negative slope per output channel (1 linear, 0 relu)
+  float* d_bias_skip = nullptr;   // [Cout_pad] this layer's bias + the skip conv's (conv3 of a block whose skip conv K2t fuses)
   CUtensorMap tmB;
   CUtensorMap tmB2;          // the same matrix with a box of BN / 2 rows: one CTA's half of a weight block in pair mode
   int has_tmB2 = 0;
@@ -129,9 +130,12 @@ int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bi
 void conv_release(ConvLayer& L);
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
 // conv_tail.cu: y = relu(conv3(in) + res) [M, 256] and y1 = relu(conv1_next(y)) [M, L1.Cout] in one launch (K2t)
+// With Ld != null the skip is Ld's 1x1 conv of `res` (= its input x) computed inside, bias1 = conv3's bias + Ld's.
 bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1);
+bool conv_tail_skip_applicable(const ConvLayer& Ld);
 int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
-                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream);
+                     const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, const ConvLayer* Ld,
+                     const float* bias1, cudaStream_t stream);
 
 // ------------------------------------------------------------------ glue kernels (glue.cu)
 int launch_preprocess_s2d(frb_ctx*, const uint8_t* d_frames, int B, int H, int W, int src_is_rgb, void* d_out, cudaStream_t);

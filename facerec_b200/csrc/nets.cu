@@ -131,7 +131,7 @@ struct View {
 // OP_CONV_TAIL: conv3 + skip (layer) and the next block's conv1 (layer2) in one launch (conv_tail.cu); out2 = conv1's output
 enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4, OP_CONV_TAIL = 5 };
 struct Op {
-  int kind = 0, layer = -1, layer2 = -1;
+  int kind = 0, layer = -1, layer2 = -1, layer3 = -1;   // layer3: skip conv computed inside OP_CONV_TAIL (res = its input)
   View in, out, res, out2;
   int res_mode = 0, out_mode = 0, pad = 0, C = 0, P_off = 0;
 };
@@ -275,6 +275,21 @@ static void load_retina(Net* net, const WeightBlob& blob, bool r50) {
         add_plain(net, blob, p + ".conv2", 0.f, s, s, 1, 1);
         add_plain(net, blob, p + ".conv3", 0.f, 1, 1, 0, 0, 0, 1.f, res_bn_cap(kR50Planes[l]));   // ReLU after the residual add
         if (i == 0) add_plain(net, blob, p + ".down", 1.f, s, s, 0, 0);
+        if (i == 0) {
+          // where K2t can compute the skip conv itself (layer1.0: stride 1), conv3 gets the sum of the two biases
+          ConvLayer& L3 = net->convs[net->conv_idx[p + ".conv3"]];
+          const ConvLayer& Ld = net->convs[net->conv_idx[p + ".down"]];
+          if (conv_tail_skip_applicable(Ld) && L3.Cout_pad == Ld.Cout_pad) {
+            std::vector<float> b3(L3.Cout_pad), bd(Ld.Cout_pad);
+            if (cudaMemcpy(b3.data(), L3.d_bias, b3.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(bd.data(), Ld.d_bias, bd.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+              throw std::runtime_error("bias read-back failed");
+            for (size_t c = 0; c < b3.size(); ++c) b3[c] += bd[c];
+            if (cudaMalloc(&L3.d_bias_skip, b3.size() * 4) != cudaSuccess ||
+                cudaMemcpy(L3.d_bias_skip, b3.data(), b3.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+              throw std::runtime_error("cudaMalloc failed for the fused skip bias");
+          }
+        }
       }
   } else {
     add_plain(net, blob, "body.0", 0.1f, 2, 2, 1, 1, 8);
@@ -438,9 +453,11 @@ struct Builder {
     touch(in); touch(out); touch(res);
     plan->ops.push_back(op);
   }
-  void conv_tail(const std::string& name3, const std::string& name1, View in, View res, View out, View out2) {
+  void conv_tail(const std::string& name3, const std::string& name1, View in, View res, View out, View out2,
+                 const std::string& skip_conv = std::string()) {
     Op op;
     op.kind = OP_CONV_TAIL; op.layer = layer(name3); op.layer2 = layer(name1); op.in = in; op.res = res; op.out = out; op.out2 = out2;
+    if (!skip_conv.empty()) op.layer3 = layer(skip_conv);
     op.res_mode = RES_PRE_ACT;
     touch(in); touch(res); touch(out); touch(out2);
     plan->ops.push_back(op);
@@ -506,18 +523,24 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
         y1_fused = -1;
         const int y2 = b.tensor(ho, wo, planes);
         b.conv(p + ".conv2", V(y1), V(y2));
+        const bool last = i + 1 == kR50Blocks[l];
+        const std::string pn = last ? sfmt("layer%d.0", l + 2) : sfmt("layer%d.%d", l + 1, i + 1);
+        const bool fuse = net->ctx->fuse_tail && !(last && l == 3) && !(net->ctx->fuse_tail == 2 && last) &&
+                          conv_tail_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")]);
+        // FRB_OPT_FUSE_TAIL = 3: the skip conv of the layer's first block is computed inside the fused tail as well
+        const bool fuse_skip = fuse && i == 0 && net->ctx->fuse_tail == 3 && net->convs[b.layer(p + ".conv3")].d_bias_skip != nullptr &&
+                               conv_tail_skip_applicable(net->convs[b.layer(p + ".down")]);
         int idn = x;
-        if (i == 0) {
+        if (i == 0 && !fuse_skip) {
           idn = b.tensor(ho, wo, planes * 4);
           b.conv(p + ".down", V(x), V(idn));
         }
         const int y = b.tensor(ho, wo, planes * 4);
-        // conv3 + skip together with the next block's conv1 (same layer: stride 1, same planes) where K2t takes the pair
-        const std::string pn = sfmt("layer%d.%d", l + 1, i + 1);
-        if (net->ctx->fuse_tail && i + 1 < kR50Blocks[l] &&
-            conv_tail_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")])) {
-          y1_fused = b.tensor(ho, wo, planes);
-          b.conv_tail(p + ".conv3", pn + ".conv1", V(y2), V(idn), V(y), V(y1_fused));
+        // conv3 + skip together with the next block's conv1 (always 1x1 / stride 1: the stride of a layer's first block
+        // sits in its 3x3) where K2t takes the pair
+        if (fuse) {
+          y1_fused = b.tensor(ho, wo, net->convs[b.layer(pn + ".conv1")].Cout);
+          b.conv_tail(p + ".conv3", pn + ".conv1", V(y2), V(idn), V(y), V(y1_fused), fuse_skip ? p + ".down" : std::string());
         } else {
           b.conv(p + ".conv3", V(y2), V(y), RES_PRE_ACT, V(idn));
         }
@@ -772,7 +795,8 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
         const TensorInfo& tr = plan.tensors[op.res.t];
         rc = conv_tail_launch(ctx, net->convs[op.layer], net->convs[op.layer2], base(op.in), ti.C,
                               static_cast<long long>(plan.B) * ti.H * ti.W, base(op.res), tr.C, base(op.out),
-                              plan.tensors[op.out.t].C, base(op.out2), plan.tensors[op.out2.t].C, st);
+                              plan.tensors[op.out.t].C, base(op.out2), plan.tensors[op.out2.t].C,
+                              op.layer3 >= 0 ? &net->convs[op.layer3] : nullptr, net->convs[op.layer].d_bias_skip, st);
         break;
       }
       case OP_DW: {
@@ -806,7 +830,8 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
         const ConvLayer& L1 = net->convs[op.layer2];
         M = static_cast<double>(plan.B) * ti.H * ti.W;
         N = L3.Cout + L1.Cout;
-        K = (static_cast<double>(L3.Cout) * L3.Cin + static_cast<double>(L1.Cout) * L1.Cin) / N;
+        K = (static_cast<double>(L3.Cout) * (L3.Cin + (op.layer3 >= 0 ? net->convs[op.layer3].Cin : 0)) +
+             static_cast<double>(L1.Cout) * L1.Cin) / N;
       } else {
         M = static_cast<double>(plan.B) * ti.H * ti.W;
         N = ti.C;

@@ -66,9 +66,11 @@ enum frb_option {
                            /* 0 never, 1 (default) for N tiles of 192 and more, 2 wherever possible                  */
   FRB_OPT_CTA2 = 14,       /* 0: never run conv CTAs as pairs (default 1: convs on the per-tap / linear path with streamed weights   */
                            /* use cta_group::2 - M = 256 MMAs over the two SMs of a TPC, each CTA loading half of the weight block)  */
-  FRB_OPT_FUSE_TAIL = 15,  /* 0: every conv of ResNet-50 is a launch of its own (default 1: in layer1 a bottleneck's conv3 + skip   */
-                           /* and the next bottleneck's conv1 run as ONE launch that never re-reads the 256-channel tensor;          */
-                           /* the outputs are the same bits either way)                                                             */
+  FRB_OPT_FUSE_TAIL = 15,  /* 0: every conv of ResNet-50 is a launch of its own; 1: in layer1 a bottleneck's conv3 + skip and the   */
+                           /* next bottleneck's conv1 run as ONE launch that never re-reads the 256-channel tensor (same bits as 0);  */
+                           /* 2: as 1, but not across the layer1 -> layer2 edge; 3 (default): as 1, and the 1x1 skip conv of          */
+                           /* layer1's first block is computed inside that launch too (its output is never rounded to 16 bits, so     */
+                           /* results differ from 0 by that one rounding)                                                           */
   FRB_OPT_GRAPHS = 13      /* 1: short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 up to 64 x 360p) are captured once per  */
                            /* shape into a CUDA graph and replayed.  Default 0: measured SLOWER than stream launches with         */
                            /* programmatic dependent launch (the kernels are GPU-bound at 10-35 us, and a replayed graph loses    */

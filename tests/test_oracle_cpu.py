@@ -342,3 +342,13 @@ def test_checkpoint_converter_folds_public_state_dicts(model, tmp_path):
     np.savez(str(tmp_path / "bad.npz"), **bad)
     with pytest.raises(ValueError):
         convert.load_weights(str(tmp_path / "bad.npz"), model)
+
+
+def test_conv_tail_barrier_protocol_has_no_deadlock_or_parity_aliasing():
+    """The barrier protocol of conv_tail_kernel (fused bottleneck tail) replayed under random interleavings: the shipped
+    protocol passes every configuration; without in-order slot taking the model finds the parity aliasing that hung the
+    first GPU version (so the model is able to see that class of bug)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import conv_tail_protocol_sim as sim
+    assert sim.sweep(in_order=True, seeds=15) == []
+    assert any("aliased" in str(d) or "deadlock" in str(d) for _, d in sim.sweep(in_order=False, seeds=15))

@@ -1,0 +1,231 @@
+"""Barrier-protocol model of conv_tail_kernel (facerec_b200/csrc/conv_tail.cu), one CTA, no GPU needed.
+
+The kernel's six roles (three epilogue groups, the MMA issuer, the TMA producer, the store warp) talk through mbarriers whose waits tell
+phases apart BY PARITY ONLY: a waiter that gets two phases ahead of a barrier takes the phase before last for its own and
+either corrupts a buffer or hangs.  This script replays the protocol under random interleavings of the roles and of the
+asynchronous completions (TMA loads, tcgen05.commit arrivals, store drains) and checks at every wait that the barrier is
+in exactly the phase the waiter means, and that nothing deadlocks.  It found the two bugs of the first version
+(groups taking slab slots independently; e2 items sharing the "slab written" phases of a slot) that only showed on the GPU
+with more than one tile per CTA and 4 slots.
+
+    python tools/conv_tail_protocol_sim.py            # the shipped protocol over a grid of (N2/64, slots, ring, tiles)
+    python tools/conv_tail_protocol_sim.py --no-turn  # without in-order slot taking: reports the aliasing
+"""
+from __future__ import annotations
+
+import random
+import sys
+
+
+class Bar:
+    """mbarrier: `count` arrivals complete a phase; test(parity) is mbarrier.test_wait.parity."""
+
+    def __init__(self, count):
+        self.count = count
+        self.pending = count
+        self.phase = 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0
+        if self.pending == 0:
+            self.pending = self.count
+            self.phase += 1
+
+    def test(self, parity):
+        return (self.phase & 1) != parity
+
+
+class ProtocolError(Exception):
+    pass
+
+
+def run(my_tiles, ns2, slots, ring, kb1=1, groups=3, seed=0, in_order=True, lag=1, nskip=4):
+    """Returns (ok, detail).  ns2 = N2 / 64 (e2 items per tile); slots / ring as in ConvTailArgs."""
+    rnd = random.Random(seed)
+    ipt = 4 + ns2
+    full = [Bar(1) for _ in range(8)]
+    empty = [Bar(1) for _ in range(8)]
+    slabw = [Bar(1) for _ in range(8)]
+    sfree = [Bar(2) for _ in range(8)]
+    swr = [Bar(1) for _ in range(8)]
+    turn = [Bar(1) for _ in range(groups)]
+    acc1, acc2 = [Bar(1), Bar(1)], [Bar(1), Bar(1)]
+    afree = [Bar(4 * ns2), Bar(4 * ns2)]
+    pending = []                               # asynchronous completions, in issue order
+
+    def later(fn):
+        pending.append(fn)
+
+    def check(cond, *what):
+        if not cond:
+            raise ProtocolError(what)
+
+    def epilogue(g):
+        q = g
+        while q < my_tiles * ipt:
+            t, j = divmod(q, ipt)
+            slot, use, buf, aph = q % slots, q // slots, t & 1, (t >> 1) & 1
+            second = j >= 4
+            if in_order and q >= 1:
+                pg, pn = (g + groups - 1) % groups, (q - 1) // groups
+                while not turn[pg].test(pn & 1):
+                    yield ("turn", pg, q)
+                check(turn[pg].phase == pn + 1, "turn barrier aliased", q)
+            while not sfree[slot].test((use & 1) ^ 1):
+                yield ("slot free", slot, q)
+            check(sfree[slot].phase == use, "slot-free barrier aliased", q, slot, use, sfree[slot].phase)
+            if in_order:
+                turn[g].arrive()
+            b = acc2[buf] if second else acc1[buf]
+            while not b.test(aph):
+                yield ("accumulator", buf, q)
+            check(b.phase == (t >> 1) + 1, "accumulator barrier aliased", q)
+            if second:
+                for _ in range(4):
+                    afree[buf].arrive()
+            yield ("work", q)
+            if not second:
+                slabw[slot].arrive()
+            swr[slot].arrive()
+            q += groups
+
+    def storer():
+        """The store warp: items in order; TMA store of a written slab, the slot's "free" arrival(s) once the store has
+        drained, at most `lag` stores behind."""
+        inflight = []
+        for q in range(my_tiles * ipt):
+            slot, use, second = q % slots, q // slots, (q % ipt) >= 4
+            while not swr[slot].test(use & 1):
+                yield ("slab staged", slot, q)
+            check(swr[slot].phase == use + 1, "slab-staged barrier aliased", q)
+            done = [False]
+            later(lambda d=done: d.__setitem__(0, True))
+            inflight.append((slot, second, done))
+            while len(inflight) > lag:
+                pslot, psecond, pdone = inflight.pop(0)
+                while not pdone[0]:
+                    yield ("store drain", pslot)
+                sfree[pslot].arrive()
+                if psecond:
+                    sfree[pslot].arrive()
+        for pslot, psecond, pdone in inflight:
+            while not pdone[0]:
+                yield ("store drain", pslot)
+            sfree[pslot].arrive()
+            if psecond:
+                sfree[pslot].arrive()
+
+    def issuer():
+        st = {"stage": 0, "phase": 0, "slot": 0}
+        e1n = [0] * 8                          # e1 slabs consumed per slot
+
+        def g1(t):
+            buf = t & 1
+            while not afree[buf].test(((t >> 1) & 1) ^ 1):
+                yield ("buffer free", buf, t)
+            check(afree[buf].phase == (t >> 1), "buffer-free barrier aliased", t)
+            for i in range(kb1 + nskip):
+                s = st["stage"]
+                while not full[s].test(st["phase"]):
+                    yield ("ring full", s)
+                later(lambda s=s: empty[s].arrive())
+                if i == kb1 + nskip - 1:
+                    later(lambda b=buf: acc1[b].arrive())
+                st["stage"] += 1
+                if st["stage"] == ring:
+                    st["stage"], st["phase"] = 0, st["phase"] ^ 1
+
+        def m2(t):
+            buf = t & 1
+            for s in range(4):
+                x = st["slot"]
+                while not slabw[x].test(e1n[x] & 1):
+                    yield ("slab written", x, t, s)
+                check(slabw[x].phase == e1n[x] + 1, "slab-written barrier aliased", t, s)
+                if s == 0 and ns2 == 2:
+                    x1 = 0 if x + 1 == slots else x + 1
+                    while not slabw[x1].test(e1n[x1] & 1):
+                        yield ("slab written", x1, t, 1)
+                    check(slabw[x1].phase == e1n[x1] + 1, "slab-written barrier aliased", t, 1)
+                later(lambda x=x: sfree[x].arrive())
+                if s == 3:
+                    later(lambda b=buf: acc2[b].arrive())
+                e1n[x] += 1
+                st["slot"] = 0 if x + 1 == slots else x + 1
+            for _ in range(ns2):
+                st["slot"] = 0 if st["slot"] + 1 == slots else st["slot"] + 1
+
+        if my_tiles > 0:
+            yield from g1(0)
+        for t in range(my_tiles):
+            if t + 1 < my_tiles:
+                yield from g1(t + 1)
+            yield from m2(t)
+
+    def producer():
+        stage = phase = 0
+        for _ in range(my_tiles):
+            for _ in range(kb1 + nskip):
+                while not empty[stage].test(phase ^ 1):
+                    yield ("ring empty", stage)
+                later(lambda s=stage: full[s].arrive())
+                stage += 1
+                if stage == ring:
+                    stage, phase = 0, phase ^ 1
+
+    agents = {f"epilogue {g}": epilogue(g) for g in range(groups)}
+    agents["issuer"] = issuer()
+    agents["store warp"] = storer()
+    agents["producer"] = producer()
+    state, idle = {}, 0
+    try:
+        while agents:
+            progressed = False
+            names = list(agents)
+            rnd.shuffle(names)
+            for n in names:
+                try:
+                    w = next(agents[n])
+                    if state.get(n) != w or w[0] == "work":
+                        progressed = True
+                    state[n] = w
+                except StopIteration:
+                    del agents[n]
+                    state.pop(n, None)
+                    progressed = True
+            if pending:
+                k = rnd.randint(1, len(pending))
+                for fn in pending[:k]:
+                    fn()
+                del pending[:k]
+                progressed = True
+            idle = 0 if progressed else idle + 1
+            if idle > 3:
+                return False, ("deadlock", dict(state))
+    except ProtocolError as e:
+        return False, e.args[0]
+    return True, None
+
+
+CONFIGS = ((2, 2, 5), (1, 2, 7), (1, 5, 4), (1, 6, 3), (1, 3, 3), (1, 4, 5), (1, 8, 8), (2, 4, 3), (2, 3, 3), (2, 5, 3), (2, 6, 3), (2, 7, 3), (2, 8, 4))
+
+
+def sweep(in_order=True, seeds=40, tiles=(1, 2, 3, 5, 12, 57)):
+    failures = []
+    for ns2, slots, ring in CONFIGS:
+        for n in tiles:
+            for seed in range(seeds):
+                ok, detail = run(n, ns2, slots, ring, seed=seed, in_order=in_order, lag=min(seed % 3, slots - 1), nskip=4 if seed % 2 else 1)
+                if not ok:
+                    failures.append(((ns2, slots, ring, n, seed), detail))
+                    break
+    return failures
+
+
+if __name__ == "__main__":
+    bad = sweep(in_order="--no-turn" not in sys.argv)
+    for cfg, detail in bad:
+        print("FAIL (N2/64, slots, ring, tiles, seed) =", cfg, detail)
+    print(f"{len(bad)} failing configurations")
+    sys.exit(1 if bad else 0)
