@@ -39,6 +39,7 @@ FRB_OPT_MPAIR = 12
 FRB_OPT_GRAPHS = 13
 FRB_OPT_CTA2 = 14
 FRB_OPT_FUSE_TAIL = 15
+FRB_OPT_FUSE_DWPW = 16
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 

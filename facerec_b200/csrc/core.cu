@@ -576,6 +576,13 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_FUSE_DWPW:
+      if (value < 0 || value > 2) return set_err(ctx, FRB_ERR_INVALID, "fuse_dwpw must be 0, 1 or 2");
+      if (ctx->fuse_dwpw != value) {
+        ctx->fuse_dwpw = value;
+        for (auto& kv : ctx->nets) net_drop_plans(kv.second);
+      }
+      return FRB_OK;
     case FRB_OPT_FUSE_TAIL:
       if (value < 0 || value > 3) return set_err(ctx, FRB_ERR_INVALID, "fuse_tail must be 0..3");
       if (ctx->fuse_tail != value) {

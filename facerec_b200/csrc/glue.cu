@@ -207,15 +207,16 @@ __global__ void __launch_bounds__(256) conv3x3_c3_direct_kernel(const uint4* __r
     s_w[i] = f;
   }
   __syncthreads();
+  // 32-bit index arithmetic (the launcher rejects problems of 2^31 items and more): 64-bit divisions cost ~100 instructions
+  // each and were most of this kernel's and the depthwise kernel's time
   const int cg = Cout >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % cg);
-    long long t = i / cg;
-    const int ow = static_cast<int>(t % Wo); t /= Wo;
-    const int oh = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+  const int total = B * Ho * Wo * cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    int t = i / cg;
+    const int ow = t % Wo; t /= Wo;
+    const int oh = t % Ho;
+    const int b = t / Ho;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) conv3x3_c3_direct_kernel(const uint4* __r
       for (int sx = 0; sx < 3; ++sx) {
         const int iw = ow * stride - pad + sx;
         if (static_cast<unsigned>(iw) >= static_cast<unsigned>(W)) continue;
-        const uint4 v = __ldg(in + (static_cast<long long>(b) * H + ih) * W + iw);
+        const uint4 v = __ldg(in + (b * H + ih) * W + iw);
         const float2 x01 = H16<kBF16>::up(v.x);
         const float x2 = H16<kBF16>::up(v.y).x;
         const float* wt = s_w + (g * 8) * 27 + (r * 3 + sx) * 3;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256) conv3x3_c3_direct_kernel(const uint4* __r
       const float y = acc[j] + __ldg(bias + g * 8 + j);
       acc[j] = fmaf(__ldg(slope + g * 8 + j), fminf(y, 0.f), fmaxf(y, 0.f));     // leaky: slope 0 = ReLU, 1 = linear
     }
-    out[((static_cast<long long>(b) * Ho + oh) * Wo + ow) * out_c8 + g] = pack8<kBF16>(acc);
+    out[static_cast<size_t>((b * Ho + oh) * Wo + ow) * out_c8 + g] = pack8<kBF16>(acc);
   }
 }
 
@@ -253,6 +254,7 @@ int launch_conv3x3_c3_direct(frb_ctx* ctx, const void* in, int B, int H, int W, 
   if (Cout % 8 || out_ld % 8 || Cout > 64) return set_err(ctx, FRB_ERR_INVALID, "direct conv: Cout must be a multiple of 8, at most 64");
   const int Ho = conv_out_dim(H, 3, stride, pad), Wo = conv_out_dim(W, 3, stride, pad);
   const long long total = static_cast<long long>(B) * Ho * Wo * (Cout / 8);
+  if (total > 0x7fffffffLL - (1 << 22) || static_cast<long long>(B) * H * W > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "direct conv: problem too large");
   const int grid = grid_for(total, 256, ctx->num_sms);
   const size_t smem = static_cast<size_t>(Cout) * 27 * 4;
   if (ctx->use_bf16)
@@ -275,32 +277,40 @@ __global__ void dwconv3x3_kernel(const uint4* __restrict__ in, int B, int H, int
                                  const float* __restrict__ w, const float* __restrict__ bias, int act, float slope,
                                  uint4* __restrict__ out) {
   const int cg = C >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * cg;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % cg);
-    long long t = i / cg;
-    const int ow = static_cast<int>(t % Wo); t /= Wo;
-    const int oh = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+  const int total = B * Ho * Wo * cg;                  // 32-bit index arithmetic, see K3
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    int t = i / cg;
+    const int ow = t % Wo; t /= Wo;
+    const int oh = t % Ho;
+    const int b = t / Ho;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + g * 8 + j);
+    // nine independent loads in flight per thread (a tap outside the image reads a clamped address and counts as zero)
+    uint4 v[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * stride - 1 + r;
-      if (static_cast<unsigned>(ih) >= static_cast<unsigned>(H)) continue;
+      const int ihc = min(max(ih, 0), H - 1);
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int iw = ow * stride - 1 + s;
-        if (static_cast<unsigned>(iw) >= static_cast<unsigned>(W)) continue;
-        const uint4 v = __ldg(in + (static_cast<long long>(b) * H * W + static_cast<long long>(ih) * W + iw) * cg + g);
-        float x[8];
-        unpack8<kBF16>(v, x);
-        const float* wt = w + (r * 3 + s) * C + g * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], __ldg(wt + j), acc[j]);
+        const int iwc = min(max(iw, 0), W - 1);
+        const uint4 t4 = __ldg(in + static_cast<size_t>((b * H + ihc) * W + iwc) * cg + g);
+        v[r * 3 + s] = (ih == ihc && iw == iwc) ? t4 : make_uint4(0, 0, 0, 0);
       }
+    }
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      float x[8];
+      unpack8<kBF16>(v[tp], x);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + tp * C + g * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + tp * C + g * 8 + 4));
+      acc[0] = fmaf(x[0], w0.x, acc[0]); acc[1] = fmaf(x[1], w0.y, acc[1]);
+      acc[2] = fmaf(x[2], w0.z, acc[2]); acc[3] = fmaf(x[3], w0.w, acc[3]);
+      acc[4] = fmaf(x[4], w1.x, acc[4]); acc[5] = fmaf(x[5], w1.y, acc[5]);
+      acc[6] = fmaf(x[6], w1.z, acc[6]); acc[7] = fmaf(x[7], w1.w, acc[7]);
     }
     if (act == 1) {
 #pragma unroll
@@ -318,6 +328,7 @@ int launch_dwconv3x3(frb_ctx* ctx, const void* in, int B, int H, int W, int C, i
   if (C % 8) return set_err(ctx, FRB_ERR_INVALID, "dwconv: C=%d must be a multiple of 8", C);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  if (total > 0x7fffffffLL - (1 << 22) || static_cast<long long>(B) * H * W > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "dwconv: problem too large");
   const int grid = grid_for(total, 256, ctx->num_sms);
   if (ctx->use_bf16)
     dwconv3x3_kernel<true><<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), B, H, W, C, stride, Ho, Wo,
@@ -327,6 +338,181 @@ int launch_dwconv3x3(frb_ctx* ctx, const void* in, int B, int H, int W, int C, i
                                                   static_cast<const float*>(d_w9c), d_bias, act, slope, static_cast<uint4*>(out));
   ctx->launches++;
   return check_last(ctx, "dwconv3x3_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ K4f
+// MobileNet block in one launch: depthwise 3x3 (pad 1, stride 1|2) + bias + LeakyReLU, then the pointwise 1x1 conv + bias +
+// per-channel LeakyReLU, NHWC 16-bit in and out.  The depthwise output never goes to memory: a block computes it for a tile
+// of 128 output pixels on the CUDA cores (fp32, rounded to 16 bits exactly like the separate kernel's output) into a
+// padded shared-memory tile, which is the A operand of the pointwise GEMM; the pointwise weights stay in shared memory for
+// the whole (persistent) block.  These GEMMs are tiny (K = 8 ... 128, 128 pixels per tile) and the block is HBM-bound
+// either way, so the GEMM runs on warp-level mma.sync (m16n8k16, fp32 accumulate) straight from ldmatrix fragments:
+// no TMA / TMEM set-up per tile, 8 warps x 16 pixels, output channels in chunks of 64.  Separate launches spent 0.21 ms
+// on body.1 at 64 x 360p (dw 0.086 + pw 0.123: a 128 x 16 x 8 GEMM per tcgen05 tile) against 0.03 ms of HBM time.
+constexpr int kDwpwTile = 128;       // output pixels per tile (8 warps x one m16 tile)
+constexpr int kDwpwThreads = 256;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+template <bool kBF16>
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  if constexpr (kBF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kDwpwThreads) dwpw_fused_kernel(
+    const uint4* __restrict__ in, int B, int H, int W, int C, int stride, int Ho, int Wo, const float* __restrict__ dw_w,
+    const float* __restrict__ dw_bias, float dw_slope, const uint16_t* __restrict__ pw_w, int K_pad, int Cout,
+    const float* __restrict__ pw_bias, const float* __restrict__ pw_slope, uint16_t* __restrict__ out, int out_ld) {
+  extern __shared__ __align__(16) uint8_t dwpw_smem[];
+  const int Kc = C < 16 ? 16 : C;                      // GEMM K (a k16 step needs 16 columns: C = 8 is zero-padded)
+  const int lda = Kc * 2 + 16;                         // bytes per tile / weight row: 16-byte pad = conflict-free ldmatrix
+  uint8_t* s_a = dwpw_smem;                            // [128][lda]   depthwise output, 16-bit
+  uint8_t* s_w = s_a + kDwpwTile * lda;                // [Cout][lda]  pointwise weights
+  float* s_dw = reinterpret_cast<float*>(s_w + Cout * lda);   // [9][C] depthwise weights, then [C] bias
+  float* s_dwb = s_dw + 9 * C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cg = C >> 3;
+
+  for (int i = tid; i < Cout * (Kc >> 3); i += kDwpwThreads) {
+    const int n = i / (Kc >> 3), k8 = i - n * (Kc >> 3);
+    *reinterpret_cast<uint4*>(s_w + n * lda + k8 * 16) = __ldg(reinterpret_cast<const uint4*>(pw_w + static_cast<size_t>(n) * K_pad + k8 * 8));
+  }
+  for (int i = tid; i < 10 * C; i += kDwpwThreads) s_dw[i] = i < 9 * C ? __ldg(dw_w + i) : __ldg(dw_bias + i - 9 * C);
+  if (C < 16)                                          // columns 8..15 of the A tile stay zero
+    for (int i = tid; i < kDwpwTile; i += kDwpwThreads) *reinterpret_cast<uint4*>(s_a + i * lda + 16) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const int M = B * Ho * Wo;                           // 32-bit index arithmetic, see K3
+  const int tiles = (M + kDwpwTile - 1) / kDwpwTile;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int m0 = tile * kDwpwTile;
+    // ---- depthwise 3x3 of the tile's pixels: one (pixel, 8-channel group) item per thread and pass
+    for (int i = tid; i < kDwpwTile * cg; i += kDwpwThreads) {
+      const int px = i / cg, g = i - px * cg;
+      const int m = m0 + px;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      if (m < M) {
+        const int ow = m % Wo;
+        const int t = m / Wo;
+        const int oh = t % Ho;
+        const int b = t / Ho;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = s_dwb[g * 8 + j];
+        // all nine taps are loaded before the first is used (branch-free: a tap outside the image reads a clamped address and
+        // is replaced by zero), so a thread has nine loads in flight instead of one
+        uint4 v[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int ih = oh * stride - 1 + r;
+          const int ihc = min(max(ih, 0), H - 1);
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx) {
+            const int iw = ow * stride - 1 + sx;
+            const int iwc = min(max(iw, 0), W - 1);
+            const uint4 t4 = __ldg(in + static_cast<size_t>((b * H + ihc) * W + iwc) * cg + g);
+            const bool ok = ih == ihc && iw == iwc;
+            v[r * 3 + sx] = ok ? t4 : make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          float x[8];
+          unpack8<kBF16>(v[tp], x);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_dw + tp * C + g * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_dw + tp * C + g * 8 + 4);
+          acc[0] = fmaf(x[0], w0.x, acc[0]); acc[1] = fmaf(x[1], w0.y, acc[1]);
+          acc[2] = fmaf(x[2], w0.z, acc[2]); acc[3] = fmaf(x[3], w0.w, acc[3]);
+          acc[4] = fmaf(x[4], w1.x, acc[4]); acc[5] = fmaf(x[5], w1.y, acc[5]);
+          acc[6] = fmaf(x[6], w1.z, acc[6]); acc[7] = fmaf(x[7], w1.w, acc[7]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * dw_slope;
+      }
+      *reinterpret_cast<uint4*>(s_a + px * lda + g * 16) = pack8<kBF16>(acc);
+    }
+    __syncthreads();
+    // ---- pointwise GEMM: warp w owns pixels [16 w, 16 w + 16), output channels in chunks of 64
+    const uint32_t a_base = smem_u32(s_a) + static_cast<uint32_t>((warp * 16 + (lane & 15)) * lda + (lane >> 4) * 16);
+    const int grow = lane >> 2, qc = lane & 3;
+    const int mr0 = m0 + warp * 16 + grow, mr1 = mr0 + 8;
+    for (int n0 = 0; n0 < Cout; n0 += 64) {
+      const int nt = min(8, (Cout - n0) >> 3);         // 8-column n tiles in this chunk
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+      // B fragments of two n tiles per ldmatrix.x4: lanes 0-7 rows n..n+7 at k, 8-15 the same rows at k + 8, 16-31 the next n tile
+      const uint32_t b_base = smem_u32(s_w) + static_cast<uint32_t>((n0 + (lane & 7) + ((lane >> 4) << 3)) * lda + ((lane >> 3) & 1) * 16);
+      for (int k = 0; k < Kc; k += 16) {
+        uint32_t a[4];
+        ldmatrix_x4(a_base + k * 2, a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          if (j < nt) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b_base + static_cast<uint32_t>(j * 8 * lda + k * 2), b0, b1, b2, b3);
+            mma_16816<kBF16>(acc[j], a, b0, b1);
+            if (j + 1 < nt) mma_16816<kBF16>(acc[j + 1], a, b2, b3);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nt) {
+          const int col = n0 + j * 8 + qc * 2;
+          const float bi0 = __ldg(pw_bias + col), bi1 = __ldg(pw_bias + col + 1);
+          const float sl0 = __ldg(pw_slope + col), sl1 = __ldg(pw_slope + col + 1);
+          float y0 = acc[j][0] + bi0, y1 = acc[j][1] + bi1, y2 = acc[j][2] + bi0, y3 = acc[j][3] + bi1;
+          y0 = fmaf(sl0, fminf(y0, 0.f), fmaxf(y0, 0.f)); y1 = fmaf(sl1, fminf(y1, 0.f), fmaxf(y1, 0.f));
+          y2 = fmaf(sl0, fminf(y2, 0.f), fmaxf(y2, 0.f)); y3 = fmaf(sl1, fminf(y3, 0.f), fmaxf(y3, 0.f));
+          if (mr0 < M) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(mr0) * out_ld + col) = H16<kBF16>::down(y0, y1);
+          if (mr1 < M) *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(mr1) * out_ld + col) = H16<kBF16>::down(y2, y3);
+        }
+      }
+    }
+    __syncthreads();                                   // the A tile is rewritten by the next tile's depthwise pass
+  }
+}
+
+size_t dwpw_smem_bytes(int C, int Cout) {
+  const int Kc = C < 16 ? 16 : C;
+  return static_cast<size_t>(kDwpwTile + Cout) * (Kc * 2 + 16) + static_cast<size_t>(10) * C * 4;
+}
+
+bool dwpw_fusable(int C, int Cout) {
+  return C % 8 == 0 && (C >= 16 ? C % 16 == 0 : C == 8) && Cout % 16 == 0 && C <= 256 && Cout <= 256 && dwpw_smem_bytes(C, Cout) <= 120 * 1024;
+}
+
+int launch_dwpw_fused(frb_ctx* ctx, const void* in, int B, int H, int W, int C, int stride, const void* d_dw_w9c,
+                      const float* d_dw_bias, float dw_slope, const void* d_pw_w16, int K_pad, int Cout, const float* d_pw_bias,
+                      const float* d_pw_slope, void* out, int out_ld, cudaStream_t st) {
+  if (!dwpw_fusable(C, Cout) || out_ld % 2) return set_err(ctx, FRB_ERR_INVALID, "dwpw: C=%d Cout=%d not supported", C, Cout);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  if (static_cast<long long>(B) * H * W > 0x7fffffffLL - (1 << 22)) return set_err(ctx, FRB_ERR_INVALID, "dwpw: problem too large");
+  const long long tiles = (static_cast<long long>(B) * Ho * Wo + kDwpwTile - 1) / kDwpwTile;
+  const size_t smem = dwpw_smem_bytes(C, Cout);
+  const int per_sm = std::max(1, std::min(4, static_cast<int>((200 * 1024) / (smem + 1024))));
+  const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(ctx->num_sms) * per_sm));
+  auto launch = [&](auto kernel) -> int {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<grid, kDwpwThreads, smem, st>>>(static_cast<const uint4*>(in), B, H, W, C, stride, Ho, Wo,
+                                             static_cast<const float*>(d_dw_w9c), d_dw_bias, dw_slope,
+                                             static_cast<const uint16_t*>(d_pw_w16), K_pad, Cout, d_pw_bias, d_pw_slope,
+                                             static_cast<uint16_t*>(out), out_ld);
+    return FRB_OK;
+  };
+  const int rc = ctx->use_bf16 ? launch(dwpw_fused_kernel<true>) : launch(dwpw_fused_kernel<false>);
+  if (rc != FRB_OK) return rc;
+  ctx->launches++;
+  return check_last(ctx, "dwpw_fused_kernel");
 }
 
 // ------------------------------------------------------------------------------------------ K9

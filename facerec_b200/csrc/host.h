@@ -47,6 +47,7 @@ struct frb_ctx {
   int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
   int fuse_tail = 3;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
+  int fuse_dwpw = 1;           // FRB_OPT_FUSE_DWPW: MobileNet blocks (depthwise 3x3 + pointwise 1x1) as one launch where the weights fit
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
   int* wd_host = nullptr;      // watchdog words (mapped pinned memory)
@@ -145,6 +146,11 @@ int launch_conv3x3_c3_direct(frb_ctx*, const void* in, int B, int H, int W, int 
                              int Cout, const float* d_bias, const float* d_slope, void* out, int out_ld, cudaStream_t);
 int launch_dwconv3x3(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_w9c,
                      const float* d_bias, int act, float slope, void* out, cudaStream_t);
+// K4f: depthwise 3x3 + pointwise 1x1 of a MobileNet block in one launch (the depthwise output stays in shared memory)
+bool dwpw_fusable(int C, int Cout);
+int launch_dwpw_fused(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_dw_w9c,
+                      const float* d_dw_bias, float dw_slope, const void* d_pw_w16, int K_pad, int Cout, const float* d_pw_bias,
+                      const float* d_pw_slope, void* out, int out_ld, cudaStream_t);
 int launch_maxpool3x3s2(frb_ctx*, const void* in, int in_ld, int B, int H, int W, int C, int pad, void* out, int out_ld,
                         cudaStream_t);
 int launch_avgpool(frb_ctx*, const void* in, int B, int HW, int C, void* out, cudaStream_t);

@@ -129,7 +129,8 @@ struct View {
   int t = -1, coff = 0;
 };
 // OP_CONV_TAIL: conv3 + skip (layer) and the next block's conv1 (layer2) in one launch (conv_tail.cu); out2 = conv1's output
-enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4, OP_CONV_TAIL = 5 };
+// OP_DWPW: depthwise 3x3 (dws[layer]) + pointwise 1x1 (convs[layer2]) of a MobileNet block in one launch (glue.cu K4f)
+enum OpKind : int { OP_CONV = 0, OP_DW = 1, OP_MAXPOOL = 2, OP_AVGPOOL = 3, OP_L2NORM = 4, OP_CONV_TAIL = 5, OP_DWPW = 6 };
 struct Op {
   int kind = 0, layer = -1, layer2 = -1, layer3 = -1;   // layer3: skip conv computed inside OP_CONV_TAIL (res = its input)
   View in, out, res, out2;
@@ -468,6 +469,12 @@ struct Builder {
     touch(in); touch(out);
     plan->ops.push_back(op);
   }
+  void dwpw(int idx, const std::string& pw, View in, View out) {
+    Op op;
+    op.kind = OP_DWPW; op.layer = idx; op.layer2 = layer(pw); op.in = in; op.out = out;
+    touch(in); touch(out);
+    plan->ops.push_back(op);
+  }
   void maxpool(View in, View out, int C, int pad) {
     Op op;
     op.kind = OP_MAXPOOL; op.in = in; op.out = out; op.C = C; op.pad = pad;
@@ -556,10 +563,16 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
     for (int i = 1; i <= 13; ++i) {
       const int s = kMnetStride[i - 1];
       const int ho = conv_out_dim(h, 3, s, 1), wo = conv_out_dim(w, 3, s, 1);
-      const int d = b.tensor(ho, wo, cin);
-      b.dw(i - 1, V(x), V(d));
       const int y = b.tensor(ho, wo, kMnetCout[i - 1]);
-      b.conv(sfmt("body.%d.pw", i), V(d), V(y));
+      // fused where it measured faster (profiles/r02_layer_times_mnet_360p_dwpw.txt): the blocks with up to 32 input channels,
+      // whose pointwise GEMM (K <= 32) wastes a tcgen05 tile; from 64 channels on the two launches are level or ahead
+      if (net->ctx->fuse_dwpw && dwpw_fusable(cin, kMnetCout[i - 1]) && (cin <= 32 || net->ctx->fuse_dwpw == 2)) {
+        b.dwpw(i - 1, sfmt("body.%d.pw", i), V(x), V(y));
+      } else {
+        const int d = b.tensor(ho, wo, cin);
+        b.dw(i - 1, V(x), V(d));
+        b.conv(sfmt("body.%d.pw", i), V(d), V(y));
+      }
       x = y; h = ho; w = wo; cin = kMnetCout[i - 1];
       if (i == 5) c[0] = x;
       if (i == 11) c[1] = x;
@@ -799,6 +812,13 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
                               op.layer3 >= 0 ? &net->convs[op.layer3] : nullptr, net->convs[op.layer].d_bias_skip, st);
         break;
       }
+      case OP_DWPW: {
+        const DwLayer& D = net->dws[op.layer];
+        const ConvLayer& P = net->convs[op.layer2];
+        rc = launch_dwpw_fused(ctx, base(op.in), plan.B, ti.H, ti.W, D.C, D.stride, D.d_w, D.d_bias, D.slope, P.d_w, P.K_pad,
+                               P.Cout, P.d_bias, P.d_slope, base(op.out), plan.tensors[op.out.t].C, st);
+        break;
+      }
       case OP_DW: {
         const DwLayer& L = net->dws[op.layer];
         rc = launch_dwconv3x3(ctx, base(op.in), plan.B, ti.H, ti.W, L.C, L.stride, L.d_w, L.d_bias, 2, L.slope, base(op.out), st);
@@ -824,6 +844,11 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
                       : static_cast<double>(plan.B) * conv_out_dim(ti.H, L.kh, L.sh, L.ph) * conv_out_dim(ti.W, L.kw, L.sw, L.pw);
         N = L.Cout;
         K = static_cast<double>(L.kh) * L.kw * L.Cin;
+      } else if (op.kind == OP_DWPW) {
+        const TensorInfo& to = plan.tensors[op.out.t];
+        M = static_cast<double>(plan.B) * to.H * to.W;
+        N = net->convs[op.layer2].Cout;
+        K = net->dws[op.layer].C + 9.0 * net->dws[op.layer].C / N;    // pointwise + depthwise FMAs per output element
       } else if (op.kind == OP_CONV_TAIL) {
         // reported as one conv row: M pixels, N = both outputs, flop of both GEMMs
         const ConvLayer& L3 = net->convs[op.layer];
@@ -836,7 +861,7 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
         M = static_cast<double>(plan.B) * ti.H * ti.W;
         N = ti.C;
       }
-      const double row[6] = {static_cast<double>(op.kind == OP_CONV_TAIL ? OP_CONV : op.kind), M, N, K, 2.0 * M * N * K, 0.0};
+      const double row[6] = {static_cast<double>(op.kind == OP_CONV_TAIL ? OP_CONV : (op.kind == OP_DWPW ? OP_DW : op.kind)), M, N, K, 2.0 * M * N * K, 0.0};
       ctx->lt_info.insert(ctx->lt_info.end(), row, row + 6);
       mark();
     }

@@ -71,6 +71,9 @@ enum frb_option {
                            /* 2: as 1, but not across the layer1 -> layer2 edge; 3 (default): as 1, and the 1x1 skip conv of          */
                            /* layer1's first block is computed inside that launch too (its output is never rounded to 16 bits, so     */
                            /* results differ from 0 by that one rounding)                                                           */
+  FRB_OPT_FUSE_DWPW = 16,  /* 0: depthwise and pointwise convs of RetinaFace-MobileNet0.25 are separate launches; 1 (default): one launch */
+                           /* per block for the blocks with up to 32 input channels (the depthwise output stays in shared memory; same   */
+                           /* rounding points, other summation order); 2: every block whose weights fit                                  */
   FRB_OPT_GRAPHS = 13      /* 1: short forwards (InceptionResnetV1, RetinaFace-MobileNet0.25 up to 64 x 360p) are captured once per  */
                            /* shape into a CUDA graph and replayed.  Default 0: measured SLOWER than stream launches with         */
                            /* programmatic dependent launch (the kernels are GPU-bound at 10-35 us, and a replayed graph loses    */

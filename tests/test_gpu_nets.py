@@ -193,3 +193,32 @@ def test_fused_bottleneck_tail_does_not_change_results(ctx, B, H, W):
         # level 3 skips ONE rounding to 16 bits (the skip conv's output): not the same bits, the same network
         ref = outs[1][k].float()
         assert (outs[3][k].float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 360, 640), (3, 135, 97)])
+def test_fused_mobilenet_blocks_match_separate_launches(ctx, B, H, W):
+    """FRB_OPT_FUSE_DWPW: depthwise 3x3 + pointwise 1x1 in one launch (glue.cu K4f, mma.sync GEMM) keeps the rounding points
+    of the two separate launches (16-bit depthwise output, fp32 accumulation); only the summation order of the pointwise
+    GEMM differs.  0 = separate, 1 = default (blocks up to 32 channels), 2 = every block that fits."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(12)
+    fr = torch.from_numpy(_frames(rng, B, H, W)).cuda()
+    mid = weights.MODEL_IDS["retina_mnet025"]
+    c = _lib.Context(0)
+    try:
+        ops.load_model(c, mid, weights.write_blob(weights.synth_weights("retina_mnet025", 0)))
+        x16 = ops.preprocess_u8(c, fr, True, ops.input_layout(mid))
+        outs = []
+        for fuse in (0, 1, 2):
+            c.set_option(_lib.FRB_OPT_FUSE_DWPW, fuse)
+            n0 = c.launch_count()
+            outs.append([t.clone() for t in ops.retina_forward(c, mid, x16, H, W)])
+            outs[-1].append(c.launch_count() - n0)
+    finally:
+        c.close()
+    assert outs[1][3] == outs[0][3] - 3 and outs[2][3] == outs[0][3] - 12
+    for k in range(3):
+        ref = outs[0][k].float()
+        for o in (outs[1], outs[2]):
+            assert torch.isfinite(o[k]).all()
+            assert (o[k].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()

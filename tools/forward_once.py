@@ -10,7 +10,11 @@ mid = W.MODEL_IDS["retina_r50"]
 ops.load_model(ctx, mid, W.write_blob(W.synth_weights("retina_r50", 0)))
 fr = torch.from_numpy(synth.clip(1234, 0, B, H, Wd)).cuda()
 x16 = ops.preprocess_u8(ctx, fr, True, ops.input_layout(mid))
+if os.environ.get("FRB_FUSE"):
+    ctx.set_option(_lib.FRB_OPT_FUSE_TAIL, int(os.environ["FRB_FUSE"]))
+n0 = 0
 for _ in range(2):
+    n0 = ctx.launch_count()
     ops.retina_forward(ctx, mid, x16, H, Wd)
 torch.cuda.synchronize()
-print("launches per forward:", 71)
+print("launches per forward:", ctx.launch_count() - n0)
