@@ -216,7 +216,7 @@ def test_fused_mobilenet_blocks_match_separate_launches(ctx, B, H, W):
             outs[-1].append(c.launch_count() - n0)
     finally:
         c.close()
-    assert outs[1][3] == outs[0][3] - 3 and outs[2][3] == outs[0][3] - 12
+    assert outs[1][3] == outs[0][3] - 4 and outs[2][3] == outs[0][3] - 12
     for k in range(3):
         ref = outs[0][k].float()
         for o in (outs[1], outs[2]):
