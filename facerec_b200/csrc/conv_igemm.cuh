@@ -81,6 +81,10 @@ struct Elem16<false> {
     __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&u), __float2half2_rn(0.f));
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
 };
 template <>
 struct Elem16<true> {
@@ -95,6 +99,10 @@ struct Elem16<true> {
   }
   static __device__ __forceinline__ uint32_t relu2(uint32_t u) {
     __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u), __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&h);
   }
 };

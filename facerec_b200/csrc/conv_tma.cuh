@@ -111,6 +111,11 @@ struct ConvTmaArgs {
   float* head_conf;
   float* head_landm;
   int head_P_total, head_P_off, head_hw;
+  // fused 3x3 / stride 2 / pad 1 max pool of the (ReLU) output (kPool variant: halo mode, 8 x 16 patches): the conv output
+  // itself is never stored; pool_out is [B, pool_Ho, pool_Wo, pool_ld] 16-bit, zero at every position with row % 8 == 0 or
+  // col % 4 == 0 before the launch (those take max-reductions from up to four tiles)
+  void* pool_out;
+  int pool_Ho, pool_Wo, pool_ld;
 };
 
 // Host entry points (conv_tma_f16.cu / conv_tma_bf16.cu / conv_tma_stall.cu): pick the kernel variant for
@@ -148,7 +153,16 @@ __device__ __forceinline__ int fastdiv(int n, const uint32_t* fd) {
 
 // kRes: 0 no residual, 1 residual added before the activation (ResNet / Inception skip), 2 nearest-upsampled
 // residual added after it (FPN top-down).  kAct: 0 per-channel slope, 1 ReLU everywhere, 2 linear everywhere.
-template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair>
+// 16-byte max-reduction of eight 16-bit floats into global memory (REDG.E.MAX.F16x8 / BF16x8)
+template <bool kBF16>
+__device__ __forceinline__ void red_max8(void* dst, const uint4& v) {
+  if constexpr (kBF16)
+    asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  else
+    asm volatile("red.global.max.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair, bool kPool = false>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ CUtensorMap tmA,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -482,7 +496,52 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       sc.start();
       named_bar_sync(1 + grp, kGroupThreads);  // barrier B
       sc.stop(st_bar);
-      if (leader) {
+      if constexpr (kPool) {
+        // Max pool 3x3 / stride 2 / pad 1 straight from the staged 8 x 16 patch (row = 8 h + w, 128 B per pixel, chunk c of
+        // row r at (c ^ (r & 7)) * 16): the patch touches 9 x 5 pooled positions; the 7 x 3 inner ones see their whole
+        // window here and are stored, the others are max-REDUCED into the pre-zeroed output together with the partial
+        // maxima of the neighbouring tiles (values are >= 0 after the ReLU, max is exact and order independent: the pooled
+        // tensor has the bits of the separate max-pool launch).  The conv output itself never reaches memory.
+        const uint8_t* const slab = smem_o + grp * kSlabBytes;
+        const int w0 = done.c1, h0 = done.c2;
+        const int pi0 = h0 >> 1, pj0 = w0 >> 1;
+        typename E::T* const pout = static_cast<typename E::T*>(p.pool_out) + static_cast<size_t>(done.c3) * p.pool_Ho * p.pool_Wo * p.pool_ld + done.n0;
+        const int nchunk = done.ncols >> 3;
+        for (int it = gtid; it < 45 * 8; it += kGroupThreads) {
+          const int pos = it >> 3, ch = it & 7;
+          const int pi = pos / 5, pj = pos - pi * 5;
+          const int gi = pi0 + pi, gj = pj0 + pj;
+          if (gi >= p.pool_Ho || gj >= p.pool_Wo || ch >= nchunk) continue;
+          // nine unconditional loads from clamped coordinates (all in flight at once), then a masked max: a window pixel
+          // outside the patch or the image counts as 0, the identity for non-negative values
+          uint4 v[9];
+          bool ok[9];
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh) {
+            const int h = 2 * pi - 1 + dh;
+            const int hc = min(max(h, 0), 15);
+            const bool okh = h == hc && h0 + h < p.Ho;
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              const int w = 2 * pj - 1 + dw;
+              const int wc = min(max(w, 0), 7);
+              const int r = hc * 8 + wc;
+              v[dh * 3 + dw] = *reinterpret_cast<const uint4*>(slab + r * 128 + ((ch ^ (r & 7)) << 4));
+              ok[dh * 3 + dw] = okh && w == wc && w0 + w < p.Wo;
+            }
+          }
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) {
+            if (ok[t9]) {
+              m.x = E::max2(m.x, v[t9].x); m.y = E::max2(m.y, v[t9].y); m.z = E::max2(m.z, v[t9].z); m.w = E::max2(m.w, v[t9].w);
+            }
+          }
+          typename E::T* const dst = pout + (static_cast<size_t>(gi) * p.pool_Wo + gj) * p.pool_ld + ch * 8;
+          if (pi >= 1 && pi <= 7 && pj >= 1 && pj <= 3) *reinterpret_cast<uint4*>(dst) = m;
+          else red_max8<kBF16>(dst, m);
+        }
+      } else if (leader) {
         if (p.patch) tma_store_4d(&tmO, smem_o + grp * kSlabBytes, done.n0, done.c1, done.c2, done.c3);
         else tma_store_2d(&tmO, smem_o + grp * kSlabBytes, done.n0, done.c1);
         tma_store_commit();

@@ -5,10 +5,10 @@
 
 namespace frb {
 
-template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair>
+template <bool kBF16, bool kStall, int kRes, int kAct, bool kPair, bool kPool = false>
 static cudaError_t conv_tma_launch_one(int grid, size_t smem, cudaStream_t st, const ConvTmaArgs& a, const CUtensorMap& tmA,
                                        const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR, const CUtensorMap& tmI) {
-  auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct, kPair>;
+  auto* kernel = conv_tma_kernel<kBF16, kStall, kRes, kAct, kPair, kPool>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -41,6 +41,7 @@ static cudaError_t conv_tma_dispatch(int res, int act, int grid, size_t smem, cu
     if (act == 2) return conv_tma_launch_one<kBF16, kStall, 1, 2, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
     return conv_tma_launch_one<kBF16, kStall, 1, 0, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   }
+  if (act == 1 && a.pool_out != nullptr) return conv_tma_launch_one<kBF16, kStall, 0, 1, kPair, true>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   if (act == 1) return conv_tma_launch_one<kBF16, kStall, 0, 1, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   if (act == 2) return conv_tma_launch_one<kBF16, kStall, 0, 2, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);
   return conv_tma_launch_one<kBF16, kStall, 0, 0, kPair>(grid, smem, st, a, tmA, tmB, tmO, tmR, tmI);

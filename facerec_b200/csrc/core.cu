@@ -226,6 +226,7 @@ static bool tma_path_ok(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io) {
   // the fused RetinaFace heads (32 linear columns) leave through the fp32 head epilogue of the TMA kernel
   const bool head = io.out_mode == OUT_HEAD_SCATTER && linear && L.Cout == 32 && L.BN == 32 && L.n_tiles == 1 &&
                     L.act_kind == 2 && io.res_mode == RES_NONE && (L.Cin % kBK) == 0 && (io.P_total % 2) == 0 && (io.P_off % 2) == 0;
+  if (io.pool_out != nullptr) return true;                          // conv_launch_tma checks the shape it needs
   if (ctx->force_gather || (io.out_mode != OUT_16BIT && !head)) return false;
   if (!linear && (L.Cin % kBK) != 0) return false;                 // taps are fetched as whole 64-channel blocks
   if (!linear && io.res_mode == RES_POST_ACT_UPSAMPLE) return false;
@@ -358,7 +359,15 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
     } else if (a.halo) {
       if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.halo_w, a.halo_h, 1, 1, 1)) != FRB_OK) return rc;
     } else if ((rc = encode_patch(ctx, &tmA, io.in, L.Cin, io.W, io.H, io.B, io.in_ld, a.bw, a.bh, a.bb, L.sw, L.sh)) != FRB_OK) return rc;
-    if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.mpair ? 8 : a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
+    if (io.pool_out != nullptr) {
+      // fused max pool (3x3 / 2 / pad 1): needs the 8 x 16 halo patches, one N tile, ReLU, no residual
+      if (!a.halo || a.mpair || a.bw != 8 || a.bh != 16 || a.bb != 1 || L.n_tiles != 1 || io.res_mode != RES_NONE || L.act_kind != 1 ||
+          (io.pool_ld % 8) != 0 || (reinterpret_cast<uintptr_t>(io.pool_out) & 15) != 0)
+        return set_err(ctx, FRB_ERR_INVALID, "conv: this layer cannot take the fused max pool");
+      a.pool_out = io.pool_out; a.pool_ld = io.pool_ld;
+      a.pool_Ho = conv_out_dim(Ho, 3, 2, 1); a.pool_Wo = conv_out_dim(Wo, 3, 2, 1);
+      tmO = tmA;                                   // never used: nothing but the pooled tensor is written
+    } else if ((rc = encode_patch(ctx, &tmO, io.out, L.Cout, Wo, Ho, io.B, io.out_ld, a.mpair ? 8 : a.bw, a.bh, a.bb, 1, 1)) != FRB_OK) return rc;
     tmR = tmO;
     if (io.res_mode == RES_PRE_ACT &&
         (rc = encode_patch(ctx, &tmR, io.res, L.Cout, Wo, Ho, io.B, io.res_ld, a.bw, a.bh, a.bb, 1, 1)) != FRB_OK)
@@ -437,6 +446,23 @@ static int conv_launch_tma(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, c
   return check_last(ctx, "conv_tma_kernel launch");
 }
 
+// Whether a conv of this shape takes the 8 x 16 halo patches the fused max pool needs: asked by the planner, answered by the
+// launch logic itself on a dry run of its patch choice (no launch).
+bool conv_pool_fusable(frb_ctx* ctx, const ConvLayer& L, int H, int W) {
+  if (!(L.special || ((L.Cin % kBK) == 0 && L.kh * L.kw > 1 && L.sh == 1 && L.sw == 1)) || L.n_tiles != 1 || L.act_kind != 1 ||
+      ctx->halo_mode < 0 || ctx->force_gather)
+    return false;
+  const int Ho = L.special ? H : conv_out_dim(H, L.kh, L.sh, L.ph), Wo = L.special ? W - 3 : conv_out_dim(W, L.kw, L.sw, L.pw);
+  constexpr int kRefBatch = 64;
+  int rw, rh, rb;
+  pick_patch(kRefBatch, Ho, Wo, L.sw, L.sh, rw, rh, rb);
+  const double eff_patch = static_cast<double>(kRefBatch) * Ho * Wo /
+                           (128.0 * ((Wo + rw - 1) / rw) * ((Ho + rh - 1) / rh) * ((kRefBatch + rb - 1) / rb));
+  const double eff_halo = static_cast<double>(Ho) * Wo / (128.0 * ((Wo + 7) / 8) * ((Ho + 15) / 16));
+  const bool resident_w = L.n_tiles * L.kh * L.kw * ((L.Cin + kBK - 1) / kBK) * L.BN * 128 <= kResidentWeightBytes;
+  return resident_w && eff_halo >= 0.85 * eff_patch;      // conv_launch_tma: `want` (resident weights) and the efficiency gate
+}
+
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
@@ -467,7 +493,7 @@ int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t
 
   if ((reinterpret_cast<uintptr_t>(io.in) & 15) || (io.in_ld % 8) != 0)
     return set_err(ctx, FRB_ERR_INVALID, "conv: input must be 16-byte aligned with in_ld %% 8 == 0");
-  if (io.out_mode != OUT_HEAD_SCATTER &&
+  if (io.out_mode != OUT_HEAD_SCATTER && io.pool_out == nullptr &&
       ((reinterpret_cast<uintptr_t>(io.out) & 15) || (io.out_ld % 8) != 0 || (L.Cout % 8) != 0))
     return set_err(ctx, FRB_ERR_INVALID, "conv: output must be 16-byte aligned with out_ld %% 8 == 0 and Cout %% 8 == 0");
   if (io.res_mode != RES_NONE && ((reinterpret_cast<uintptr_t>(io.res) & 15) || (io.res_ld % 8) != 0))
@@ -576,6 +602,12 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_FUSE_POOL:
+      if (ctx->fuse_pool != (value ? 1 : 0)) {
+        ctx->fuse_pool = value ? 1 : 0;
+        for (auto& kv : ctx->nets) net_drop_plans(kv.second);
+      }
+      return FRB_OK;
     case FRB_OPT_FUSE_DWPW:
       if (value < 0 || value > 2) return set_err(ctx, FRB_ERR_INVALID, "fuse_dwpw must be 0, 1 or 2");
       if (ctx->fuse_dwpw != value) {

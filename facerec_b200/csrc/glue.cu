@@ -515,6 +515,29 @@ int launch_dwpw_fused(frb_ctx* ctx, const void* in, int B, int H, int W, int C, 
   return check_last(ctx, "dwpw_fused_kernel");
 }
 
+// ------------------------------------------------------------------------------------------ K9z
+// Zero fill of the pooled positions the fused stem + max-pool epilogue (conv_tma_kernel<..., kPool>) max-reduces into: pooled
+// rows that are a multiple of 8 and pooled columns that are a multiple of 4 (the seams of the 8 x 16 stem patches), i.e.
+// 34 % of the tensor; every other position is written whole by exactly one tile.
+__global__ void pool_border_zero_kernel(uint4* __restrict__ out, int B, int Ho, int Wo, int cg, int ld8) {
+  const int total = B * Ho * Wo * cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    int t = i / cg;
+    const int j = t % Wo; t /= Wo;
+    const int r = t % Ho;
+    if ((r & 7) == 0 || (j & 3) == 0) out[static_cast<size_t>(i / cg) * ld8 + g] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int launch_pool_border_zero(frb_ctx* ctx, void* out, int B, int Ho, int Wo, int C, int out_ld, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  if (C % 8 || out_ld % 8 || total > 0x7fffffffLL - (1 << 22)) return set_err(ctx, FRB_ERR_INVALID, "pool zero fill: bad shape");
+  pool_border_zero_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(static_cast<uint4*>(out), B, Ho, Wo, C / 8, out_ld / 8);
+  ctx->launches++;
+  return check_last(ctx, "pool_border_zero_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ K9
 // 3x3 stride-2 max pool, `pad` in {0,1} (padding never wins: -inf), pixel strides in elements.
 // One thread owns 8 channels of one output column and walks a strip of kPoolRows output rows: every input row of the

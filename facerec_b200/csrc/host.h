@@ -47,6 +47,7 @@ struct frb_ctx {
   int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
   int fuse_tail = 3;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
+  int fuse_pool = 1;           // FRB_OPT_FUSE_POOL: the ResNet stem's max pool runs in the stem conv's epilogue
   int fuse_dwpw = 1;           // FRB_OPT_FUSE_DWPW: MobileNet blocks (depthwise 3x3 + pointwise 1x1) as one launch where the weights fit
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
   std::string err;
@@ -113,6 +114,10 @@ struct ConvIO {
   float* conf = nullptr;
   float* landm = nullptr;
   int P_total = 0, P_off = 0;
+  // 3x3 / stride 2 / pad 1 max pool fused into the conv's epilogue (the ResNet stem): `out` is not written; pool_out is
+  // [B, pool_Ho, pool_Wo, pool_ld] and must have been prepared by launch_pool_border_zero
+  void* pool_out = nullptr;
+  int pool_ld = 0;
 };
 
 inline int conv_out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
@@ -130,6 +135,8 @@ int ctx_scratch(frb_ctx* ctx, int slot, size_t bytes, void** out);
 int conv_prepare(frb_ctx* ctx, ConvLayer& L, const float* h_w, const float* h_bias, const float* h_slope);
 void conv_release(ConvLayer& L);
 int conv_launch(frb_ctx* ctx, const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
+// true when a conv over an H x W input runs on 8 x 16 halo patches, i.e. can take ConvIO::pool_out (the fused 3x3 / 2 max pool)
+bool conv_pool_fusable(frb_ctx* ctx, const ConvLayer& L, int H, int W);
 // conv_tail.cu: y = relu(conv3(in) + res) [M, 256] and y1 = relu(conv1_next(y)) [M, L1.Cout] in one launch (K2t)
 // With Ld != null the skip is Ld's 1x1 conv of `res` (= its input x) computed inside, bias1 = conv3's bias + Ld's.
 bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1);
@@ -151,6 +158,8 @@ bool dwpw_fusable(int C, int Cout);
 int launch_dwpw_fused(frb_ctx*, const void* in, int B, int H, int W, int C, int stride, const void* d_dw_w9c,
                       const float* d_dw_bias, float dw_slope, const void* d_pw_w16, int K_pad, int Cout, const float* d_pw_bias,
                       const float* d_pw_slope, void* out, int out_ld, cudaStream_t);
+// zeroes the positions of a pooled tensor that the fused stem + pool epilogue max-reduces into (row % 8 == 0 or col % 4 == 0)
+int launch_pool_border_zero(frb_ctx*, void* out, int B, int Ho, int Wo, int C, int out_ld, cudaStream_t);
 int launch_maxpool3x3s2(frb_ctx*, const void* in, int in_ld, int B, int H, int W, int C, int pad, void* out, int out_ld,
                         cudaStream_t);
 int launch_avgpool(frb_ctx*, const void* in, int B, int HW, int C, void* out, cudaStream_t);

@@ -469,6 +469,12 @@ struct Builder {
     touch(in); touch(out);
     plan->ops.push_back(op);
   }
+  void conv_pool(const std::string& name, View in, View pooled) {      // conv whose epilogue max-pools (3x3 / 2 / pad 1) into `pooled`
+    Op op;
+    op.kind = OP_CONV; op.layer = layer(name); op.in = in; op.out2 = pooled;
+    touch(in); touch(pooled);
+    plan->ops.push_back(op);
+  }
   void dwpw(int idx, const std::string& pw, View in, View out) {
     Op op;
     op.kind = OP_DWPW; op.layer = idx; op.layer2 = layer(pw); op.in = in; op.out = out;
@@ -510,11 +516,16 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
   int c[3];
   if (r50) {
     const int H1 = (H + 1) / 2, W1 = (W + 1) / 2;
-    const int t1 = b.tensor(H1, W1, 64);
-    b.conv("conv1", V(x0), V(t1));
     int h = conv_out_dim(H1, 3, 2, 1), w = conv_out_dim(W1, 3, 2, 1);
     int x = b.tensor(h, w, 64);
-    b.maxpool(V(t1), V(x), 64, 1);
+    if (net->ctx->fuse_pool && conv_pool_fusable(net->ctx, net->convs[b.layer("conv1")], H1, W1 + 3)) {
+      // stem conv with the max pool in its epilogue: the 64-channel stem output (4.25 GB at 64 x 1080p) never exists
+      b.conv_pool("conv1", V(x0), V(x));
+    } else {
+      const int t1 = b.tensor(H1, W1, 64);
+      b.conv("conv1", V(x0), V(t1));
+      b.maxpool(V(t1), V(x), 64, 1);
+    }
     int y1_fused = -1;
     for (int l = 0; l < 4; ++l) {
       const int planes = kR50Planes[l];
@@ -794,6 +805,12 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
           io.res = base(op.res); io.res_ld = tr.C; io.rH = tr.H; io.rW = tr.W;
         }
         io.loc = ep.loc; io.conf = ep.conf; io.landm = ep.landm; io.P_total = plan.P_total; io.P_off = op.P_off;
+        if (op.out2.t >= 0) {                      // max pool in the epilogue (the ResNet stem)
+          const TensorInfo& tp = plan.tensors[op.out2.t];
+          io.pool_out = base(op.out2); io.pool_ld = tp.C;
+          rc = launch_pool_border_zero(ctx, io.pool_out, plan.B, tp.H, tp.W, net->convs[op.layer].Cout, tp.C, st);
+          if (rc != FRB_OK) return rc;
+        }
         {
           const ConvLayer& L = net->convs[op.layer];
           if (L.direct3 && io.out_mode == OUT_16BIT && io.res_mode == RES_NONE && ti.C == 8 && op.in.coff == 0)

@@ -222,3 +222,30 @@ def test_fused_mobilenet_blocks_match_separate_launches(ctx, B, H, W):
         for o in (outs[1], outs[2]):
             assert torch.isfinite(o[k]).all()
             assert (o[k].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 270, 480), (3, 135, 97), (1, 64, 64), (2, 1080, 1920), (5, 203, 311)])
+def test_fused_stem_max_pool_does_not_change_results(ctx, B, H, W):
+    """FRB_OPT_FUSE_POOL: the ResNet stem's 3x3 / stride 2 max pool computed in the stem conv's epilogue (inner positions of
+    an 8 x 16 patch stored, seam positions max-reduced into the pre-zeroed tensor).  max is exact and order independent:
+    heads identical bit for bit with the separate max-pool launch, on ragged patches and odd sizes too, and repeatable."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(13)
+    fr = torch.from_numpy(_frames(rng, B, H, W)).cuda()
+    mid = weights.MODEL_IDS["retina_r50"]
+    c = _lib.Context(0)
+    try:
+        ops.load_model(c, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+        x16 = ops.preprocess_u8(c, fr, True, ops.input_layout(mid))
+        outs = []
+        for fuse in (1, 0, 1):
+            c.set_option(_lib.FRB_OPT_FUSE_POOL, fuse)
+            n0 = c.launch_count()
+            outs.append([t.clone() for t in ops.retina_forward(c, mid, x16, H, W)])
+            outs[-1].append(c.launch_count() - n0)
+    finally:
+        c.close()
+    assert outs[0][3] == outs[1][3] == outs[2][3]              # stem + zero fill instead of stem + max pool
+    for k in range(3):
+        assert torch.isfinite(outs[0][k]).all()
+        assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k])
