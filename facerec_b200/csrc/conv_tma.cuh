@@ -321,6 +321,32 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
       sl.ncols = min(kSlab, p.BN - s2 * kSlab);
       return sl;
     };
+    // kPool: a thread's pooling items (pooled position, 16-byte channel chunk) are the same for every patch, so their
+    // shared-memory offsets (window clamped into the patch) and the output offset are worked out once
+    // (three items per thread at most: 45 positions x 8 chunks over 128 threads), packed into three registers per item
+    uint32_t pk_row[3] = {0u, 0u, 0u}, pk_col[3] = {0u, 0u, 0u}, pk_dst[3] = {0u, 0u, 0u};
+    if constexpr (kPool) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int it = gtid + k * kGroupThreads;
+        if (it < 45 * 8) {
+          const int pos = it >> 3, ch = it & 7;
+          const int pi = pos / 5, pj = pos - pi * 5;
+          uint32_t rows = 0u, cols = 0u;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {                    // window rows / columns clamped into the patch
+            const int hc = min(max(2 * pi - 1 + d, 0), 15);
+            const int wc = min(max(2 * pj - 1 + d, 0), 7);
+            rows |= static_cast<uint32_t>(hc) << (4 * d);
+            cols |= static_cast<uint32_t>(wc * 128 + ((ch ^ wc) << 4)) << (10 * d);
+          }
+          const uint32_t inner = (pi >= 1 && pi <= 7 && pj >= 1 && pj <= 3) ? 1u : 0u;
+          pk_row[k] = rows | (inner << 21) | (1u << 22);
+          pk_col[k] = cols;
+          pk_dst[k] = static_cast<uint32_t>((pi * p.pool_Wo + pj) * p.pool_ld + ch * 8);
+        }
+      }
+    }
     float next_bs = 0.f;                       // bias (threads 0-63 of the group) / slope (64-127) of the next slab
     auto prefetch = [&](const Slab& sl) {
       const int col = gtid & (kSlab - 1);
@@ -507,6 +533,33 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
         const int pi0 = h0 >> 1, pj0 = w0 >> 1;
         typename E::T* const pout = static_cast<typename E::T*>(p.pool_out) + static_cast<size_t>(done.c3) * p.pool_Ho * p.pool_Wo * p.pool_ld + done.n0;
         const int nchunk = done.ncols >> 3;
+        const bool whole = h0 + 16 <= p.Ho && w0 + 8 <= p.Wo && pi0 + 9 <= p.pool_Ho && pj0 + 5 <= p.pool_Wo && nchunk == 8;
+        if (whole) {
+          // the patch lies inside the image: only the precomputed in-patch validity matters
+          typename E::T* const ptile = pout + (static_cast<size_t>(pi0) * p.pool_Wo + pj0) * p.pool_ld;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const uint32_t pr = pk_row[k], pc = pk_col[k];
+            if (pr == 0u) continue;
+            const uint8_t* const rp[3] = {slab + ((pr & 15u) << 10), slab + (((pr >> 4) & 15u) << 10), slab + (((pr >> 8) & 15u) << 10)};
+            const uint32_t cp[3] = {pc & 1023u, (pc >> 10) & 1023u, pc >> 20};
+            // a window row / column outside the patch was clamped onto the nearest one inside, which belongs to the same
+            // window: duplicates do not change a max, so all nine loads are unconditional (and in flight together)
+            uint4 v[9];
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+              for (int dw = 0; dw < 3; ++dw) v[dh * 3 + dw] = *reinterpret_cast<const uint4*>(rp[dh] + cp[dw]);
+            uint4 m = v[0];
+#pragma unroll
+            for (int t9 = 1; t9 < 9; ++t9) {
+              m.x = E::max2(m.x, v[t9].x); m.y = E::max2(m.y, v[t9].y); m.z = E::max2(m.z, v[t9].z); m.w = E::max2(m.w, v[t9].w);
+            }
+            typename E::T* const dst = ptile + pk_dst[k];
+            if (pr & (1u << 21)) *reinterpret_cast<uint4*>(dst) = m;
+            else red_max8<kBF16>(dst, m);
+          }
+        } else
         for (int it = gtid; it < 45 * 8; it += kGroupThreads) {
           const int pos = it >> 3, ch = it & 7;
           const int pi = pos / 5, pj = pos - pi * 5;
