@@ -41,6 +41,7 @@ FRB_OPT_CTA2 = 14
 FRB_OPT_FUSE_TAIL = 15
 FRB_OPT_FUSE_DWPW = 16
 FRB_OPT_FUSE_POOL = 17
+FRB_OPT_FUSE_TAIL2 = 18
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 

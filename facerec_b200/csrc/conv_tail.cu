@@ -25,6 +25,7 @@
 // (tools/conv_tail_protocol_sim.py replays the barrier protocol under random interleavings and checks every parity wait).
 // Linear M tiling (1x1, stride 1, no padding); ragged last tile: loads zero-fill, stores clip.
 #include <algorithm>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -373,6 +374,435 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2t2 — the same fusion for layer2 of RetinaFace-R50: conv3 (128 -> 512) + skip and the next block's conv1 (512 -> 128).
+// Neither weight matrix fits beside the pipeline buffers (128 KB each), so both are streamed, and the 512 output channels
+// of conv3 are worked on as two halves of 256 (TMEM holds two accumulators of 256 columns):
+//
+//   G ring (16 KB units, G producer)   per half: for each of conv3's two k-blocks: a, W3 rows 0-127, W3 rows 128-255 of
+//                                      the half; then the half's four skip slabs.  20 units per tile.
+//   W ring (16 KB units, W producer)   the eight 64-wide k-blocks of the next conv1's weights [128 x 512], 8 per tile
+//   issuer    G1(t, h): acc1 = a x W3_h (two N = 128 MMAs per k16 step) + skip slabs x I, into buffer X_t = t & 1 for
+//             h = 0 and Y_t = 1 - X_t for h = 1;  M2(t, h): columns [0, 128) of X_t (+)= staged slab x W1n k-block, slabs in
+//             channel order over both halves.  Order: M2(t,0); G1(t+1,0); M2(t,1); G1(t+1,1).
+//   epilogue  ten items per tile: e1 of half 0 (4 slabs), e1 of half 1 (4), e2 (2 slabs of the 128 conv1 channels).
+//             Y_t is free for G1(t+1, 0) once e1(t, 1) has drained it, X_t for G1(t+1, 1) once e2(t) has.
+//   store warp as in K2t.
+// At least four slab slots: G1(t+1, 0) waits for all four e1 items of half 1, whose fourth needs the slot of an item that only
+// M2(t, 0) frees (with three slots it would be one of half 1 itself, freed by M2(t, 1) AFTER G1(t+1, 0): the deadlock
+// tools/conv_tail_protocol_sim.py run2 finds).  Accumulation orders are those of the separate launches: same bits.
+constexpr int kTail2Threads = (kTailEpiWarps + 4) * 32;    // + MMA issuer, G producer, store warp, W producer
+constexpr int kTail2N1 = 512, kTail2K1 = 128, kTail2N2 = 128;
+constexpr int kTail2Ipt = 10;                              // epilogue items per tile
+
+struct ConvTail2Args {
+  int M, m_tiles;
+  int gring, wring, slots;
+  const float* bias1;    // [512]
+  const float* bias2;    // [128]
+  int* watchdog;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kTail2Threads, 1)
+conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant__ CUtensorMap tmA,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO1,
+                  const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmW3,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmI) {
+  using E = Elem16<kBF16>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  uint8_t* smem_g = smem;                                            // G ring
+  uint8_t* smem_w = smem_g + p.gring * kTailSlabBytes;               // W ring
+  uint8_t* smem_slot = smem_w + p.wring * kTailSlabBytes;            // output slab slots
+  uint8_t* smem_i = smem_slot + p.slots * kTailSlabBytes;            // 64 x 64 identity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_i + kTailIdentBytes);
+  uint64_t* gfull_bar = bars;            // [8]
+  uint64_t* gempty_bar = bars + 8;       // [8]
+  uint64_t* wfull_bar = bars + 16;       // [4]
+  uint64_t* wempty_bar = bars + 20;      // [4]
+  uint64_t* slabw_bar = bars + 24;       // [8] e1 slab written -> M2
+  uint64_t* sfree_bar = bars + 32;       // [8] slot free: store drained + M2 retired
+  uint64_t* staged_bar = bars + 40;      // [8] slab staged -> store warp
+  uint64_t* acc1_bar = bars + 48;        // [2] G1 + skip of a half complete (one phase per tile and buffer)
+  uint64_t* acc2_bar = bars + 50;        // [2] M2 of both halves complete (buffer X_t: one phase every two tiles)
+  uint64_t* free1_bar = bars + 52;       // [2] buffer drained by the four e1 items of a second half (16 warps)
+  uint64_t* free2_bar = bars + 54;       // [2] buffer drained by the two e2 items (8 warps)
+  uint64_t* bres_bar = bars + 56;
+  uint64_t* turn_bar = bars + 57;        // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 60);
+  float* s_bias1 = reinterpret_cast<float*>(bars + 62);   // [512]
+  float* s_bias2 = s_bias1 + kTail2N1;                    // [128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kMmaWarp = kTailEpiWarps, kGWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2, kWWarp = kTailEpiWarps + 3;
+  const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == kGWarp && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO1); tma_prefetch_desc(&tmO2);
+    tma_prefetch_desc(&tmW3); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmI);
+  }
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int i = 0; i < 8; ++i) {
+        mbar_init(&gfull_bar[i], 1);
+        mbar_init(&gempty_bar[i], 1);
+        mbar_init(&slabw_bar[i], 1);
+        mbar_init(&sfree_bar[i], 2);
+        mbar_init(&staged_bar[i], 1);
+      }
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(&wfull_bar[i], 1);
+        mbar_init(&wempty_bar[i], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&acc1_bar[b], 1);
+        mbar_init(&acc2_bar[b], 1);
+        mbar_init(&free1_bar[b], 16);
+        mbar_init(&free2_bar[b], 8);
+      }
+      mbar_init(bres_bar, 1);
+      for (int g = 0; g < kTailGroups; ++g) mbar_init(&turn_bar[g], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kTail2N1 + kTail2N2; i += kTail2Threads)
+    s_bias1[i] = i < kTail2N1 ? __ldg(p.bias1 + i) : __ldg(p.bias2 + i - kTail2N1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kTailEpiWarps) {
+    // ================================================================ epilogue groups
+    const int quarter = warp & 3;
+    const int grp = warp >> 2;
+    const int gtid = threadIdx.x & 127;
+    const bool leader = gtid == 0;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw7 = static_cast<uint32_t>(row & 7);
+    const int my_items = my_tiles * kTail2Ipt;
+    int t = grp / kTail2Ipt, j = grp - t * kTail2Ipt;
+    int slot = grp % p.slots, use = grp / p.slots;
+    for (int q = grp; q < my_items; q += kTailGroups) {
+      const int X = t & 1;
+      const bool second = j >= 8;                                    // e2 item
+      const int h = j < 4 ? 0 : 1;                                   // half (e1 items)
+      const int s = second ? j - 8 : (j & 3);
+      const int buf = (second || h == 0) ? X : 1 - X;
+      if (leader) {                            // slots in item order, one waiting thread per group: see K2t
+        if (q > 0) mbar_wait(&turn_bar[(grp + kTailGroups - 1) % kTailGroups], static_cast<uint32_t>((q - 1) / kTailGroups) & 1u, p.watchdog, 130 + grp);
+        mbar_wait(&sfree_bar[slot], (static_cast<uint32_t>(use) & 1u) ^ 1u, p.watchdog, 100 + slot);
+        mbar_arrive(&turn_bar[grp]);
+      }
+      named_bar_sync(1 + grp, 128);
+      if (second) mbar_wait(&acc2_bar[buf], static_cast<uint32_t>(t >> 1) & 1u, p.watchdog, 120 + buf);
+      else mbar_wait(&acc1_bar[buf], static_cast<uint32_t>(t) & 1u, p.watchdog, 110 + buf);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTailN1 + s * kTailSlab);
+      const float* bias = second ? s_bias2 + s * kTailSlab : s_bias1 + h * kTailN1 + s * kTailSlab;
+      uint8_t* const orow = smem_slot + slot * kTailSlabBytes + static_cast<uint32_t>(row) * 128u;
+      uint32_t v0[16], v1[16];
+      auto finish16 = [&](const uint32_t* v, int cbase) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int cc = cbase + c * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + cc);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + cc + 4);
+          uint4 o;
+          o.x = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y));
+          o.y = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w));
+          o.z = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y));
+          o.w = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(cc >> 3) ^ sw7) << 4)) = o;
+        }
+      };
+      tmem_ld16(taddr, v0);
+      tc_wait_ld16(v0);
+      tmem_ld16(taddr + 16, v1);
+      finish16(v0, 0);
+      tc_wait_ld16(v1);
+      tmem_ld16(taddr + 32, v0);
+      finish16(v1, 16);
+      tc_wait_ld16(v0);
+      tmem_ld16(taddr + 48, v1);
+      finish16(v0, 32);
+      tc_wait_ld16(v1);
+      tc_fence_before();                       // the accumulator columns of this warp are in registers
+      if (second || h == 1) {                  // this warp's part of a buffer hand-over (e2: X_t, e1 of half 1: Y_t)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(second ? &free2_bar[buf] : &free1_bar[buf]);
+      }
+      finish16(v1, 48);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + grp, 128);
+      if (leader) {
+        if (!second) mbar_arrive(&slabw_bar[slot]);
+        mbar_arrive(&staged_bar[slot]);
+      }
+      j += kTailGroups;
+      while (j >= kTail2Ipt) { j -= kTail2Ipt; ++t; }
+      slot += kTailGroups;
+      while (slot >= p.slots) { slot -= p.slots; ++use; }
+    }
+  } else if (warp == kStoreWarp) {
+    // ================================================================ store warp
+    if (lane == 0) {
+      const int my_items = my_tiles * kTail2Ipt;
+      int t = 0, j = 0, slot = 0;
+      uint32_t par = 0;
+      int pend_slot = -1, last_slot = -1;
+      auto give_back = [&](int ps) {
+        mbar_arrive(&sfree_bar[ps & 15]);
+        if (ps & 16) mbar_arrive(&sfree_bar[ps & 15]);
+      };
+      for (int q = 0; q < my_items; ++q) {
+        const bool second = j >= 8;
+        const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
+        mbar_wait(&staged_bar[slot], (par >> slot) & 1u, p.watchdog, 400 + slot);
+        par ^= 1u << slot;
+        if (second) tma_store_2d(&tmO2, smem_slot + slot * kTailSlabBytes, (j - 8) * kTailSlab, m0);
+        else tma_store_2d(&tmO1, smem_slot + slot * kTailSlabBytes, j * kTailSlab, m0);       // j = 4 h + s: channel 64 j
+        tma_store_commit();
+        pend_slot = last_slot;
+        last_slot = slot | (second ? 16 : 0);
+        if (pend_slot >= 0) {
+          tma_store_wait_read<1>();
+          give_back(pend_slot);
+        }
+        if (++j == kTail2Ipt) { j = 0; ++t; }
+        if (++slot == p.slots) slot = 0;
+      }
+      if (last_slot >= 0) {
+        tma_store_wait_read<0>();
+        give_back(last_slot);
+      }
+      tma_store_wait<0>();
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc_h = make_idesc_f16(kBM, 128, kBF16 ? 1 : 0);
+    const uint32_t idesc_r = make_idesc_f16(kBM, kTailSlab, kBF16 ? 1 : 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t g_lo = desc_lo(smem_u32(smem_g)), w_lo = desc_lo(smem_u32(smem_w)), slot_lo = desc_lo(smem_u32(smem_slot)),
+                   id_lo = desc_lo(smem_u32(smem_i));
+    const uint32_t step = kTailSlabBytes >> 4;
+    const uint32_t gfull0 = smem_u32(gfull_bar), gempty0 = smem_u32(gempty_bar), wfull0 = smem_u32(wfull_bar), wempty0 = smem_u32(wempty_bar),
+                   slabw0 = smem_u32(slabw_bar), sfree0 = smem_u32(sfree_bar), acc10 = smem_u32(acc1_bar), acc20 = smem_u32(acc2_bar),
+                   free10 = smem_u32(free1_bar), free20 = smem_u32(free2_bar);
+    int gs = 0, ws = 0;
+    uint32_t gph = 0, wph = 0;
+    mbar_wait(bres_bar, 0, p.watchdog, 250);
+    auto mma4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc0) {
+      tc_mma_f16(d, pack_desc(a, hi), pack_desc(b, hi), idesc, acc0);
+      tc_mma_f16(d, pack_desc(a + 2, hi), pack_desc(b + 2, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 4, hi), pack_desc(b + 4, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 6, hi), pack_desc(b + 6, hi), idesc, 1u);
+    };
+    auto g_take = [&](int& unit) {             // wait for the next G-ring unit, return its index, advance
+      mbar_wait_a(gfull0 + gs * 8, gph, p.watchdog, 210 + gs);
+      unit = gs;
+      if (++gs == p.gring) { gs = 0; gph ^= 1; }
+    };
+    auto issue_g1 = [&](int t, int h) {
+      const int X = t & 1;
+      const int buf = h == 0 ? X : 1 - X;
+      const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTailN1);
+      if (t >= 1) {
+        const uint32_t par = static_cast<uint32_t>((t - 1) >> 1) & 1u;
+        mbar_wait_a((h == 0 ? free10 : free20) + buf * 8, par, p.watchdog, 200 + buf + 2 * h);
+      }
+      tc_fence_after();
+      for (int kb = 0; kb < 2; ++kb) {
+        int ua, ub0, ub1;
+        g_take(ua); g_take(ub0); g_take(ub1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a = g_lo + static_cast<uint32_t>(ua) * step;
+          mma4(d, a, g_lo + static_cast<uint32_t>(ub0) * step, idesc_h, kb != 0 ? 1u : 0u);
+          mma4(d + 128u, a, g_lo + static_cast<uint32_t>(ub1) * step, idesc_h, kb != 0 ? 1u : 0u);
+          tc_commit_a(gempty0 + ua * 8);
+          tc_commit_a(gempty0 + ub0 * 8);
+          tc_commit_a(gempty0 + ub1 * 8);
+        }
+        __syncwarp();
+      }
+      for (int rs = 0; rs < 4; ++rs) {
+        int u;
+        g_take(u);
+        tc_fence_after();
+        if (elect_one()) {
+          mma4(d + static_cast<uint32_t>(rs * kTailSlab), g_lo + static_cast<uint32_t>(u) * step, id_lo, idesc_r, 1u);
+          tc_commit_a(gempty0 + u * 8);
+          if (rs == 3) tc_commit_a(acc10 + buf * 8);
+        }
+        __syncwarp();
+      }
+    };
+    int slot = 0;
+    uint32_t e1par = 0;
+    auto issue_m2 = [&](int t, int h) {
+      const int X = t & 1;
+      const uint32_t d = tmem_base + static_cast<uint32_t>(X * kTailN1);
+      for (int s = 0; s < 4; ++s) {
+        mbar_wait_a(slabw0 + slot * 8, (e1par >> slot) & 1u, p.watchdog, 230 + slot);
+        if (s == 0 && h == 0) {                // acc2 covers the columns of slabs 0 and 1 of half 0
+          const int s1 = slot + 1 == p.slots ? 0 : slot + 1;
+          mbar_wait_a(slabw0 + s1 * 8, (e1par >> s1) & 1u, p.watchdog, 240 + s1);
+        }
+        mbar_wait_a(wfull0 + ws * 8, wph, p.watchdog, 260 + ws);
+        tc_fence_after();
+        if (elect_one()) {
+          mma4(d, slot_lo + static_cast<uint32_t>(slot) * step, w_lo + static_cast<uint32_t>(ws) * step, idesc_h, (h != 0 || s != 0) ? 1u : 0u);
+          tc_commit_a(sfree0 + slot * 8);
+          tc_commit_a(wempty0 + ws * 8);
+          if (h == 1 && s == 3) tc_commit_a(acc20 + X * 8);
+        }
+        __syncwarp();
+        e1par ^= 1u << slot;
+        if (++slot == p.slots) slot = 0;
+        if (++ws == p.wring) { ws = 0; wph ^= 1; }
+      }
+      if (h == 1)                              // the tile's two e2 items take the next two slots
+        for (int e = 0; e < 2; ++e)
+          if (++slot == p.slots) slot = 0;
+    };
+    if (my_tiles > 0) {
+      issue_g1(0, 0);
+      issue_g1(0, 1);
+    }
+    for (int t = 0; t < my_tiles; ++t) {
+      issue_m2(t, 0);
+      if (t + 1 < my_tiles) issue_g1(t + 1, 0);
+      issue_m2(t, 1);
+      if (t + 1 < my_tiles) issue_g1(t + 1, 1);
+    }
+  } else if (warp == kGWarp) {
+    // ================================================================ G producer
+    const uint32_t g0 = smem_u32(smem_g);
+    const uint32_t gfull0 = smem_u32(gfull_bar), gempty0 = smem_u32(gempty_bar);
+    if (lane == 0) {
+      const uint32_t bres = smem_u32(bres_bar);
+      mbar_expect_tx_a(bres, kTailIdentBytes);
+      tma_load_2d_a(smem_u32(smem_i), &tmI, bres, 0, 0);
+    }
+    int gs = 0;
+    uint32_t gph = 0;
+    auto put = [&](const CUtensorMap* m, int x, int y) {
+      mbar_wait_a(gempty0 + gs * 8, gph ^ 1u, p.watchdog, 300 + gs);
+      if (elect_one()) {
+        mbar_expect_tx_a(gfull0 + gs * 8, kTailSlabBytes);
+        tma_load_2d_a(g0 + static_cast<uint32_t>(gs * kTailSlabBytes), m, gfull0 + gs * 8, x, y);
+      }
+      __syncwarp();
+      if (++gs == p.gring) { gs = 0; gph ^= 1; }
+    };
+    for (int t = 0; t < my_tiles; ++t) {
+      const int m0 = (static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x)) * kBM;
+      for (int h = 0; h < 2; ++h) {
+        for (int kb = 0; kb < 2; ++kb) {
+          put(&tmA, kb * kBK, m0);
+          put(&tmW3, kb * kBK, h * kTailN1);
+          put(&tmW3, kb * kBK, h * kTailN1 + 128);
+        }
+        for (int rs = 0; rs < 4; ++rs) put(&tmR, h * kTailN1 + rs * kTailSlab, m0);
+      }
+    }
+  } else {
+    // ================================================================ W producer
+    const uint32_t w0 = smem_u32(smem_w);
+    const uint32_t wfull0 = smem_u32(wfull_bar), wempty0 = smem_u32(wempty_bar);
+    int ws = 0;
+    uint32_t wph = 0;
+    for (int t = 0; t < my_tiles; ++t)
+      for (int kb = 0; kb < 8; ++kb) {
+        mbar_wait_a(wempty0 + ws * 8, wph ^ 1u, p.watchdog, 320 + ws);
+        if (elect_one()) {
+          mbar_expect_tx_a(wfull0 + ws * 8, kTailSlabBytes);
+          tma_load_2d_a(w0 + static_cast<uint32_t>(ws * kTailSlabBytes), &tmW1, wfull0 + ws * 8, kb * kBK, 0);
+        }
+        __syncwarp();
+        if (++ws == p.wring) { ws = 0; wph ^= 1; }
+      }
+  }
+
+  // -------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem_base, 512);
+  }
+}
+
+bool conv_tail2_applicable(const ConvLayer& L3, const ConvLayer& L1) {
+  auto lin = [](const ConvLayer& L) { return L.kh == 1 && L.kw == 1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0 && !L.special; };
+  return lin(L3) && lin(L1) && L3.Cout == kTail2N1 && L3.Cout_pad == kTail2N1 && L3.Cin == kTail2K1 && L3.K_pad == kTail2K1 &&
+         L1.Cin == kTail2N1 && L1.K_pad == kTail2N1 && L1.Cout == kTail2N2 && L1.Cout_pad == kTail2N2 && L3.act_kind == 1 &&
+         L1.act_kind == 1;
+}
+
+int conv_tail2_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
+                      const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream) {
+  if (!conv_tail2_applicable(L3, L1)) return set_err(ctx, FRB_ERR_INVALID, "conv_tail2: layer pair not supported");
+  if (M <= 0 || M > 0x7fffffffLL) return set_err(ctx, FRB_ERR_INVALID, "conv_tail2: bad problem size");
+  const void* ptrs[4] = {in, res, out1, out2};
+  const int lds[4] = {in_ld, res_ld, out1_ld, out2_ld};
+  for (int i = 0; i < 4; ++i)
+    if ((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) != 0 || (lds[i] % 8) != 0)
+      return set_err(ctx, FRB_ERR_INVALID, "conv_tail2: operands must be 16-byte aligned with a pixel stride that is a multiple of 8");
+  ConvTail2Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = static_cast<int>(M);
+  a.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  a.bias1 = L3.d_bias;
+  a.bias2 = L1.d_bias;
+  a.watchdog = ctx->wd_dev;
+  const int fixed = kTailIdentBytes + 62 * 8 + (kTail2N1 + kTail2N2) * 4 + 1024;
+  const int units = (227 * 1024 - fixed) / kTailSlabBytes;               // 13
+  // the G ring is what hides the load latency (20 units per tile): measured per launch with 7 / 6 / 5 units 1.30 / 1.36 / 1.52 ms
+  a.slots = 4;
+  a.wring = 2;
+  a.gring = std::min(8, units - a.slots - a.wring);
+  if (const char* e = getenv("FRB_TAIL2_SPLIT")) {                       // tuning experiment: "SLOTSxWRING"
+    int sl = 4, wr = 3;
+    if (sscanf(e, "%dx%d", &sl, &wr) == 2 && sl >= 4 && sl <= 8 && wr >= 2 && wr <= 4 && units - sl - wr >= 4) {
+      a.slots = sl; a.wring = wr; a.gring = std::min(8, units - sl - wr);
+    }
+  }
+  if (a.gring < 4) return set_err(ctx, FRB_ERR_INVALID, "conv_tail2: shared-memory plan does not fit");
+  const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.gring + a.wring + a.slots) * kTailSlabBytes;
+
+  void* ident = nullptr;
+  int rc = ctx_identity(ctx, &ident);
+  if (rc != FRB_OK) return rc;
+  CUtensorMap tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI;
+  if ((rc = encode_2d(ctx, &tmA, in, kTail2K1, M, static_cast<uint64_t>(in_ld) * 2, kBK, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmR, res, kTail2N1, M, static_cast<uint64_t>(res_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmO1, out1, kTail2N1, M, static_cast<uint64_t>(out1_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmO2, out2, kTail2N2, M, static_cast<uint64_t>(out2_ld) * 2, kTailSlab, kBM)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmW3, L3.d_w, L3.K_pad, L3.Cout_pad, static_cast<uint64_t>(L3.K_pad) * 2, kBK, 128)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmW1, L1.d_w, L1.K_pad, L1.Cout_pad, static_cast<uint64_t>(L1.K_pad) * 2, kBK, 128)) != FRB_OK) return rc;
+  if ((rc = encode_2d(ctx, &tmI, ident, 64, 64, 128, 64, 64)) != FRB_OK) return rc;
+
+  const int grid = std::min(a.m_tiles, ctx->num_sms);
+  if (ctx->use_bf16) {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tail2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_tail2_kernel<true><<<grid, kTail2Threads, smem, stream>>>(a, tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI);
+  } else {
+    FRB_CUDA(ctx, cudaFuncSetAttribute(conv_tail2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_tail2_kernel<false><<<grid, kTail2Threads, smem, stream>>>(a, tmA, tmR, tmO1, tmO2, tmW3, tmW1, tmI);
+  }
+  ctx->launches++;
+  return check_last(ctx, "conv_tail2_kernel launch");
 }
 
 // Which pairs of layers the fused kernel takes: conv3 (1x1, Cin 64 or 128 -> 256, ReLU after the skip) followed by the next

@@ -602,6 +602,12 @@ int frb_set_option(frb_ctx* ctx, int option, int value) {
     case FRB_OPT_WEIGHT_SLICE: ctx->weight_slice = value; return FRB_OK;
     case FRB_OPT_GRAPHS: ctx->graphs = value ? 1 : 0; return FRB_OK;
     case FRB_OPT_CTA2: ctx->cta2 = value ? 1 : 0; return FRB_OK;
+    case FRB_OPT_FUSE_TAIL2:
+      if (ctx->fuse_tail2 != (value ? 1 : 0)) {
+        ctx->fuse_tail2 = value ? 1 : 0;
+        for (auto& kv : ctx->nets) net_drop_plans(kv.second);
+      }
+      return FRB_OK;
     case FRB_OPT_FUSE_POOL:
       if (ctx->fuse_pool != (value ? 1 : 0)) {
         ctx->fuse_pool = value ? 1 : 0;

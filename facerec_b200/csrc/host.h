@@ -47,6 +47,7 @@ struct frb_ctx {
   int cta2 = 1;                // FRB_OPT_CTA2: CTA pairs (cta_group::2) for per-tap / linear convs with streamed weights
   int graphs = 0;              // FRB_OPT_GRAPHS: short forwards (InceptionResnetV1, MobileNet RetinaFace at small sizes) replay a CUDA graph
   int fuse_tail = 3;           // FRB_OPT_FUSE_TAIL: layer1 of R50 runs conv3 + skip and the next block's conv1 as one launch (conv_tail.cu)
+  int fuse_tail2 = 1;          // FRB_OPT_FUSE_TAIL2: the same fusion in layer2 (streamed weights, conv_tail2_kernel)
   int fuse_pool = 1;           // FRB_OPT_FUSE_POOL: the ResNet stem's max pool runs in the stem conv's epilogue
   int fuse_dwpw = 1;           // FRB_OPT_FUSE_DWPW: MobileNet blocks (depthwise 3x3 + pointwise 1x1) as one launch where the weights fit
   int halo_mode = 0;           // halo tiles for stride-1 k x k convs: 0 where it pays (see conv_launch_tma), 1 always, -1 never
@@ -141,6 +142,10 @@ bool conv_pool_fusable(frb_ctx* ctx, const ConvLayer& L, int H, int W);
 // With Ld != null the skip is Ld's 1x1 conv of `res` (= its input x) computed inside, bias1 = conv3's bias + Ld's.
 bool conv_tail_applicable(const ConvLayer& L3, const ConvLayer& L1);
 bool conv_tail_skip_applicable(const ConvLayer& Ld);
+// K2t2: the same for layer2 (conv3 128 -> 512 + skip, next conv1 512 -> 128; both weight matrices streamed)
+bool conv_tail2_applicable(const ConvLayer& L3, const ConvLayer& L1);
+int conv_tail2_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
+                      const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, cudaStream_t stream);
 int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, const void* in, int in_ld, long long M,
                      const void* res, int res_ld, void* out1, int out1_ld, void* out2, int out2_ld, const ConvLayer* Ld,
                      const float* bias1, cudaStream_t stream);

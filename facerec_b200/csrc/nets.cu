@@ -544,7 +544,8 @@ static void plan_retina(Net* net, Plan& plan, bool r50) {
         const bool last = i + 1 == kR50Blocks[l];
         const std::string pn = last ? sfmt("layer%d.0", l + 2) : sfmt("layer%d.%d", l + 1, i + 1);
         const bool fuse = net->ctx->fuse_tail && !(last && l == 3) && !(net->ctx->fuse_tail == 2 && last) &&
-                          conv_tail_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")]);
+                          (conv_tail_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")]) ||
+                           (net->ctx->fuse_tail2 && conv_tail2_applicable(net->convs[b.layer(p + ".conv3")], net->convs[b.layer(pn + ".conv1")])));
         // FRB_OPT_FUSE_TAIL = 3: the skip conv of the layer's first block is computed inside the fused tail as well
         const bool fuse_skip = fuse && i == 0 && net->ctx->fuse_tail == 3 && net->convs[b.layer(p + ".conv3")].d_bias_skip != nullptr &&
                                conv_tail_skip_applicable(net->convs[b.layer(p + ".down")]);
@@ -823,6 +824,11 @@ static int run_plan(frb_ctx* ctx, Net* net, const Plan& plan, const ExecPtrs& ep
       }
       case OP_CONV_TAIL: {
         const TensorInfo& tr = plan.tensors[op.res.t];
+        if (conv_tail2_applicable(net->convs[op.layer], net->convs[op.layer2]))
+          rc = conv_tail2_launch(ctx, net->convs[op.layer], net->convs[op.layer2], base(op.in), ti.C,
+                                 static_cast<long long>(plan.B) * ti.H * ti.W, base(op.res), tr.C, base(op.out),
+                                 plan.tensors[op.out.t].C, base(op.out2), plan.tensors[op.out2.t].C, st);
+        else
         rc = conv_tail_launch(ctx, net->convs[op.layer], net->convs[op.layer2], base(op.in), ti.C,
                               static_cast<long long>(plan.B) * ti.H * ti.W, base(op.res), tr.C, base(op.out),
                               plan.tensors[op.out.t].C, base(op.out2), plan.tensors[op.out2.t].C,

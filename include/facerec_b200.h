@@ -71,6 +71,8 @@ enum frb_option {
                            /* 2: as 1, but not across the layer1 -> layer2 edge; 3 (default): as 1, and the 1x1 skip conv of          */
                            /* layer1's first block is computed inside that launch too (its output is never rounded to 16 bits, so     */
                            /* results differ from 0 by that one rounding)                                                           */
+  FRB_OPT_FUSE_TAIL2 = 18, /* 0: FRB_OPT_FUSE_TAIL stops at layer1 (default 1: layer2's conv3 + skip -> next conv1 pairs are fused as well,     */
+                           /* with both weight matrices streamed; same bits)                                                            */
   FRB_OPT_FUSE_POOL = 17,  /* 0: the ResNet-50 stem and its 3x3 / stride 2 max pool are two launches (default 1: the pool runs in the stem's  */
                            /* epilogue, the stem output is never stored; the pooled tensor has the same bits)                            */
   FRB_OPT_FUSE_DWPW = 16,  /* 0: depthwise and pointwise convs of RetinaFace-MobileNet0.25 are separate launches; 1 (default): one launch */

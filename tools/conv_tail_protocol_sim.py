@@ -229,3 +229,214 @@ if __name__ == "__main__":
         print("FAIL (N2/64, slots, ring, tiles, seed) =", cfg, detail)
     print(f"{len(bad)} failing configurations")
     sys.exit(1 if bad else 0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# conv_tail2_kernel (layer2: 512 output channels of conv3 as two halves of 256, both weight matrices streamed)
+def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
+    """Per tile: halves h = 0, 1.  G1(t, h): 10 G-ring units (per k-block: a, W3 rows 0-127, W3 rows 128-255; then 4 skip
+    slabs) into buffer X_t = t & 1 (h = 0) or Y_t = 1 - X_t (h = 1).  Items per tile: e1(h0) x 4, e1(h1) x 4, e2 x 2.
+    M2(t, h): 4 slabs x one W-ring unit each, accumulating into columns [0, 128) of X_t.  Buffer Y_t is free once e1(t, h1)
+    has drained it (16 warp arrivals), X_t once e2(t) has (8 warp arrivals)."""
+    rnd = random.Random(seed)
+    ipt = 10
+    gfull = [Bar(1) for _ in range(8)]
+    gempty = [Bar(1) for _ in range(8)]
+    wfull = [Bar(1) for _ in range(8)]
+    wempty = [Bar(1) for _ in range(8)]
+    slabw = [Bar(1) for _ in range(8)]
+    sfree = [Bar(2) for _ in range(8)]
+    swr = [Bar(1) for _ in range(8)]
+    turn = [Bar(1) for _ in range(groups)]
+    acc1 = [Bar(1), Bar(1)]
+    acc2 = [Bar(1), Bar(1)]
+    free_e1 = [Bar(16), Bar(16)]               # buffer drained by the four e1 items of a second half
+    free_e2 = [Bar(8), Bar(8)]                 # buffer drained by the two e2 items
+    pending = []
+
+    def later(fn):
+        pending.append(fn)
+
+    def check(cond, *what):
+        if not cond:
+            raise ProtocolError(what)
+
+    def epilogue(g):
+        q = g
+        while q < my_tiles * ipt:
+            t, j = divmod(q, ipt)
+            slot, use = q % slots, q // slots
+            X = t & 1
+            second = j >= 8
+            h = 0 if j < 4 else 1
+            buf = X if (second or h == 0) else 1 - X
+            if q >= 1:
+                pg, pn = (g + groups - 1) % groups, (q - 1) // groups
+                while not turn[pg].test(pn & 1):
+                    yield ("turn", pg, q)
+                check(turn[pg].phase == pn + 1, "turn barrier aliased", q)
+            while not sfree[slot].test((use & 1) ^ 1):
+                yield ("slot free", slot, q)
+            check(sfree[slot].phase == use, "slot-free barrier aliased", q)
+            turn[g].arrive()
+            if second:
+                b, want = acc2[buf], (t >> 1)
+            else:
+                b, want = acc1[buf], t                     # every buffer is filled once per tile
+            while not b.test(want & 1):
+                yield ("accumulator", buf, q)
+            check(b.phase == want + 1, "accumulator barrier aliased", q, b.phase, want)
+            if second:
+                for _ in range(4):
+                    free_e2[buf].arrive()
+            elif h == 1:
+                for _ in range(4):
+                    free_e1[buf].arrive()
+            yield ("work", q)
+            if not second:
+                slabw[slot].arrive()
+            swr[slot].arrive()
+            q += groups
+
+    def storer():
+        inflight = []
+        for q in range(my_tiles * ipt):
+            slot, use, second = q % slots, q // slots, (q % ipt) >= 8
+            while not swr[slot].test(use & 1):
+                yield ("slab staged", slot, q)
+            check(swr[slot].phase == use + 1, "slab-staged barrier aliased", q)
+            done = [False]
+            later(lambda d=done: d.__setitem__(0, True))
+            inflight.append((slot, second, done))
+            while len(inflight) > lag:
+                pslot, psecond, pdone = inflight.pop(0)
+                while not pdone[0]:
+                    yield ("store drain", pslot)
+                sfree[pslot].arrive()
+                if psecond:
+                    sfree[pslot].arrive()
+        for pslot, psecond, pdone in inflight:
+            while not pdone[0]:
+                yield ("store drain", pslot)
+            sfree[pslot].arrive()
+            if psecond:
+                sfree[pslot].arrive()
+
+    def issuer():
+        st = {"g": 0, "gp": 0, "w": 0, "wp": 0, "slot": 0}
+        e1n = [0] * 8
+
+        def g1(t, h):
+            X = t & 1
+            buf = X if h == 0 else 1 - X
+            if t >= 1:
+                k = (t - 1) >> 1
+                b = free_e1[buf] if h == 0 else free_e2[buf]
+                while not b.test(k & 1):
+                    yield ("buffer free", buf, t, h)
+                check(b.phase == k + 1, "buffer-free barrier aliased", t, h, b.phase, k)
+            for i in range(10):
+                s = st["g"]
+                while not gfull[s].test(st["gp"]):
+                    yield ("G ring full", s)
+                later(lambda s=s: gempty[s].arrive())
+                if i == 9:
+                    later(lambda b=buf: acc1[b].arrive())
+                st["g"] += 1
+                if st["g"] == gring:
+                    st["g"], st["gp"] = 0, st["gp"] ^ 1
+
+        def m2(t, h):
+            X = t & 1
+            for s in range(4):
+                x = st["slot"]
+                while not slabw[x].test(e1n[x] & 1):
+                    yield ("slab written", x, t, h, s)
+                check(slabw[x].phase == e1n[x] + 1, "slab-written barrier aliased", t, h, s)
+                if s == 0 and h == 0:
+                    x1 = 0 if x + 1 == slots else x + 1
+                    while not slabw[x1].test(e1n[x1] & 1):
+                        yield ("slab written", x1, t, h, 1)
+                    check(slabw[x1].phase == e1n[x1] + 1, "slab-written barrier aliased", t, h, 1)
+                ws = st["w"]
+                while not wfull[ws].test(st["wp"]):
+                    yield ("W ring full", ws)
+                later(lambda ws=ws: wempty[ws].arrive())
+                st["w"] += 1
+                if st["w"] == wring:
+                    st["w"], st["wp"] = 0, st["wp"] ^ 1
+                later(lambda x=x: sfree[x].arrive())
+                if s == 3 and h == 1:
+                    later(lambda b=X: acc2[b].arrive())
+                e1n[x] += 1
+                st["slot"] = 0 if x + 1 == slots else x + 1
+            if h == 1:
+                for _ in range(2):
+                    st["slot"] = 0 if st["slot"] + 1 == slots else st["slot"] + 1
+
+        if my_tiles > 0:
+            yield from g1(0, 0)
+            yield from g1(0, 1)
+        for t in range(my_tiles):
+            yield from m2(t, 0)
+            if t + 1 < my_tiles:
+                yield from g1(t + 1, 0)
+            yield from m2(t, 1)
+            if t + 1 < my_tiles:
+                yield from g1(t + 1, 1)
+
+    def producer(full, empty, depth, per_tile):
+        stage = phase = 0
+        for _ in range(my_tiles * per_tile):
+            while not empty[stage].test(phase ^ 1):
+                yield ("ring empty", stage)
+            later(lambda s=stage: full[s].arrive())
+            stage += 1
+            if stage == depth:
+                stage, phase = 0, phase ^ 1
+
+    agents = {f"epilogue {g}": epilogue(g) for g in range(groups)}
+    agents["issuer"] = issuer()
+    agents["store warp"] = storer()
+    agents["G producer"] = producer(gfull, gempty, gring, 20)
+    agents["W producer"] = producer(wfull, wempty, wring, 8)
+    state, idle = {}, 0
+    try:
+        while agents:
+            progressed = False
+            names = list(agents)
+            rnd.shuffle(names)
+            for n in names:
+                try:
+                    w = next(agents[n])
+                    if state.get(n) != w or w[0] == "work":
+                        progressed = True
+                    state[n] = w
+                except StopIteration:
+                    del agents[n]
+                    state.pop(n, None)
+                    progressed = True
+            if pending:
+                k = rnd.randint(1, len(pending))
+                for fn in pending[:k]:
+                    fn()
+                del pending[:k]
+                progressed = True
+            idle = 0 if progressed else idle + 1
+            if idle > 3:
+                return False, ("deadlock", dict(state))
+    except ProtocolError as e:
+        return False, e.args[0]
+    return True, None
+
+
+def sweep2(seeds=30, tiles=(1, 2, 3, 4, 7, 30)):
+    failures = []
+    for slots, gring, wring in ((3, 6, 3), (3, 5, 2), (4, 6, 3), (2, 7, 3), (5, 4, 2)):
+        for n in tiles:
+            for seed in range(seeds):
+                ok, detail = run2(n, slots, gring, wring, seed=seed, lag=min(seed % 3, slots - 1))
+                if not ok:
+                    failures.append(((slots, gring, wring, n, seed), detail))
+                    break
+    return failures

@@ -37,6 +37,8 @@ def main():
         ctx.set_option(_lib.FRB_OPT_CTA2, int(os.environ["FRB_CTA2"]))
     if os.environ.get("FRB_FUSE"):
         ctx.set_option(_lib.FRB_OPT_FUSE_TAIL, int(os.environ["FRB_FUSE"]))
+    if os.environ.get("FRB_TAIL2"):
+        ctx.set_option(_lib.FRB_OPT_FUSE_TAIL2, int(os.environ["FRB_TAIL2"]))
     if os.environ.get("FRB_POOL"):
         ctx.set_option(_lib.FRB_OPT_FUSE_POOL, int(os.environ["FRB_POOL"]))
     if os.environ.get("FRB_DWPW"):
