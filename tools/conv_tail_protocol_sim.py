@@ -223,14 +223,6 @@ def sweep(in_order=True, seeds=40, tiles=(1, 2, 3, 5, 12, 57)):
     return failures
 
 
-if __name__ == "__main__":
-    bad = sweep(in_order="--no-turn" not in sys.argv)
-    for cfg, detail in bad:
-        print("FAIL (N2/64, slots, ring, tiles, seed) =", cfg, detail)
-    print(f"{len(bad)} failing configurations")
-    sys.exit(1 if bad else 0)
-
-
 # ----------------------------------------------------------------------------------------------------------------------
 # conv_tail2_kernel (layer2: 512 output channels of conv3 as two halves of 256, both weight matrices streamed)
 def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
@@ -432,7 +424,7 @@ def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
 
 def sweep2(seeds=30, tiles=(1, 2, 3, 4, 7, 30)):
     failures = []
-    for slots, gring, wring in ((3, 6, 3), (3, 5, 2), (4, 6, 3), (2, 7, 3), (5, 4, 2)):
+    for slots, gring, wring in ((4, 7, 2), (4, 6, 3), (4, 5, 3), (5, 5, 3), (6, 4, 2), (8, 3, 2)):
         for n in tiles:
             for seed in range(seeds):
                 ok, detail = run2(n, slots, gring, wring, seed=seed, lag=min(seed % 3, slots - 1))
@@ -440,3 +432,11 @@ def sweep2(seeds=30, tiles=(1, 2, 3, 4, 7, 30)):
                     failures.append(((slots, gring, wring, n, seed), detail))
                     break
     return failures
+
+
+if __name__ == "__main__":
+    bad = sweep(in_order="--no-turn" not in sys.argv) + sweep2()
+    for cfg, detail in bad:
+        print("FAIL (N2/64, slots, ring, tiles, seed) =", cfg, detail)
+    print(f"{len(bad)} failing configurations")
+    sys.exit(1 if bad else 0)
