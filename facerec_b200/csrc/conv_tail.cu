@@ -386,14 +386,14 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
 //   W ring (16 KB units, W producer)   the eight 64-wide k-blocks of the next conv1's weights [128 x 512], 8 per tile
 //   issuer    G1(t, h): acc1 = a x W3_h (two N = 128 MMAs per k16 step) + skip slabs x I, into buffer X_t = t & 1 for
 //             h = 0 and Y_t = 1 - X_t for h = 1;  M2(t, h): columns [0, 128) of X_t (+)= staged slab x W1n k-block, slabs in
-//             channel order over both halves.  Order: M2(t,0); G1(t+1,0); M2(t,1); G1(t+1,1).
+//             channel order over both halves.  G1 and M2 have an issuer warp each.
 //   epilogue  ten items per tile: e1 of half 0 (4 slabs), e1 of half 1 (4), e2 (2 slabs of the 128 conv1 channels).
 //             Y_t is free for G1(t+1, 0) once e1(t, 1) has drained it, X_t for G1(t+1, 1) once e2(t) has.
 //   store warp as in K2t.
-// At least four slab slots: G1(t+1, 0) waits for all four e1 items of half 1, whose fourth needs the slot of an item that only
-// M2(t, 0) frees (with three slots it would be one of half 1 itself, freed by M2(t, 1) AFTER G1(t+1, 0): the deadlock
-// tools/conv_tail_protocol_sim.py run2 finds).  Accumulation orders are those of the separate launches: same bits.
-constexpr int kTail2Threads = (kTailEpiWarps + 4) * 32;    // + MMA issuer, G producer, store warp, W producer
+// (With ONE issuer walking M2(t,0); G1(t+1,0); M2(t,1); G1(t+1,1) three slab slots deadlock - G1(t+1, 0) waits for all four e1
+// items of half 1, whose fourth then needs a slot that only M2(t, 1) frees - which tools/conv_tail_protocol_sim.py found
+// before the GPU did.)  Accumulation orders are those of the separate launches: same bits.
+constexpr int kTail2Threads = (kTailEpiWarps + 5) * 32;    // + G1 issuer, G producer, store warp, W producer, M2 issuer
 constexpr int kTail2N1 = 512, kTail2K1 = 128, kTail2N2 = 128;
 constexpr int kTail2Ipt = 10;                              // epilogue items per tile
 
@@ -440,7 +440,8 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = kTailEpiWarps, kGWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2, kWWarp = kTailEpiWarps + 3;
+  constexpr int kMmaWarp = kTailEpiWarps, kGWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2, kWWarp = kTailEpiWarps + 3,
+                kM2Warp = kTailEpiWarps + 4;
   const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == kGWarp && lane == 0) {
@@ -588,18 +589,16 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
       tma_store_wait<0>();
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================ MMA issuer
+    // ================================================================ G1 issuer
     const uint32_t idesc_h = make_idesc_f16(kBM, 128, kBF16 ? 1 : 0);
     const uint32_t idesc_r = make_idesc_f16(kBM, kTailSlab, kBF16 ? 1 : 0);
     const uint32_t hi = desc_hi(1024);
-    const uint32_t g_lo = desc_lo(smem_u32(smem_g)), w_lo = desc_lo(smem_u32(smem_w)), slot_lo = desc_lo(smem_u32(smem_slot)),
-                   id_lo = desc_lo(smem_u32(smem_i));
+    const uint32_t g_lo = desc_lo(smem_u32(smem_g)), id_lo = desc_lo(smem_u32(smem_i));
     const uint32_t step = kTailSlabBytes >> 4;
-    const uint32_t gfull0 = smem_u32(gfull_bar), gempty0 = smem_u32(gempty_bar), wfull0 = smem_u32(wfull_bar), wempty0 = smem_u32(wempty_bar),
-                   slabw0 = smem_u32(slabw_bar), sfree0 = smem_u32(sfree_bar), acc10 = smem_u32(acc1_bar), acc20 = smem_u32(acc2_bar),
+    const uint32_t gfull0 = smem_u32(gfull_bar), gempty0 = smem_u32(gempty_bar), acc10 = smem_u32(acc1_bar),
                    free10 = smem_u32(free1_bar), free20 = smem_u32(free2_bar);
-    int gs = 0, ws = 0;
-    uint32_t gph = 0, wph = 0;
+    int gs = 0;
+    uint32_t gph = 0;
     mbar_wait(bres_bar, 0, p.watchdog, 250);
     auto mma4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc0) {
       tc_mma_f16(d, pack_desc(a, hi), pack_desc(b, hi), idesc, acc0);
@@ -647,6 +646,33 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
         __syncwarp();
       }
     };
+    if (my_tiles > 0) {
+      issue_g1(0, 0);
+      issue_g1(0, 1);
+    }
+    for (int t = 1; t < my_tiles; ++t) {
+      issue_g1(t, 0);
+      issue_g1(t, 1);
+    }
+  } else if (warp == kM2Warp) {
+    // ================================================================ M2 issuer
+    // A warp of its own: a G1 that waits for its loads (the G ring turns over three times per tile) must not hold up the
+    // M2 MMAs of slabs that are ready, and with them e2 and the hand-over of the buffer the next G1 needs.  What orders the
+    // two issuers' MMAs on a TMEM buffer are the barriers (slab written, buffer drained), never program order.
+    const uint32_t idesc_h = make_idesc_f16(kBM, 128, kBF16 ? 1 : 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t w_lo = desc_lo(smem_u32(smem_w)), slot_lo = desc_lo(smem_u32(smem_slot));
+    const uint32_t step = kTailSlabBytes >> 4;
+    const uint32_t wfull0 = smem_u32(wfull_bar), wempty0 = smem_u32(wempty_bar), slabw0 = smem_u32(slabw_bar), sfree0 = smem_u32(sfree_bar),
+                   acc20 = smem_u32(acc2_bar);
+    int ws = 0;
+    uint32_t wph = 0;
+    auto mma4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc0) {
+      tc_mma_f16(d, pack_desc(a, hi), pack_desc(b, hi), idesc, acc0);
+      tc_mma_f16(d, pack_desc(a + 2, hi), pack_desc(b + 2, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 4, hi), pack_desc(b + 4, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 6, hi), pack_desc(b + 6, hi), idesc, 1u);
+    };
     int slot = 0;
     uint32_t e1par = 0;
     auto issue_m2 = [&](int t, int h) {
@@ -675,15 +701,9 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
         for (int e = 0; e < 2; ++e)
           if (++slot == p.slots) slot = 0;
     };
-    if (my_tiles > 0) {
-      issue_g1(0, 0);
-      issue_g1(0, 1);
-    }
     for (int t = 0; t < my_tiles; ++t) {
       issue_m2(t, 0);
-      if (t + 1 < my_tiles) issue_g1(t + 1, 0);
       issue_m2(t, 1);
-      if (t + 1 < my_tiles) issue_g1(t + 1, 1);
     }
   } else if (warp == kGWarp) {
     // ================================================================ G producer
@@ -774,7 +794,7 @@ int conv_tail2_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, co
   a.gring = std::min(8, units - a.slots - a.wring);
   if (const char* e = getenv("FRB_TAIL2_SPLIT")) {                       // tuning experiment: "SLOTSxWRING"
     int sl = 4, wr = 3;
-    if (sscanf(e, "%dx%d", &sl, &wr) == 2 && sl >= 4 && sl <= 8 && wr >= 2 && wr <= 4 && units - sl - wr >= 4) {
+    if (sscanf(e, "%dx%d", &sl, &wr) == 2 && sl >= 2 && sl <= 8 && wr >= 2 && wr <= 4 && units - sl - wr >= 4) {
       a.slots = sl; a.wring = wr; a.gring = std::min(8, units - sl - wr);
     }
   }

@@ -351,7 +351,5 @@ def test_conv_tail_barrier_protocol_has_no_deadlock_or_parity_aliasing():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import conv_tail_protocol_sim as sim
     assert sim.sweep(in_order=True, seeds=15) == []
-    assert sim.sweep2(seeds=12) == []                      # layer2 variant (two halves per tile, two load rings)
-    ok, detail = sim.run2(4, 3, 6, 3)                       # ... which needs at least four slab slots
-    assert not ok and "deadlock" in str(detail)
+    assert sim.sweep2(seeds=12) == []                      # layer2 variant (two halves per tile, two load rings, two issuers)
     assert any("aliased" in str(d) or "deadlock" in str(d) for _, d in sim.sweep(in_order=False, seeds=15))

@@ -314,7 +314,7 @@ def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
             if psecond:
                 sfree[pslot].arrive()
 
-    def issuer():
+    def issuer(which):                         # the G1 issuer and the M2 issuer are warps of their own
         st = {"g": 0, "gp": 0, "w": 0, "wp": 0, "slot": 0}
         e1n = [0] * 8
 
@@ -366,16 +366,14 @@ def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
                 for _ in range(2):
                     st["slot"] = 0 if st["slot"] + 1 == slots else st["slot"] + 1
 
-        if my_tiles > 0:
-            yield from g1(0, 0)
-            yield from g1(0, 1)
-        for t in range(my_tiles):
-            yield from m2(t, 0)
-            if t + 1 < my_tiles:
-                yield from g1(t + 1, 0)
-            yield from m2(t, 1)
-            if t + 1 < my_tiles:
-                yield from g1(t + 1, 1)
+        if which == "g1":
+            for t in range(my_tiles):
+                yield from g1(t, 0)
+                yield from g1(t, 1)
+        else:
+            for t in range(my_tiles):
+                yield from m2(t, 0)
+                yield from m2(t, 1)
 
     def producer(full, empty, depth, per_tile):
         stage = phase = 0
@@ -388,7 +386,8 @@ def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
                 stage, phase = 0, phase ^ 1
 
     agents = {f"epilogue {g}": epilogue(g) for g in range(groups)}
-    agents["issuer"] = issuer()
+    agents["G1 issuer"] = issuer("g1")
+    agents["M2 issuer"] = issuer("m2")
     agents["store warp"] = storer()
     agents["G producer"] = producer(gfull, gempty, gring, 20)
     agents["W producer"] = producer(wfull, wempty, wring, 8)
@@ -424,7 +423,7 @@ def run2(my_tiles, slots, gring, wring, groups=3, seed=0, lag=1):
 
 def sweep2(seeds=30, tiles=(1, 2, 3, 4, 7, 30)):
     failures = []
-    for slots, gring, wring in ((4, 7, 2), (4, 6, 3), (4, 5, 3), (5, 5, 3), (6, 4, 2), (8, 3, 2)):
+    for slots, gring, wring in ((3, 8, 2), (2, 8, 3), (4, 7, 2), (4, 6, 3), (4, 5, 3), (5, 5, 3), (6, 4, 2), (8, 3, 2)):
         for n in tiles:
             for seed in range(seeds):
                 ok, detail = run2(n, slots, gring, wring, seed=seed, lag=min(seed % 3, slots - 1))
