@@ -36,7 +36,7 @@ namespace frb {
 
 constexpr int kTailEpiWarps = 12;
 constexpr int kTailGroups = kTailEpiWarps / 4;
-constexpr int kTailThreads = (kTailEpiWarps + 3) * 32;     // + MMA issuer + TMA producer + store warp
+constexpr int kTailThreads = (kTailEpiWarps + 4) * 32;     // + G1 issuer + TMA producer + store warp + M2 issuer
 constexpr int kTailN1 = 256;                               // conv3 output channels = one MMA N
 constexpr int kTailSlab = 64;
 constexpr int kTailSlabBytes = kBM * kTailSlab * 2;        // 16 KB: one A box, one skip slab, one output slab
@@ -89,7 +89,7 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = kTailEpiWarps, kTmaWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2;
+  constexpr int kMmaWarp = kTailEpiWarps, kTmaWarp = kTailEpiWarps + 1, kStoreWarp = kTailEpiWarps + 2, kM2Warp = kTailEpiWarps + 3;
   const int ns2 = p.N2 / kTailSlab;
   const int ipt = 4 + ns2;                                           // epilogue items per tile
   const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -242,16 +242,14 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
       tma_store_wait<0>();                     // stores must land before the CTA (and its smem) goes away
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================ MMA issuer
+    // ================================================================ G1 issuer
     const uint32_t idesc1 = make_idesc_f16(kBM, kTailN1, kBF16 ? 1 : 0);
     const uint32_t idesc_r = make_idesc_f16(kBM, kTailSlab, kBF16 ? 1 : 0);
-    const uint32_t idesc2 = make_idesc_f16(kBM, p.N2, kBF16 ? 1 : 0);
     const uint32_t hi = desc_hi(1024);
-    const uint32_t ring_lo = desc_lo(smem_u32(smem_ring)), slot_lo = desc_lo(smem_u32(smem_slot));
-    const uint32_t w3_lo = desc_lo(smem_u32(smem_w3)), w1_lo = desc_lo(smem_u32(smem_w1)), id_lo = desc_lo(smem_u32(smem_i));
+    const uint32_t ring_lo = desc_lo(smem_u32(smem_ring));
+    const uint32_t w3_lo = desc_lo(smem_u32(smem_w3)), id_lo = desc_lo(smem_u32(smem_i));
     const uint32_t step = kTailSlabBytes >> 4;
-    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), slabw0 = smem_u32(slabw_bar),
-                   sfree0 = smem_u32(sfree_bar), acc10 = smem_u32(acc1_bar), acc20 = smem_u32(acc2_bar), afree0 = smem_u32(afree_bar);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), acc10 = smem_u32(acc1_bar), afree0 = smem_u32(afree_bar);
     int stage = 0;
     uint32_t phase = 0;
     mbar_wait(bres_bar, 0, p.watchdog, 250);
@@ -304,6 +302,23 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
         if (++stage == p.ring) { stage = 0; phase ^= 1; }
       }
     };
+    for (int t = 0; t < my_tiles; ++t) issue_g1(t);
+  } else if (warp == kM2Warp) {
+    // ================================================================ M2 issuer (a warp of its own: a G1 that waits for a buffer
+    // or for its loads must not hold up the M2 MMAs of slabs that are staged; barriers, not program order, order the two
+    // issuers' MMAs on a TMEM buffer)
+    const uint32_t idesc2 = make_idesc_f16(kBM, p.N2, kBF16 ? 1 : 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t slot_lo = desc_lo(smem_u32(smem_slot)), w1_lo = desc_lo(smem_u32(smem_w1));
+    const uint32_t step = kTailSlabBytes >> 4;
+    const uint32_t slabw0 = smem_u32(slabw_bar), sfree0 = smem_u32(sfree_bar), acc20 = smem_u32(acc2_bar);
+    mbar_wait(bres_bar, 0, p.watchdog, 251);
+    auto mma4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc0) {
+      tc_mma_f16(d, pack_desc(a, hi), pack_desc(b, hi), idesc, acc0);
+      tc_mma_f16(d, pack_desc(a + 2, hi), pack_desc(b + 2, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 4, hi), pack_desc(b + 4, hi), idesc, 1u);
+      tc_mma_f16(d, pack_desc(a + 6, hi), pack_desc(b + 6, hi), idesc, 1u);
+    };
     int slot = 0;                             // slab slot of the next e1 item M2 consumes
     uint32_t e1par = 0;                       // per slot: parity of the number of e1 slabs consumed from it ("written" phases
                                               // count e1 items only; e2 items share the slots but never arrive there)
@@ -332,12 +347,8 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
       for (int e = 0; e < ns2; ++e)
         if (++slot == p.slots) slot = 0;
     };
-    if (my_tiles > 0) issue_g1(0);
-    for (int t = 0; t < my_tiles; ++t) {
-      if (t + 1 < my_tiles) issue_g1(t + 1);
-      issue_m2(t);
-    }
-  } else {
+    for (int t = 0; t < my_tiles; ++t) issue_m2(t);
+  } else if (warp == kTmaWarp) {
     // ================================================================ TMA producer
     const uint32_t ring0 = smem_u32(smem_ring);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);

@@ -1,6 +1,6 @@
 """Barrier-protocol model of conv_tail_kernel (facerec_b200/csrc/conv_tail.cu), one CTA, no GPU needed.
 
-The kernel's six roles (three epilogue groups, the MMA issuer, the TMA producer, the store warp) talk through mbarriers whose waits tell
+The kernel's seven roles (three epilogue groups, the G1 and M2 issuers, the TMA producer, the store warp) talk through mbarriers whose waits tell
 phases apart BY PARITY ONLY: a waiter that gets two phases ahead of a barrier takes the phase before last for its own and
 either corrupts a buffer or hangs.  This script replays the protocol under random interleavings of the roles and of the
 asynchronous completions (TMA loads, tcgen05.commit arrivals, store drains) and checks at every wait that the barrier is
@@ -116,7 +116,7 @@ def run(my_tiles, ns2, slots, ring, kb1=1, groups=3, seed=0, in_order=True, lag=
             if psecond:
                 sfree[pslot].arrive()
 
-    def issuer():
+    def issuer(which):                         # G1 and M2 are issued by a warp each
         st = {"stage": 0, "phase": 0, "slot": 0}
         e1n = [0] * 8                          # e1 slabs consumed per slot
 
@@ -156,12 +156,8 @@ def run(my_tiles, ns2, slots, ring, kb1=1, groups=3, seed=0, in_order=True, lag=
             for _ in range(ns2):
                 st["slot"] = 0 if st["slot"] + 1 == slots else st["slot"] + 1
 
-        if my_tiles > 0:
-            yield from g1(0)
         for t in range(my_tiles):
-            if t + 1 < my_tiles:
-                yield from g1(t + 1)
-            yield from m2(t)
+            yield from (g1(t) if which == "g1" else m2(t))
 
     def producer():
         stage = phase = 0
@@ -175,7 +171,8 @@ def run(my_tiles, ns2, slots, ring, kb1=1, groups=3, seed=0, in_order=True, lag=
                     stage, phase = 0, phase ^ 1
 
     agents = {f"epilogue {g}": epilogue(g) for g in range(groups)}
-    agents["issuer"] = issuer()
+    agents["G1 issuer"] = issuer("g1")
+    agents["M2 issuer"] = issuer("m2")
     agents["store warp"] = storer()
     agents["producer"] = producer()
     state, idle = {}, 0
