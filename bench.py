@@ -151,7 +151,8 @@ def cited_traffic(backbone, B, H, W):
     d = json.load(open(p))
     return {"traffic": d["dram_bytes"],
             "traffic_unit": f"bytes per forward, CITED from the ncu launch list {d['source']} ({d['dram_read_bytes'] / 1e9:.1f} GB read + "
-                            f"{d['dram_write_bytes'] / 1e9:.1f} GB written over {d['launches']} launches; algorithmic minimum 2.60 GB/frame x 64 = 166 GB; "
+                            f"{d['dram_write_bytes'] / 1e9:.1f} GB written over {d['launches']} launches; layer-by-layer minimum (every layer output written "
+                            f"and read once, SURVEY App. C) 2.60 GB/frame x 64 = 166 GB: the fused tails / stem pool remove 45 GB of it; "
                             f"L2 -> SM {d['l2_bytes'] / 1e9:.0f} GB; time-weighted tensor-pipe active {d['tensor_pipe_active_pct_time_weighted']:.1f} %)"}
 
 

@@ -24,12 +24,12 @@ def load(path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
-    ap.add_argument("--forward", type=int, default=0, help="the first N conv/maxpool launches after --skip are one forward")
+    ap.add_argument("--forward", type=int, default=0, help="the first N conv / pool launches after --skip are one forward")
     ap.add_argument("--skip", type=int, default=0, help="conv/maxpool launches to skip (warm-up forward)")
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
     by = load(a.csv)
-    fwd = [d for d in by.values() if d["name"].startswith(("conv_", "maxpool"))][a.skip:]
+    fwd = [d for d in by.values() if d["name"].startswith(("conv_", "maxpool", "pool_border"))][a.skip:]
     if a.forward:
         fwd = fwd[:a.forward]
     print(f"{'kernel':42s} {'grid':>14s} {'us':>9s} {'dramR MB':>9s} {'dramW MB':>9s} {'GB/s':>8s} {'L2 MB':>9s} {'tensor%':>8s}")
@@ -47,7 +47,8 @@ def main():
                "dram_write_bytes": sum(d.get("dram__bytes_write.sum", 0.0) for d in fwd),
                "l2_bytes": sum(d.get("lts__t_bytes.sum", 0.0) for d in fwd),
                "tensor_pipe_active_pct_time_weighted": tw,
-               "pair_launches": sum(1 for d in fwd if d["name"].count(",") == 4 and d["name"].rstrip(">").rstrip().endswith("1")),
+               "pair_launches": sum(1 for d in fwd if d["name"].startswith("conv_tma_kernel<") and
+                                    [x.strip() for x in d["name"].split("<")[1].rstrip(">").split(",")][4:5] == ["1"]),
                "kernels": dict(collections.Counter(d["name"].split("<")[0] for d in fwd))}
         out["dram_bytes"] = out["dram_read_bytes"] + out["dram_write_bytes"]
         print(json.dumps(out))
