@@ -250,3 +250,30 @@ def test_fused_stem_max_pool_does_not_change_results(ctx, B, H, W):
     for k in range(3):
         assert torch.isfinite(outs[0][k]).all()
         assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k])
+
+
+def test_fusions_in_bf16_give_the_bits_of_the_separate_launches(ctx):
+    """The fused kernels are templated on the element type: with FRB_OPT_BF16 the bit-preserving fusions (tails at level 1 in
+    layer1 and layer2, stem pool) still reproduce the separate launches exactly, also with several tiles per CTA."""
+    from facerec_b200 import ops, weights, _lib
+    rng = np.random.RandomState(14)
+    B, H, W = 9, 270, 480
+    fr = torch.from_numpy(_frames(rng, B, H, W)).cuda()
+    mid = weights.MODEL_IDS["retina_r50"]
+    c = _lib.Context(0)
+    try:
+        c.set_option(_lib.FRB_OPT_BF16, 1)
+        ops.load_model(c, mid, weights.write_blob(weights.synth_weights("retina_r50", 0)))
+        x16 = ops.preprocess_u8(c, fr, True, ops.input_layout(mid))
+        outs = []
+        for tail, tail2, pool in ((1, 1, 1), (0, 0, 0), (1, 0, 1), (2, 1, 0)):
+            c.set_option(_lib.FRB_OPT_FUSE_TAIL, tail)
+            c.set_option(_lib.FRB_OPT_FUSE_TAIL2, tail2)
+            c.set_option(_lib.FRB_OPT_FUSE_POOL, pool)
+            outs.append([t.clone() for t in ops.retina_forward(c, mid, x16, H, W)])
+    finally:
+        c.close()
+    for o in outs[1:]:
+        for k in range(3):
+            assert torch.isfinite(o[k]).all()
+            assert torch.equal(outs[0][k], o[k])
