@@ -803,12 +803,14 @@ int conv_tail2_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, co
   a.slots = 4;
   a.wring = 2;
   a.gring = std::min(8, units - a.slots - a.wring);
+#ifdef FRB_DEBUG_BUILD
   if (const char* e = getenv("FRB_TAIL2_SPLIT")) {                       // tuning experiment: "SLOTSxWRING"
     int sl = 4, wr = 3;
     if (sscanf(e, "%dx%d", &sl, &wr) == 2 && sl >= 2 && sl <= 8 && wr >= 2 && wr <= 4 && units - sl - wr >= 4) {
       a.slots = sl; a.wring = wr; a.gring = std::min(8, units - sl - wr);
     }
   }
+#endif
   if (a.gring < 4) return set_err(ctx, FRB_ERR_INVALID, "conv_tail2: shared-memory plan does not fit");
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.gring + a.wring + a.slots) * kTailSlabBytes;
 
@@ -883,7 +885,9 @@ int conv_tail_launch(frb_ctx* ctx, const ConvLayer& L3, const ConvLayer& L1, con
   a.slots = units >= 9 ? 4 : 3;
   if (a.kbx) a.slots = units - 4;                                        // two loads per tile: a short ring is enough
   a.ring = std::min(kTailMaxRing, units - a.slots);
+#ifdef FRB_DEBUG_BUILD
   if (const char* e = getenv("FRB_TAIL_RING")) { a.ring = std::max(2, std::min(units - 2, atoi(e))); a.slots = units - a.ring; }   // tuning experiment
+#endif
   a.slots = std::min(kTailMaxSlots, a.slots);
   if (a.ring < 2 || a.slots < 2) return set_err(ctx, FRB_ERR_INVALID, "conv_tail: shared-memory plan does not fit");
   const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(a.ring + a.slots) * kTailSlabBytes;
