@@ -34,7 +34,7 @@
 
 namespace frb {
 
-constexpr int kTailEpiWarps = 12;
+constexpr int kTailEpiWarps = 12;             // (16 = four groups measured no faster: profiles/r02_layer_times_r50_tail2_ab.txt)
 constexpr int kTailGroups = kTailEpiWarps / 4;
 constexpr int kTailThreads = (kTailEpiWarps + 4) * 32;     // + G1 issuer + TMA producer + store warp + M2 issuer
 constexpr int kTailN1 = 256;                               // conv3 output channels = one MMA N
@@ -81,9 +81,9 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
   uint64_t* acc2_bar = bars + 34;                     // [2] M2 complete
   uint64_t* afree_bar = bars + 36;                    // [2] e2 has drained the buffer
   uint64_t* bres_bar = bars + 38;                     // resident operands have landed
-  uint64_t* turn_bar = bars + 39;                     // [3] group g has taken the slab slot of its current item
-  uint64_t* staged_bar = bars + 42;                   // [8] slab slot staged (e1 and e2): the store warp may send it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
+  uint64_t* turn_bar = bars + 39;                     // [kTailGroups <= 4] group g has taken the slab slot of its current item
+  uint64_t* staged_bar = bars + 43;                   // [8] slab slot staged (e1 and e2): the store warp may send it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 51);
   float* s_bias1 = reinterpret_cast<float*>(bars + 52);   // [256]
   float* s_bias2 = s_bias1 + kTailN1;                     // [128]
 
@@ -444,8 +444,8 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
   uint64_t* free1_bar = bars + 52;       // [2] buffer drained by the four e1 items of a second half (16 warps)
   uint64_t* free2_bar = bars + 54;       // [2] buffer drained by the two e2 items (8 warps)
   uint64_t* bres_bar = bars + 56;
-  uint64_t* turn_bar = bars + 57;        // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 60);
+  uint64_t* turn_bar = bars + 57;        // [kTailGroups <= 4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 61);
   float* s_bias1 = reinterpret_cast<float*>(bars + 62);   // [512]
   float* s_bias2 = s_bias1 + kTail2N1;                    // [128]
 
