@@ -21,7 +21,7 @@ device-timed rate, end-to-end rate and roofline, so that the driver's 1/2/4/8-GP
 `e2e`    : the same from pinned HOST frames: every step copies its own 64 frames host -> device (a copy stream prefetches
            step k+1 under step k, as the extractor does) into FacePipeline.step_device and reads detections + embeddings
            back (D2H) inside the timed region.
-`roofline`: the RetinaFace-R50 forward (67 launches: conv_tma_kernel, 3 fused conv_tail_kernel, one zero fill), timed with
+`roofline`: the RetinaFace-R50 forward (64 launches: conv_tma_kernel, 3 + 3 fused conv_tail / conv_tail2 kernels, one zero fill), timed with
            CUDA events on the launching stream inside the timed region; algorithmic work
            449.71 GFLOP/frame x 64 frames per launch of the forward.  `traffic` is not measured by this
            script: it is the dram__bytes sum of the committed ncu launch list of the same forward (profiles/r02_fwd_traffic.json).
@@ -645,8 +645,8 @@ def run_b200(a):
                          "frac": fwd_tflops / peak,
                          **cited_traffic(a.backbone, B, H, W),
                          "kernel": f"one frb_retina_forward over {B} frames = {fwd_launches} launches: conv_tma_kernel (single-CTA and CTA-pair "
-                                   "instantiations; stem with the max pool in its epilogue; heads included), 3 x conv_tail_kernel (layer1: conv3 + skip "
-                                   "+ next conv1 fused) and the zero fill of the pooled tensor's seam positions",
+                                   "instantiations; stem with the max pool in its epilogue; heads included), 3 x conv_tail_kernel + 3 x conv_tail2_kernel "
+                                   "(layer1 / layer2: conv3 + skip + next conv1 fused) and the zero fill of the pooled tensor's seam positions",
                          "algorithmic_gflop_per_frame": gflop, "launch_ms": fwd_ms, "peak_source": peak_src},
         }
         if dist_recs:
