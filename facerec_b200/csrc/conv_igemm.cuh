@@ -85,6 +85,12 @@ struct Elem16<false> {
     __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<uint32_t*>(&h);
   }
+  // relu2(from_f2(a, b)) in one instruction (rounding is monotonic and keeps the sign: same bits for every non-NaN input)
+  static __device__ __forceinline__ uint32_t from_f2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
 };
 template <>
 struct Elem16<true> {
@@ -104,6 +110,11 @@ struct Elem16<true> {
   static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
     __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t from_f2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
 };
 

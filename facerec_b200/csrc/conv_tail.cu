@@ -167,10 +167,10 @@ conv_tail_kernel(const __grid_constant__ ConvTailArgs p, const __grid_constant__
           const float4 b0 = *reinterpret_cast<const float4*>(bias + cc);
           const float4 b1 = *reinterpret_cast<const float4*>(bias + cc + 4);
           uint4 o;
-          o.x = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y));
-          o.y = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w));
-          o.z = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y));
-          o.w = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          o.x = E::from_f2_relu(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y);
+          o.y = E::from_f2_relu(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w);
+          o.z = E::from_f2_relu(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y);
+          o.w = E::from_f2_relu(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w);
           *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(cc >> 3) ^ sw7) << 4)) = o;
         }
       };
@@ -530,10 +530,10 @@ conv_tail2_kernel(const __grid_constant__ ConvTail2Args p, const __grid_constant
           const float4 b0 = *reinterpret_cast<const float4*>(bias + cc);
           const float4 b1 = *reinterpret_cast<const float4*>(bias + cc + 4);
           uint4 o;
-          o.x = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y));
-          o.y = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w));
-          o.z = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y));
-          o.w = E::relu2(E::from_f2(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          o.x = E::from_f2_relu(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y);
+          o.y = E::from_f2_relu(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w);
+          o.z = E::from_f2_relu(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y);
+          o.w = E::from_f2_relu(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w);
           *reinterpret_cast<uint4*>(orow + ((static_cast<uint32_t>(cc >> 3) ^ sw7) << 4)) = o;
         }
       };

@@ -432,13 +432,17 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs p, const __grid_constant__ C
             }
           }
           uint4 o;
-          o.x = E::from_f2(y[0], y[1]);
-          o.y = E::from_f2(y[2], y[3]);
-          o.z = E::from_f2(y[4], y[5]);
-          o.w = E::from_f2(y[6], y[7]);
           if constexpr (kAct == 1) {
-            // ReLU on the packed 16-bit pairs: rounding is monotonic and keeps the sign, so this is max(x, 0) rounded
-            o.x = E::relu2(o.x); o.y = E::relu2(o.y); o.z = E::relu2(o.z); o.w = E::relu2(o.w);
+            // ReLU inside the conversion (cvt.rn.relu): rounding is monotonic and keeps the sign, so this is max(x, 0) rounded
+            o.x = E::from_f2_relu(y[0], y[1]);
+            o.y = E::from_f2_relu(y[2], y[3]);
+            o.z = E::from_f2_relu(y[4], y[5]);
+            o.w = E::from_f2_relu(y[6], y[7]);
+          } else {
+            o.x = E::from_f2(y[0], y[1]);
+            o.y = E::from_f2(y[2], y[3]);
+            o.z = E::from_f2(y[4], y[5]);
+            o.w = E::from_f2(y[6], y[7]);
           }
           *reinterpret_cast<uint4*>(dst) = o;
         }
