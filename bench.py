@@ -17,10 +17,12 @@ The default line also carries a `distance` object: configs[3] (50k x 512 pdist, 
 all_gather of the embeddings) and configs[4] (50k queries x 1M actor embeddings, fused top-10, queries sharded), each with its own
 device-timed rate, end-to-end rate and roofline, so that the driver's 1/2/4/8-GPU runs exercise the path's only collective.
 
-`value`  : frames/s with the batch already resident in HBM when the timed region starts.
-`e2e`    : the same from pinned HOST frames: every step copies its own 64 frames host -> device (a copy stream prefetches
-           step k+1 under step k, as the extractor does) into FacePipeline.step_device and reads detections + embeddings
-           back (D2H) inside the timed region.
+`value`  : frames/s with the batch already resident in HBM when the timed region starts, K steps through
+           FacePipeline.run_pipelined (two batches in flight, the schedule of facerec_b200.extract: detection of step k+1 is
+           enqueued before the host collects step k; every step's results are complete inside the timed region).
+           `ms_per_step_sequential` is the same K steps one at a time (FacePipeline.step_device).
+`e2e`    : the same from pinned HOST frames: every step copies its own 64 frames host -> device (a copy stream runs ahead,
+           as the extractor's prefetch does) and reads its detections + embeddings back (D2H) inside the timed region.
 `roofline`: the RetinaFace-R50 forward (64 launches: conv_tma_kernel, 3 + 3 fused conv_tail / conv_tail2 kernels, one zero fill), timed with
            CUDA events on the launching stream inside the timed region; algorithmic work
            449.71 GFLOP/frame x 64 frames per launch of the forward.  `traffic` is not measured by this
@@ -548,13 +550,24 @@ def run_b200(a):
     l0 = ctx.launch_count()
     t0 = time.time()
     ev[0].record(stream)
-    for _ in range(a.steps):
-        pipe.step_device(frames_d, first)
+    # two batches in flight (FacePipeline.run_pipelined, the schedule of facerec_b200.extract): detection of step k+1 is
+    # enqueued before the host collects step k, so the GPU does not idle while the host picks the faces to embed.  Every
+    # step's detection, crop, embedding and both result copies complete inside the timed region (the generator drains).
+    for _ in pipe.run_pipelined((frames_d, first) for _ in range(a.steps)):
+        pass
     ev[1].record(stream)
     barrier()
     t1 = time.time()
     launches = ctx.launch_count() - l0
     ms_total = ev[0].elapsed_time(ev[1])
+    # the same K steps one after the other (step_device: each step waits for its own results before the next starts)
+    es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    es[0].record(stream)
+    for _ in range(a.steps):
+        pipe.step_device(frames_d, first)
+    es[1].record(stream)
+    torch.cuda.synchronize()
+    ms_sequential = es[0].elapsed_time(es[1]) / a.steps
 
     # ---- RetinaFace forward alone, CUDA events on the launching stream (roofline) ---------
     from facerec_b200 import ops
@@ -576,27 +589,38 @@ def run_b200(a):
     # Every step copies ITS OWN 64 frames host->device (pinned memory, a second stream so the copy of step k+1
     # overlaps the compute of step k, as the extractor's prefetch does) and reads detections + embeddings back.
     copy_stream = torch.cuda.Stream()
-    dbuf = [torch.empty_like(frames_d) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
+    NB = 4                                   # device buffers: two batches in flight on the GPU + the copy running ahead
+    dbuf = [torch.empty_like(frames_d) for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    released = [None] * NB                   # event after the last GPU work that reads buffer i
 
     def h2d(k):
         with torch.cuda.stream(copy_stream):
-            dbuf[k % 2].copy_(pinned, non_blocking=True)
-            ready[k % 2].record(copy_stream)
+            if released[k % NB] is not None:
+                copy_stream.wait_event(released[k % NB])
+            dbuf[k % NB].copy_(pinned, non_blocking=True)
+            ready[k % NB].record(copy_stream)
 
-    for k in range(2):
-        h2d(k)
-        stream.wait_event(ready[k % 2])
-        pipe.step_device(dbuf[k % 2], first)
+    def host_batches(n):
+        h2d(0)
+        for k in range(n):
+            if k + 1 < n:
+                h2d(k + 1)
+            stream.wait_event(ready[k % NB])
+            yield dbuf[k % NB], first
+
+    def run_e2e(n):
+        k = 0
+        for r in pipe.run_pipelined(host_batches(n)):     # r: detections + embeddings of batch k on the host
+            released[k % NB] = torch.cuda.Event()
+            released[k % NB].record(stream)
+            k += 1
+
+    run_e2e(2)
     ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     ev2[0].record(stream)
-    h2d(0)
-    for k in range(a.steps):
-        if k + 1 < a.steps:
-            h2d(k + 1)                       # buffer (k+1)%2 was released when step k-1 synchronised
-        stream.wait_event(ready[k % 2])
-        r = pipe.step_device(dbuf[k % 2], first)
+    run_e2e(a.steps)
     ev2[1].record(stream)
     barrier()
     t2 = time.time()
@@ -638,7 +662,9 @@ def run_b200(a):
             "faces_per_step_per_gpu": faces_per_step, "detections_per_step_per_gpu": dets_per_step,
             "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
-                    "api": "FacePipeline.step_device on frames copied from pinned host memory every step (copy stream prefetch of step k+1 under step k) + D2H of detections and embeddings"},
+                    "api": "FacePipeline.run_pipelined (two batches in flight, as facerec_b200.extract runs) on frames copied from pinned host "
+                           "memory every step (copy stream running ahead) + D2H of every step's detections and embeddings"},
+            "ms_per_step_sequential": ms_sequential,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peak, "unit": "TFLOP/s",

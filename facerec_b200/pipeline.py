@@ -76,6 +76,7 @@ class FacePipeline:
         self.embedder = B200FaceNet(weights=emb_weights, seed=seed, ctx=self.ctx)
         self.save_every = int(save_every)
         self.max_out = int(max_faces_per_frame)
+        self.detector.keep_top_k = self.max_out          # the launch / collect halves of the detector use its own cap
         self.min_size = min_face_size
         self._pin_in = None
         self._pin_det = None
@@ -135,6 +136,50 @@ class FacePipeline:
         else:
             emb_h = np.zeros((0, 512), np.float32)
         return BatchResult(dets, ff, fd, rects, emb_h)
+
+    # ---- the same step in two halves, so that two batches can be in flight (what facerec_b200.extract does) -----------
+    def step_launch(self, frames_u8: torch.Tensor, first_index: int = 0):
+        """First half of a step over a GPU-resident batch: enqueue detection and the copy of the kept detections to pinned
+        host memory.  Nothing here waits for the GPU."""
+        return self.detector.detect_batch_launch(frames_u8), frames_u8, first_index
+
+    def step_embed(self, handle):
+        """Second half: wait for THIS batch's detections only, pick the faces on the host, enqueue crop + embed and the copy
+        of the embeddings.  Work enqueued after step_launch(next batch) runs behind it, so the GPU stays busy while the host
+        is in here."""
+        dh, frames_u8, first_index = handle
+        _, H, W, _ = frames_u8.shape
+        dets = []
+        for d in self.detector.detect_batch_collect(dh):
+            if self.min_size > 0 and len(d):
+                d = d[np.minimum(d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]) >= self.min_size]
+            dets.append(d)
+        ff, fd, rects = self.select_faces(dets, first_index, W, H)
+        eh = self.embedder.embed_boxes_launch(frames_u8, rects, checked=True) if len(rects) else None
+        return dets, ff, fd, rects, eh
+
+    def step_collect(self, handle) -> BatchResult:
+        dets, ff, fd, rects, eh = handle
+        emb = self.embedder.embed_collect(eh).copy() if eh is not None else np.zeros((0, 512), np.float32)
+        return BatchResult(dets, ff, fd, rects, emb)
+
+    def run_pipelined(self, batches):
+        """batches: iterable of (frames_u8 on the GPU, first_index).  Yields one BatchResult per batch, in order, equal to
+        step_device's, with two batches in flight: detection of batch k+1 is enqueued before the host collects batch k."""
+        prev = pend = None
+        for frames_u8, first_index in batches:
+            h = self.step_launch(frames_u8, first_index)
+            if prev is not None:
+                h2 = self.step_embed(prev)
+                if pend is not None:
+                    yield self.step_collect(pend)
+                pend = h2
+            prev = h
+        if prev is not None:
+            h2 = self.step_embed(prev)
+            if pend is not None:
+                yield self.step_collect(pend)
+            yield self.step_collect(h2)
 
     def to_device(self, frames: np.ndarray) -> torch.Tensor:
         if self._pin_in is None or tuple(self._pin_in.shape) != tuple(frames.shape):

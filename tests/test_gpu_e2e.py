@@ -144,3 +144,22 @@ def test_cluster_and_classify_on_gpu_reproduce_reference_outputs(ctx, tmp_path):
         classify_knn.classify(d, X, y, 10)
     assert open(os.path.join(d, "clusters.json")).read() == film["clusters_json"]
     assert open(os.path.join(d, "predictions.json")).read() == film["predictions_json"]
+
+
+def test_pipelined_steps_equal_sequential_steps(ctx):
+    """FacePipeline.run_pipelined (two batches in flight: detection of batch k+1 enqueued before the host collects batch k,
+    the schedule of facerec_b200.extract and of bench.py) returns, batch by batch, exactly what step_device returns."""
+    import torch
+    from facerec_b200 import synth
+    from facerec_b200.pipeline import FacePipeline
+    pipe = FacePipeline("mnet025", min_face_size=20, save_every=2, ctx=ctx)
+    H, W, B = 360, 640, 6
+    batches = [(torch.from_numpy(synth.clip(77, k * B, B, H, W)).cuda(), k * B) for k in range(5)]
+    seq = [pipe.step_device(fr, first) for fr, first in batches]
+    par = list(pipe.run_pipelined(batches))
+    assert len(par) == len(seq) and sum(len(r.rects) for r in seq) > 0
+    for a, b in zip(seq, par):
+        assert len(a.dets) == len(b.dets) and all(np.array_equal(x, y) for x, y in zip(a.dets, b.dets))
+        assert np.array_equal(a.face_frame, b.face_frame) and np.array_equal(a.face_det, b.face_det)
+        assert np.array_equal(a.rects, b.rects) and np.array_equal(a.embeddings, b.embeddings)
+    assert list(pipe.run_pipelined([])) == [] and len(list(pipe.run_pipelined(batches[:1]))) == 1
