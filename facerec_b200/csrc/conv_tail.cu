@@ -1,4 +1,4 @@
-// K2t — the tail of a ResNet bottleneck fused with the head of the next one (layer1 of RetinaFace-R50):
+// K2t — the tail of a ResNet bottleneck fused with the head of the next one (layer1 of RetinaFace-R50; layer2: K2t2 below):
 //
 //   y  = relu(conv3_1x1(a) + skip)          [M, 256]   (what conv_tma_kernel<res = 1, act = 1> writes)
 //   y1 = relu(conv1_1x1_next(y))            [M, N2]    (what the next block's conv_tma_kernel<0, 1> writes)
@@ -8,20 +8,23 @@
 // y again: the staged output slabs of y — which the epilogue packs into the 128-byte-swizzled K-major layout for their TMA
 // store anyway — are at the same time the A operand of the second GEMM.  Per 128-pixel tile:
 //
-//   producer   A block(s) of a and the four 64-channel skip slabs -> stage ring (16 KB boxes)
-//   issuer     G1: acc1[buf] (256 TMEM columns)  = a x W3   (N = 256 MMAs), then += skip slab x I (N = 64 MMAs on the slab's
-//                  columns: the skip is added by the tensor core exactly as in conv_tma_kernel, same order, same bits)
-//   epilogue   e1: per 64-column slab: TMEM -> +bias -> 16-bit -> ReLU -> slab slot (swizzled) -> TMA store into y,
-//                  and "slab written" to the issuer
-//   issuer     M2: acc2 (columns [0, N2) of the SAME buffer, drained by then) (+)= slab x W1n block, slabs in channel
-//                  order (the accumulation order of the unfused conv1: its output bits do not change either)
-//   epilogue   e2: TMEM -> +bias2 -> 16-bit -> ReLU -> slab slot -> TMA store into y1; buffer back to the issuer
-//   store warp sends the staged slabs (e1 and e2, in order) and hands a slot back once its store has drained
+//   producer    A block(s) of a and the four 64-channel skip slabs -> stage ring (16 KB boxes)
+//   G1 issuer   acc1[buf] (256 TMEM columns)  = a x W3   (N = 256 MMAs), then += skip slab x I (N = 64 MMAs on the slab's
+//               columns: the skip is added by the tensor core exactly as in conv_tma_kernel, same order, same bits); with
+//               FRB_OPT_FUSE_TAIL = 3 and a 1x1 skip conv (layer1.0) instead += x x Wd: the skip conv as one more k-block
+//   epilogue    e1: per 64-column slab: TMEM -> +bias -> 16-bit with ReLU -> slab slot (swizzled), "slab written" to the M2
+//               issuer, "slab staged" to the store warp
+//   M2 issuer   acc2 (columns [0, N2) of the SAME buffer, drained by then) (+)= slab x W1n block, slabs in channel
+//               order (the accumulation order of the unfused conv1: its output bits do not change either)
+//   epilogue    e2: TMEM -> +bias2 -> 16-bit with ReLU -> slab slot; buffer back to the G1 issuer
+//   store warp  TMA-stores the staged slabs (e1 into y, e2 into y1, in item order) and hands a slot back once its store has
+//               drained, one store behind
 //
-// Weights of both layers and the identity stay resident in shared memory.  Epilogue items (4 e1 slabs + N2/64 e2 slabs per
-// tile) are dealt round-robin to three independent 4-warp groups that take the slab slots in item order; a slot is reused when its TMA
-// store has finished reading it and (e1) the M2 MMAs on it have retired.  The issuer runs G1 one tile ahead of M2, so the epilogue of tile t
-// overlaps G1 of tile t + 1; every wait in here depends only on earlier items, so the pipeline cannot deadlock
+// Weights of both layers and the identity (or the skip conv's weights) stay resident in shared memory.  Epilogue items (4 e1
+// slabs + N2/64 e2 slabs per tile) are dealt round-robin to three independent 4-warp groups that take the slab slots in item
+// order; a slot is reused when its TMA store has finished reading it and (e1) the M2 MMAs on it have retired.  G1 runs
+// ahead of M2 by up to a tile (two TMEM buffers), so the epilogue of tile t overlaps G1 of tile t + 1; what orders the two
+// issuers' MMAs on a buffer are barriers, and every wait depends only on earlier items, so the pipeline cannot deadlock
 // (tools/conv_tail_protocol_sim.py replays the barrier protocol under random interleavings and checks every parity wait).
 // Linear M tiling (1x1, stride 1, no padding); ragged last tile: loads zero-fill, stores clip.
 #include <algorithm>
